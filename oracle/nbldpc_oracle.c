@@ -1,0 +1,495 @@
+/* TEST INFRASTRUCTURE ONLY -- see nbldpc_oracle.h.
+ *
+ * Plain-C restatement of the reference decode path.  Every routine names the reference lines it
+ * follows (/root/reference/...).  The order of floating-point operations is kept (including the
+ * reference's add-then-subtract "undo" in its recursive configuration searches and the x87
+ * long double accumulators of the QSPA box-plus), so results match the compiled reference
+ * bit for bit on the same machine.  Compile with -ffp-contract=off and without -ffast-math.
+ */
+#include "nbldpc_oracle.h"
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct orc_code {
+    int q, p, N, M, maxdv, maxdc;
+    int *mul, *inv;
+    int *vdeg, *cdeg;
+    int *vlink, *vcoef, *vdc; /* [N][maxdv] */
+    int *clink, *ccoef, *cdv; /* [M][maxdc] */
+};
+
+static double g_tems_leaves;
+double orc_last_tems_leaves(void) { return g_tems_leaves; }
+
+/* ---------------------------------------------------------------- GF(q) (GF.cpp:27-47) */
+void orc_gf_tables(int q, int poly, int *mul, int *inv) {
+    for (int a = 0; a < q; ++a)
+        for (int b = 0; b < q; ++b) {
+            int r = 0, x = a;
+            for (int y = b; y; y >>= 1) {
+                if (y & 1) r ^= x;
+                x <<= 1;
+                if (x & q) x ^= poly;
+            }
+            mul[a * q + b] = r;
+        }
+    inv[0] = 0;
+    for (int a = 1; a < q; ++a)
+        for (int b = 1; b < q; ++b)
+            if (mul[a * q + b] == 1) inv[a] = b;
+}
+#define MUL(c, a, b) ((c)->mul[(a) * (c)->q + (b)])
+#define INV(c, a) ((c)->inv[(a)])
+
+/* ------------------------------------------------- graph (NBLDPC.cpp:147-263) */
+orc_code *orc_code_create(int q, int poly, int N, int M, const int *var_deg, const int *chk_deg,
+                          const int *var_link, const int *var_coef, int var_stride,
+                          const int *chk_link, const int *chk_coef, int chk_stride) {
+    orc_code *c = calloc(1, sizeof *c);
+    c->q = q; c->N = N; c->M = M;
+    for (c->p = 0; (1 << c->p) < q; ++c->p) ;
+    c->mul = malloc(sizeof(int) * q * q);
+    c->inv = malloc(sizeof(int) * q);
+    orc_gf_tables(q, poly, c->mul, c->inv);
+    for (int i = 0; i < N; ++i) if (var_deg[i] > c->maxdv) c->maxdv = var_deg[i];
+    for (int i = 0; i < M; ++i) if (chk_deg[i] > c->maxdc) c->maxdc = chk_deg[i];
+    c->vdeg = malloc(sizeof(int) * N); memcpy(c->vdeg, var_deg, sizeof(int) * N);
+    c->cdeg = malloc(sizeof(int) * M); memcpy(c->cdeg, chk_deg, sizeof(int) * M);
+    c->vlink = calloc(N * c->maxdv, sizeof(int)); c->vcoef = calloc(N * c->maxdv, sizeof(int));
+    c->vdc = calloc(N * c->maxdv, sizeof(int));
+    c->clink = calloc(M * c->maxdc, sizeof(int)); c->ccoef = calloc(M * c->maxdc, sizeof(int));
+    c->cdv = calloc(M * c->maxdc, sizeof(int));
+    for (int i = 0; i < N; ++i)
+        for (int d = 0; d < var_deg[i]; ++d) {
+            c->vlink[i * c->maxdv + d] = var_link[i * var_stride + d];
+            c->vcoef[i * c->maxdv + d] = var_coef[i * var_stride + d];
+        }
+    for (int r = 0; r < M; ++r)
+        for (int d = 0; d < chk_deg[r]; ++d) {
+            c->clink[r * c->maxdc + d] = chk_link[r * chk_stride + d];
+            c->ccoef[r * c->maxdc + d] = chk_coef[r * chk_stride + d];
+        }
+    /* cross indices: last match wins, as in the reference loops (NBLDPC.cpp:236-263) */
+    for (int i = 0; i < N; ++i)
+        for (int dv = 0; dv < c->vdeg[i]; ++dv) {
+            int r = c->vlink[i * c->maxdv + dv];
+            for (int dc = 0; dc < c->cdeg[r]; ++dc)
+                if (c->clink[r * c->maxdc + dc] == i) c->vdc[i * c->maxdv + dv] = dc;
+        }
+    for (int r = 0; r < M; ++r)
+        for (int dc = 0; dc < c->cdeg[r]; ++dc) {
+            int i = c->clink[r * c->maxdc + dc];
+            for (int dv = 0; dv < c->vdeg[i]; ++dv)
+                if (c->vlink[i * c->maxdv + dv] == r) c->cdv[r * c->maxdc + dc] = dv;
+        }
+    return c;
+}
+
+void orc_code_destroy(orc_code *c) {
+    if (!c) return;
+    free(c->mul); free(c->inv); free(c->vdeg); free(c->cdeg);
+    free(c->vlink); free(c->vcoef); free(c->vdc); free(c->clink); free(c->ccoef); free(c->cdv);
+    free(c);
+}
+
+/* ------------------------------------------------- soft demapper (Comm.cpp:340-407) */
+static int is_punct(const int *ps, int n, int s) {
+    for (int i = 0; i < n; ++i) if (ps[i] == s) return 1;
+    return 0;
+}
+
+void orc_demap_bpsk(int q, int N, const double *y_re, double sigma, const int *punct_sym, int n_punct, double *L_ch) {
+    int p = 0; while ((1 << p) < q) ++p;
+    double *lb = malloc(sizeof(double) * N * p);
+    int pi = 0; /* y_re holds only the transmitted (un-punctured) bits, Comm.cpp:346-358 */
+    for (int b = 0; b < N * p; ++b) {
+        if (is_punct(punct_sym, n_punct, b / p)) { ++pi; lb[b] = 0; }
+        else lb[b] = -2 * y_re[b - pi] / (sigma * sigma);
+    }
+    for (int s = 0; s < N; ++s)          /* Comm.cpp:360-373: bits added in ascending bit order */
+        for (int k = 1; k < q; ++k) {
+            double a = 0;
+            for (int b = 0; b < p; ++b) if (k & (1 << b)) a += lb[s * p + b];
+            L_ch[s * (q - 1) + k - 1] = a;
+        }
+    free(lb);
+}
+
+void orc_demap_qam(int q, int N, const double *y, const double *cs, double sigma,
+                   const int *punct_sym, int n_punct, double *L_ch) {
+    int pi = 0;
+    for (int s = 0; s < N; ++s) {        /* Comm.cpp:378-398 */
+        if (is_punct(punct_sym, n_punct, s)) {
+            ++pi;
+            for (int k = 1; k < q; ++k) L_ch[s * (q - 1) + k - 1] = 0;
+        } else {
+            double yr = y[2 * (s - pi)], yi = y[2 * (s - pi) + 1];
+            for (int k = 1; k < q; ++k)
+                L_ch[s * (q - 1) + k - 1] =
+                    ((2 * yr - cs[0] - cs[2 * k]) * (cs[2 * k] - cs[0]) +
+                     (2 * yi - cs[1] - cs[2 * k + 1]) * (cs[2 * k + 1] - cs[1])) / (2 * sigma * sigma);
+        }
+    }
+}
+
+/* ------------------------------------------------- shared helpers */
+/* DecideLLRVector, NBLDPC.cpp:1542-1562: strict '>' scan from 0 => ties go to the lowest symbol */
+static int decide(const double *L, int q) {
+    double mx = 0; int a = 0;
+    for (int k = 0; k < q - 1; ++k) if (L[k] > mx) { mx = L[k]; a = k + 1; }
+    return mx <= 0 ? 0 : a;
+}
+
+typedef struct {
+    const orc_code *c;
+    double *v2c;  /* [N][maxdv][q-1] */
+    double *c2v;  /* [M][maxdc][q-1] */
+    double *tmp;  /* [q-1] */
+} state;
+
+#define V2C(s, col, d) ((s)->v2c + ((size_t)((col) * (s)->c->maxdv + (d))) * ((s)->c->q - 1))
+#define C2V(s, row, d) ((s)->c2v + ((size_t)((row) * (s)->c->maxdc + (d))) * ((s)->c->q - 1))
+
+/* steps A,B of every Decoding_* (NBLDPC.cpp:676-715 / 808-846 / 977-1026) */
+static int posterior_and_syndrome(state *s, const double *L_ch, double *L_post, int *out) {
+    const orc_code *c = s->c; int q1 = c->q - 1;
+    for (int col = 0; col < c->N; ++col) {
+        double *P = L_post + (size_t)col * q1;
+        memcpy(P, L_ch + (size_t)col * q1, sizeof(double) * q1);
+        for (int d = 0; d < c->vdeg[col]; ++d) {
+            const double *m = C2V(s, c->vlink[col * c->maxdv + d], c->vdc[col * c->maxdv + d]);
+            for (int k = 0; k < q1; ++k) P[k] = P[k] + m[k];
+        }
+        out[col] = decide(P, c->q);
+    }
+    for (int row = 0; row < c->M; ++row) {
+        int syn = 0;
+        for (int d = 0; d < c->cdeg[row]; ++d)
+            syn ^= MUL(c, c->ccoef[row * c->maxdc + d], out[c->clink[row * c->maxdc + d]]);
+        if (syn) return 0;
+    }
+    return 1;
+}
+
+/* step C (NBLDPC.cpp:718-744 / 848-857 / 1029-1052); w_old = 0 means "no damping" (EMS) */
+static void var_to_check(state *s, const double *L_post, double w_old, double w_new) {
+    const orc_code *c = s->c; int q1 = c->q - 1;
+    for (int col = 0; col < c->N; ++col)
+        for (int dv = 0; dv < c->vdeg[col]; ++dv) {
+            double *v = V2C(s, col, dv);
+            const double *m = C2V(s, c->vlink[col * c->maxdv + dv], c->vdc[col * c->maxdv + dv]);
+            const double *P = L_post + (size_t)col * q1;
+            int before = decide(v, c->q);
+            memcpy(s->tmp, v, sizeof(double) * q1);
+            for (int k = 0; k < q1; ++k) v[k] = P[k] - m[k];
+            if (w_old != 0 && decide(v, c->q) != before)
+                for (int k = 0; k < q1; ++k) v[k] = w_old * s->tmp[k] + w_new * v[k];
+        }
+}
+
+static double soft_threshold(double x, double factor, double offset) {
+    x = x / factor;                       /* NBLDPC.cpp:903-915, 1114-1126 */
+    if (x < -1 * offset) return x + offset;
+    if (x > offset) return x - offset;
+    return 0;
+}
+
+/* ------------------------------------------------- QSPA check node (NBLDPC.cpp:1565-1712) */
+typedef struct { state *s; double *sigma, *rho, *llrv; } bp_ctx;
+
+static void box_plus(bp_ctx *b, double *L, const double *L1, const double *L2, int A1, int A2) {
+    const orc_code *c = b->s->c; int q = c->q;
+    double *out = b->llrv;
+    if (A1 == 0) {
+        for (int a = 1; a < q; ++a) out[a - 1] = L2[MUL(c, INV(c, A2), a) - 1];
+    } else if (A2 == 0) {
+        for (int a = 1; a < q; ++a) out[a - 1] = L1[MUL(c, INV(c, A1), a) - 1];
+    } else {
+        long double den = 0;              /* NBLDPC.cpp:1645: x87 extended accumulators */
+        for (int x = 0; x < q; ++x) {
+            int v1 = x, v2 = MUL(c, INV(c, A2), MUL(c, A1, x));
+            if (v1 != 0 && v2 != 0) {
+                double t = L1[v1 - 1] + L2[v2 - 1];
+                if (den > t) den = den + logl(1 + expl(-1 * (den - t)));
+                else den = t + logl(1 + expl(-1 * (t - den)));
+            }
+        }
+        for (int a = 1; a < q; ++a) {
+            long double num;
+            int v1 = MUL(c, INV(c, A1), a), v2 = MUL(c, INV(c, A2), a);
+            if (L1[v1 - 1] > L2[v2 - 1]) num = L1[v1 - 1] + log(1 + exp(-1 * (L1[v1 - 1] - L2[v2 - 1])));
+            else num = L2[v2 - 1] + log(1 + exp(-1 * (L2[v2 - 1] - L1[v1 - 1])));
+            for (int x = 0; x < q; ++x) {
+                v1 = x; v2 = MUL(c, INV(c, A2), a ^ MUL(c, x, A1));
+                if (v1 != 0 && v2 != 0) {
+                    double t = L1[v1 - 1] + L2[v2 - 1];
+                    if (num > t) num = num + logl(1 + expl(-1 * (num - t)));
+                    else num = t + logl(1 + expl(-1 * (t - num)));
+                }
+            }
+            out[a - 1] = (double)(num - den);
+        }
+    }
+    memcpy(L, out, sizeof(double) * (q - 1));
+}
+
+static void chain_back(bp_ctx *b, int row, int l) {       /* L_Back, NBLDPC.cpp:1565-1591 */
+    const orc_code *c = b->s->c;
+    if (l < 0) return;
+    if (l > 0) chain_back(b, row, l - 1);
+    box_plus(b, b->sigma, b->sigma, V2C(b->s, c->clink[row * c->maxdc + l], c->cdv[row * c->maxdc + l]),
+             l == 0 ? 0 : 1, c->ccoef[row * c->maxdc + l]);
+}
+static void chain_forward(bp_ctx *b, int row, int l) {    /* L_Forward, NBLDPC.cpp:1593-1619 */
+    const orc_code *c = b->s->c;
+    if (l >= c->cdeg[row]) return;
+    if (l < c->cdeg[row] - 1) chain_forward(b, row, l + 1);
+    box_plus(b, b->rho, b->rho, V2C(b->s, c->clink[row * c->maxdc + l], c->cdv[row * c->maxdc + l]),
+             l == c->cdeg[row] - 1 ? 0 : 1, c->ccoef[row * c->maxdc + l]);
+}
+
+static void cn_qspa(state *s, bp_ctx *b) {                /* NBLDPC.cpp:747-767 */
+    const orc_code *c = s->c; int q1 = c->q - 1;
+    for (int row = 0; row < c->M; ++row)
+        for (int d = 0; d < c->cdeg[row]; ++d) {
+            memset(b->sigma, 0, sizeof(double) * q1);
+            memset(b->rho, 0, sizeof(double) * q1);
+            chain_back(b, row, d - 1);
+            chain_forward(b, row, d + 1);
+            int A1 = INV(c, c->ccoef[row * c->maxdc + d]), A2 = A1;
+            if (d == 0) A1 = 0; else if (d == c->cdeg[row] - 1) A2 = 0;
+            box_plus(b, C2V(s, row, d), b->sigma, b->rho, A1, A2);
+        }
+}
+
+/* ------------------------------------------------- EMS check node (NBLDPC.cpp:859-918, 1715-1786) */
+typedef struct {
+    state *s; int row, nm, nc, except, end;
+    double **srt; int **sym; double *best;
+    int sum_sym, diff; double sum_llr;
+} ems_ctx;
+
+/* SortLLRVector: insertion from the tail, '>=' moves the newcomer ahead of equals */
+static void ems_sort(double *Ls, int *Es, const double *L, int q1) {
+    Ls[0] = 0; Es[0] = 0;
+    for (int n = 0; n < q1; ++n) {
+        double cand = L[n];
+        Ls[n + 1] = cand; Es[n + 1] = n + 1;
+        for (int i = n; i >= 0; --i) {
+            if (cand >= Ls[i]) { Ls[i + 1] = Ls[i]; Ls[i] = cand; Es[i + 1] = Es[i]; Es[i] = n + 1; }
+            else break;
+        }
+    }
+}
+
+/* ConstructConf: depth-first over the inputs, running sums updated and then undone in place */
+static void ems_conf(ems_ctx *e, int lim, int begin) {
+    const orc_code *c = e->s->c;
+    if (begin > e->end) {
+        if (e->sum_llr > e->best[e->sum_sym]) e->best[e->sum_sym] = e->sum_llr;
+        return;
+    }
+    if (begin == e->except) { ems_conf(e, lim, begin + 1); return; }
+    int h = c->ccoef[e->row * c->maxdc + begin];
+    for (int k = 0; k < lim; ++k) {
+        int g = MUL(c, e->sym[begin][k], h);
+        e->sum_sym ^= g;
+        e->sum_llr = e->sum_llr + e->srt[begin][k];
+        e->diff += (k != 0);
+        int go = e->diff <= e->nc;
+        if (go) ems_conf(e, lim, begin + 1);
+        e->sum_sym ^= g;
+        e->sum_llr = e->sum_llr - e->srt[begin][k];
+        e->diff -= (k != 0);
+        if (!go) break;
+    }
+}
+
+static void cn_ems(state *s, ems_ctx *e, double factor, double offset) {
+    const orc_code *c = s->c; int q = c->q;
+    for (int row = 0; row < c->M; ++row) {
+        int dcn = c->cdeg[row];
+        for (int d = 0; d < dcn; ++d)
+            ems_sort(e->srt[d], e->sym[d], V2C(s, c->clink[row * c->maxdc + d], c->cdv[row * c->maxdc + d]), q - 1);
+        for (int d = 0; d < dcn; ++d) {
+            for (int k = 0; k < q; ++k) e->best[k] = -DBL_MAX;
+            e->row = row; e->except = d; e->end = dcn - 1;
+            int keep_nc = e->nc;
+            e->sum_sym = 0; e->sum_llr = 0; e->diff = 0; e->nc = 1;
+            ems_conf(e, q, 0);                                   /* conf(q,1)   NBLDPC.cpp:893-894 */
+            e->sum_sym = 0; e->sum_llr = 0; e->diff = 0; e->nc = keep_nc;
+            ems_conf(e, e->nm, 0);                               /* conf(nm,nc) NBLDPC.cpp:896-897 */
+            double *o = C2V(s, row, d);
+            int h = c->ccoef[row * c->maxdc + d];
+            for (int k = 1; k < q; ++k)
+                o[k - 1] = soft_threshold(e->best[MUL(c, k, h)] - e->best[0], factor, offset);
+        }
+    }
+}
+
+/* ------------------------------------------------- T-EMS check node (NBLDPC.cpp:1055-1130, 1789-1944) */
+typedef struct {
+    state *s; int nr, nc, end;
+    double **dU; int *beta; int syn;
+    int **ord; unsigned char **allowed;   /* TEMS_Min, TEMS_inConf_Nr: [q][dc] */
+    double *dW; int **eta; int *cand; unsigned char *used;
+    double *T; unsigned char *hit;
+    int sum_sym, diff; double sum;
+} tems_ctx;
+
+static void tems_conf(tems_ctx *t, int begin) {            /* TEMS_ConstructConf, NBLDPC.cpp:1892-1944 */
+    int q = t->s->c->q;
+    if (begin > t->end) {
+        g_tems_leaves += 1;
+        if (t->sum < t->dW[t->sum_sym]) {
+            t->dW[t->sum_sym] = t->sum;
+            for (int d = 0; d <= t->end; ++d) t->eta[t->sum_sym][d] = t->cand[d];
+        }
+        return;
+    }
+    for (int e = 0; e < q; ++e) {
+        if (!t->allowed[e][begin] || t->used[e]) continue;
+        t->diff += (e != 0);
+        if (t->diff <= t->nc) {
+            t->used[e] = (e != 0);
+            t->sum_sym ^= e;
+            t->sum += t->dU[begin][e];
+            t->cand[begin] = e;
+            tems_conf(t, begin + 1);
+            t->sum_sym ^= e;
+            t->sum -= t->dU[begin][e];
+            t->used[e] = 0;
+            t->diff -= (e != 0);
+        } else {
+            t->diff -= (e != 0);
+            break;
+        }
+    }
+}
+
+static void cn_tems(state *s, tems_ctx *t, double factor, double offset) {
+    const orc_code *c = s->c; int q = c->q;
+    for (int row = 0; row < c->M; ++row) {
+        int dcn = c->cdeg[row];
+        /* TEMS_Get_Beta (1789-1812) */
+        t->syn = 0;
+        for (int d = 0; d < dcn; ++d) {
+            const double *v = V2C(s, c->clink[row * c->maxdc + d], c->cdv[row * c->maxdc + d]);
+            int h = c->ccoef[row * c->maxdc + d];
+            double mx = 0; int me = 0;
+            for (int k = 1; k < q; ++k) if (v[k - 1] > mx) { mx = v[k - 1]; me = MUL(c, k, h); }
+            t->beta[d] = me; t->syn ^= me;
+        }
+        /* TEMS_Get_deltaU (1814-1834) */
+        for (int d = 0; d < dcn; ++d) {
+            const double *v = V2C(s, c->clink[row * c->maxdc + d], c->cdv[row * c->maxdc + d]);
+            int hi = INV(c, c->ccoef[row * c->maxdc + d]);
+            int bp = MUL(c, hi, t->beta[d]);
+            double mx = bp == 0 ? 0 : v[bp - 1];
+            t->dU[d][t->beta[d]] = mx - 0;
+            for (int x = 1; x < q; ++x) t->dU[d][x ^ t->beta[d]] = mx - v[MUL(c, hi, x) - 1];
+        }
+        /* TEMS_Get_Min (1836-1890): per eta, stable insertion order of the columns by dU */
+        for (int e = 0; e < q; ++e) {
+            for (int d = 0; d < dcn; ++d) t->ord[e][d] = d;
+            for (int d = 1; d < dcn; ++d)
+                for (int k = d; k >= 1; --k) {
+                    if (t->dU[t->ord[e][k]][e] < t->dU[t->ord[e][k - 1]][e]) {
+                        int tmp = t->ord[e][k]; t->ord[e][k] = t->ord[e][k - 1]; t->ord[e][k - 1] = tmp;
+                    } else break;
+                }
+        }
+        for (int d = 0; d < dcn; ++d) t->allowed[0][d] = 1;
+        for (int e = 1; e < q; ++e) {
+            for (int d = 0; d < dcn; ++d) t->allowed[e][d] = 0;
+            for (int i = 0; i < t->nr && i < dcn; ++i) t->allowed[e][t->ord[e][i]] = 1;
+        }
+        /* configuration search (1064-1072) */
+        for (int e = 0; e < q; ++e) { t->dW[e] = DBL_MAX; t->used[e] = 0; }
+        t->sum_sym = 0; t->diff = 0; t->sum = 0.0; t->end = dcn - 1;
+        tems_conf(t, 0);
+        /* outputs (1075-1129) */
+        for (int d = 0; d < dcn; ++d) {
+            for (int e = 0; e < q; ++e) { t->T[e] = DBL_MAX; t->hit[e] = 0; }
+            for (int e = 0; e < q; ++e) {
+                int dev = t->eta[e][d], tgt = e ^ dev;
+                double m = t->dW[e] - t->dU[d][dev];
+                if (t->T[tgt] > m) { t->T[tgt] = m; t->hit[tgt] = 1; }
+            }
+            for (int e = 0; e < q; ++e)
+                if (!t->hit[e]) t->T[e] = (d == t->ord[e][0]) ? t->dU[t->ord[e][1]][e] : t->dU[t->ord[e][0]][e];
+            int hi = INV(c, c->ccoef[row * c->maxdc + d]);
+            int bs = t->syn ^ t->beta[d];
+            double L0 = -1.0 * t->T[bs];
+            double *o = C2V(s, row, d);
+            for (int e = 0; e < q; ++e)
+                if (e != bs) {
+                    int k = MUL(c, hi, e ^ bs);
+                    o[k - 1] = soft_threshold(-1.0 * t->T[e] - L0, factor, offset);
+                }
+        }
+    }
+}
+
+/* ------------------------------------------------- the three decoders */
+static void *alloc2(int rows, int cols, size_t esz, void ***index) {
+    char *blk = calloc((size_t)rows * cols, esz);
+    void **ix = malloc(sizeof(void *) * rows);
+    for (int r = 0; r < rows; ++r) ix[r] = blk + (size_t)r * cols * esz;
+    *index = ix;
+    return blk;
+}
+
+int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, double factor, double offset,
+               const double *L_ch, int *out, double *L_post, int *iters) {
+    int q = c->q, q1 = q - 1;
+    state s; s.c = c;
+    s.v2c = malloc(sizeof(double) * c->N * c->maxdv * q1);
+    s.c2v = calloc((size_t)c->M * c->maxdc * q1, sizeof(double));
+    s.tmp = malloc(sizeof(double) * q1);
+    for (int col = 0; col < c->N; ++col)                 /* init, NBLDPC.cpp:649-667 / 781-800 / 934-969 */
+        for (int d = 0; d < c->vdeg[col]; ++d) memcpy(V2C(&s, col, d), L_ch + (size_t)col * q1, sizeof(double) * q1);
+
+    bp_ctx b = {&s, 0, 0, 0};
+    ems_ctx e; memset(&e, 0, sizeof e);
+    tems_ctx t; memset(&t, 0, sizeof t);
+    void *blk[8] = {0}; int nblk = 0;
+    if (method == 1) {
+        b.sigma = calloc(q1, sizeof(double)); b.rho = calloc(q1, sizeof(double)); b.llrv = calloc(q1, sizeof(double));
+    } else if (method == 2) {
+        e.s = &s; e.nm = p0; e.nc = p1;
+        blk[nblk++] = alloc2(c->maxdc, q, sizeof(double), (void ***)&e.srt);
+        blk[nblk++] = alloc2(c->maxdc, q, sizeof(int), (void ***)&e.sym);
+        e.best = malloc(sizeof(double) * q);
+    } else {
+        t.s = &s; t.nr = p0; t.nc = p1;
+        blk[nblk++] = alloc2(c->maxdc, q, sizeof(double), (void ***)&t.dU);
+        blk[nblk++] = alloc2(q, c->maxdc, sizeof(int), (void ***)&t.ord);
+        blk[nblk++] = alloc2(q, c->maxdc, 1, (void ***)&t.allowed);
+        blk[nblk++] = alloc2(q, c->maxdc, sizeof(int), (void ***)&t.eta);
+        t.beta = calloc(c->maxdc, sizeof(int)); t.cand = calloc(c->maxdc, sizeof(int));
+        t.dW = malloc(sizeof(double) * q); t.T = malloc(sizeof(double) * q);
+        t.used = calloc(q, 1); t.hit = calloc(q, 1);
+        g_tems_leaves = 0;
+    }
+
+    int ok = 0, it = 0;
+    while (it++ < max_iter) {
+        ok = posterior_and_syndrome(&s, L_ch, L_post, out);
+        if (ok) break;
+        if (method == 1) { var_to_check(&s, L_post, 0.5, 0.5); cn_qspa(&s, &b); }
+        else if (method == 2) { var_to_check(&s, L_post, 0, 1); cn_ems(&s, &e, factor, offset); }
+        else { var_to_check(&s, L_post, 0.25, 0.75); cn_tems(&s, &t, factor, offset); }
+    }
+    *iters = ok ? it : max_iter;
+
+    free(s.v2c); free(s.c2v); free(s.tmp);
+    free(b.sigma); free(b.rho); free(b.llrv);
+    free(e.srt); free(e.sym); free(e.best);
+    free(t.dU); free(t.ord); free(t.allowed); free(t.eta); free(t.beta); free(t.cand);
+    free(t.dW); free(t.T); free(t.used); free(t.hit);
+    for (int i = 0; i < nblk; ++i) free(blk[i]);
+    return ok;
+}
