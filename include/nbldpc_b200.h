@@ -1,0 +1,172 @@
+/* nbldpc_b200 -- C ABI of the B200-native non-binary LDPC decode path.
+ *
+ * Drop-in boundary for the decode path of YongonY/NBLDPC.  The reference has no FFI; its boundary is the
+ * public C++ surface  CNBLDPC::Initial / CNBLDPC::Decoding / CComm::Demodulate / CComm::Err.  Every entry
+ * point below names the reference interface it replaces (file:line into the reference tree).  Plain
+ * pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative nbl_status on error; nbl_last_error() gives text.
+ *     Nothing throws across the ABI and nothing calls exit() (the reference exit(-1)s on config errors,
+ *     e.g. NBLDPC.cpp:282-286, 619-638; the C++ harness on top keeps that behaviour).
+ *   - "LLR vector" layout is the reference's: q-1 doubles per symbol, entry k-1 = ln P(x=k)/P(x=0)
+ *     (NBLDPC.cpp:1542-1562, Comm.cpp:360-398).  Batched arrays are dense [B][N][q-1].
+ *   - data pointers may be HOST or DEVICE pointers (detected with cudaPointerGetAttributes); device
+ *     pointers must belong to the decoder's device.  Host pointers are staged through pinned buffers.
+ *   - handles are not thread-safe; distinct decoder handles are independent (one CUDA stream each).
+ *   - there is no CPU fallback: every compute entry point fails with NBL_ERR_CUDA when no B200 is present.
+ */
+#ifndef NBLDPC_B200_H
+#define NBLDPC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBL_ABI_VERSION 1
+
+typedef enum {
+    NBL_OK = 0,
+    NBL_ERR_ARG = -1,     /* bad argument / unsupported configuration */
+    NBL_ERR_IO = -2,      /* file missing or malformed */
+    NBL_ERR_CUDA = -3,    /* CUDA runtime error (message in nbl_last_error) */
+    NBL_ERR_ALLOC = -4
+} nbl_status;
+
+/* decode methods: same numbers as the reference's profile / Simulation.h:3-9 */
+#define NBL_METHOD_QSPA 1 /* BP_DECODE    -> CNBLDPC::Decoding_BP   NBLDPC.cpp:643-776  (FWHT check node)   */
+#define NBL_METHOD_EMS 2  /* EMS_DECODE   -> CNBLDPC::Decoding_EMS  NBLDPC.cpp:778-927                      */
+#define NBL_METHOD_TEMS 4 /* T_EMS_DECODE -> CNBLDPC::Decoding_TEMS NBLDPC.cpp:929-1143                     */
+
+#define NBL_PREC_F32 0 /* fast mode: fp32 messages and arithmetic (QSPA transform in fp64)               */
+#define NBL_PREC_F64 1 /* parity mode: fp64 everywhere, reference operation order, no FMA contraction   */
+
+typedef struct nbl_code nbl_code;       /* GF(q) tables + parity-check graph, resident on one device */
+typedef struct nbl_decoder nbl_decoder; /* message workspace for up to max_batch frames + a stream    */
+
+int nbl_abi_version(void);
+const char *nbl_last_error(void);
+int nbl_device_count(void); /* number of visible CUDA devices (0 without a GPU; never an error) */
+
+/* ---- code and table loading: replaces CGF::Initial (GF.cpp:50-155) and the graph part of
+ *      CNBLDPC::Initial (NBLDPC.cpp:140-263).  These are host-only until a decoder is created. ---- */
+
+/* GF(q) arithmetic from the primitive polynomial of Arith.Table.GF.q.txt (0 = the polynomial the
+ * reference ships for that q: 7,11,19,37,67,137,285,529).  mul is q*q ints, inv q ints (inv[0] = 0,
+ * where the reference's GFInverse(0) exits, GF.cpp:41-45). */
+int nbl_gf_tables(int q, int prim_poly, int *mul, int *inv);
+/* cross-check an Arith.Table.GF.q.txt file against the generated tables (0 = identical). */
+int nbl_gf_check_table_file(const char *path, int q);
+
+/* graph from explicit edge lists, both in the reference's file order (chk_* row-major CSR,
+ * var_* column-major CSR; var_ptr may be NULL => variable side ordered by ascending check index). */
+int nbl_code_create(nbl_code **out, int q, int prim_poly, int N, int M,
+                    const int *chk_ptr, const int *chk_var, const int *chk_coef,
+                    const int *var_ptr, const int *var_chk, const int *var_coef);
+/* the reference's alist-like code file (divsalar.*, BDS.*; parsed at NBLDPC.cpp:147-205) */
+int nbl_code_load_file(nbl_code **out, const char *path, int prim_poly);
+/* binary image H_bit_GF*.txt (no reference loader exists; layout in DESIGN.md) */
+int nbl_code_load_hbit(nbl_code **out, const char *path, int q, int prim_poly);
+void nbl_code_destroy(nbl_code *code);
+
+typedef struct {
+    int q, p, N, M, E, max_dv, max_dc, prim_poly;
+} nbl_code_info;
+int nbl_code_get_info(const nbl_code *code, nbl_code_info *info);
+/* copy the edge lists out (any pointer may be NULL): chk_ptr[M+1], chk_var[E], chk_coef[E], chk_dv[E]
+ * (= ChkLinkDv), var_ptr[N+1], var_chk[E], var_coef[E], var_dc[E] (= VarLinkDc) */
+int nbl_code_get_graph(const nbl_code *code, int *chk_ptr, int *chk_var, int *chk_coef, int *chk_dv,
+                       int *var_ptr, int *var_chk, int *var_coef, int *var_dc);
+/* variables whose degree equals punct_degree (the reference's puncture rule, NBLDPC.cpp:163-177);
+ * returns the count, fills positions[] (capacity N) when not NULL. */
+int nbl_code_puncture_set(const nbl_code *code, int punct_degree, int *positions);
+
+/* ---- decoder: replaces the per-method scratch of CNBLDPC::Initial (NBLDPC.cpp:267-329) and
+ *      CNBLDPC::Decoding + Decoding_BP/EMS/TEMS (NBLDPC.cpp:607-1143) ---- */
+typedef struct {
+    int method;      /* NBL_METHOD_*                                                           */
+    int max_iter;    /* maxIter of the profile                                                 */
+    int p0;          /* EMS: n_m            T-EMS: n_r            QSPA: ignored                */
+    int p1;          /* EMS: n_c            T-EMS: n_c            QSPA: ignored                */
+    double factor;   /* EMS/T-EMS correction factor (divide)                                   */
+    double offset;   /* EMS/T-EMS offset (soft threshold)                                      */
+    int precision;   /* NBL_PREC_*                                                             */
+    int early_stop;  /* 1: frames leave the batch when their syndrome is zero (reference rule);
+                        0: every frame runs max_iter iterations, outputs are still the reference's
+                           (decision / iteration count latched at the first zero syndrome)       */
+    int max_batch;   /* frames per nbl_decode_batch call that the workspace is sized for        */
+    int device;      /* CUDA device ordinal                                                     */
+} nbl_decoder_config;
+
+/* stream: a cudaStream_t (as void*) to launch on, or NULL for a private non-blocking stream */
+int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const nbl_decoder_config *cfg, void *stream);
+void nbl_decoder_destroy(nbl_decoder *dec);
+void *nbl_decoder_stream(nbl_decoder *dec);
+int nbl_decoder_sync(nbl_decoder *dec);
+
+/* CNBLDPC::Decoding for B frames (B = 1 is the reference's call, Comm.cpp:417).
+ *   L_ch       [B][N][q-1] doubles (channel LLRs, as RX_LLR_SYM)
+ *   out_sym    [B][N] ints        hard decisions (as DecodeOutput / RX_DECODE_SYM)
+ *   converged  [B] ints or NULL   the reference's return value, 1 = syndrome satisfied
+ *   iterations [B] ints or NULL   value of the reference's iter_number at return (max_iter on failure)
+ *   L_post     [B][N][q-1] doubles or NULL   posterior at return (public member CNBLDPC::L_post)
+ * The call is synchronous for host outputs; with device outputs it only enqueues on the stream. */
+int nbl_decode_batch(nbl_decoder *dec, const double *L_ch, int B, int *out_sym, int *converged,
+                     int *iterations, double *L_post);
+
+/* ---- channel front end: replaces CComm::Demodulate (Comm.cpp:340-407); sigma from CComm::SetEbN0
+ *      (Comm.cpp:157-179).  Output is L_ch [B][N][q-1] doubles (host or device). ---- */
+/* BPSK: y_re [B][(N - n_punct) * p] received real parts in transmit order */
+int nbl_demap_bpsk(nbl_decoder *dec, const double *y_re, int B, double sigma, const int *punct_sym,
+                   int n_punct, double *L_ch);
+/* nQAM == q: y [B][N - n_punct][2] received points, constellation [q][2] */
+int nbl_demap_qam(nbl_decoder *dec, const double *y, int B, const double *constellation, double sigma,
+                  const int *punct_sym, int n_punct, double *L_ch);
+/* fused front end + decode (what CComm::Demodulate followed by CComm::Decode does per frame,
+ * Comm.cpp:188-189): received samples in, decisions out, channel LLRs never leave the device.
+ * modulation: 2 = BPSK (y is [B][(N-n_punct)*p]), q = QAM (y is [B][N-n_punct][2]) */
+int nbl_demap_decode_batch(nbl_decoder *dec, int modulation, const double *y, int B, const double *constellation,
+                           double sigma, const int *punct_sym, int n_punct, int *out_sym, int *converged,
+                           int *iterations);
+
+/* ---- device Monte-Carlo: the frame loop of main.cpp:43-55 (source -> map -> AWGN -> demap -> decode
+ *      -> CComm::Err, Comm.cpp:446-503) for `frames` frames starting at global index first_frame.
+ *      Noise is counter-based (Philox4x32-10 keyed by (seed, frame index)) so that counters do not
+ *      depend on how frames are split over calls, streams or GPUs. ---- */
+#define NBL_CNT_FRAMES 0
+#define NBL_CNT_ERR_FRAMES 1
+#define NBL_CNT_ERR_SYMS 2
+#define NBL_CNT_ERR_BITS 3
+#define NBL_CNT_CONVERGED 4   /* decoder returned 1                                         */
+#define NBL_CNT_UNDETECTED 5  /* converged to a wrong codeword                              */
+#define NBL_CNT_ITERATIONS 6  /* sum of iteration counts                                    */
+#define NBL_CNT_RESERVED 7
+#define NBL_NUM_COUNTERS 8
+
+typedef struct {
+    double ebn0_db;
+    int modulation;             /* 2 = BPSK, q = QAM                                                 */
+    const double *constellation;/* [q][2] host pointer, QAM only                                     */
+    uint64_t seed;
+    uint64_t first_frame;       /* global index of the first frame of this call                      */
+    uint64_t frames;            /* number of frames to simulate (any size; processed in max_batch chunks) */
+    const int *codewords;       /* host [n_codewords][N] pool of valid codewords (NULL = all-zero codeword);
+                                   frame f transmits codeword f % n_codewords                        */
+    int n_codewords;
+} nbl_sim_config;
+
+/* counters: host uint64[NBL_NUM_COUNTERS], ACCUMULATED into (caller zeroes). */
+int nbl_simulate(nbl_decoder *dec, const nbl_sim_config *cfg, uint64_t *counters);
+/* same, but leaves the sums in a device-resident uint64[8] (for an in-place NCCL all-reduce) and
+ * does not synchronise; dev_counters is accumulated into. */
+int nbl_simulate_async(nbl_decoder *dec, const nbl_sim_config *cfg, uint64_t *dev_counters);
+
+/* timing hook: milliseconds the GPU spent in the decode kernels of the last nbl_decode_batch /
+ * nbl_demap_decode_batch / nbl_simulate call on this decoder (CUDA events on the decoder's stream),
+ * and the number of kernel launches it made. */
+int nbl_decoder_last_timing(nbl_decoder *dec, float *kernel_ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

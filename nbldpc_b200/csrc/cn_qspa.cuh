@@ -1,0 +1,86 @@
+// QSPA (sum-product) check node as a fast Walsh-Hadamard transform, one group of Q threads per check row.
+//
+// Replaces L_Back / L_Forward / LLR_BoxPlus of the reference (NBLDPC.cpp:747-767, 1565-1712), which evaluates
+// every pairwise box-plus in the log domain with q^2 Jacobian terms (O(dc^2 q^2) exp/log per check).
+// GF(2^p) addition is XOR, so the check constraint sum_l h_l x_l = 0 makes the extrinsic distribution of
+// h_d x_d the XOR-convolution of the other inputs' (permuted) distributions; the Walsh-Hadamard transform
+// diagonalises XOR-convolution:   c2v_d = ln( WHT( prod_{l != d} WHT(P_l) ) ),  P_l[h_l x] = softmax(V_l)[x].
+// O(dc q log q) per check.  The transform runs in fp64 in both precision modes (probabilities below
+// ~1e-7 of the maximum would vanish in an fp32 transform).
+#pragma once
+#include "dev_common.cuh"
+
+namespace nbl {
+
+template <typename T, int Q> struct QspaSmem {
+    using K = typename Real<T>::key_t;
+    T *V;         // [maxdc][Q]
+    double *F;    // [maxdc][Q] transformed inputs
+    double *R;    // [Q] product / output work vector
+    int *sdec;    // [maxdc]
+    RedScratch<K, Grp<Q>::WARPS, 1> *red1;
+    RedScratch<K, Grp<Q>::WARPS, 2> *red;
+    __host__ __device__ static size_t bytes(int maxdc) {
+        size_t b = sizeof(double) * (size_t)Q * (maxdc + 1) + sizeof(T) * (size_t)Q * maxdc;
+        b = align_up(b, 8);
+        b += sizeof(RedScratch<K, Grp<Q>::WARPS, 1>) + sizeof(RedScratch<K, Grp<Q>::WARPS, 2>);
+        b = align_up(b, 4);
+        b += sizeof(int) * maxdc;
+        return align_up(b, 16);
+    }
+    __device__ void carve(unsigned char *base, int maxdc) {
+        double *f = reinterpret_cast<double *>(base);
+        F = f; f += (size_t)maxdc * Q; R = f; f += Q;
+        T *t = reinterpret_cast<T *>(f);
+        V = t; t += (size_t)maxdc * Q;
+        unsigned char *c = base + align_up((size_t)(reinterpret_cast<unsigned char *>(t) - base), 8);
+        red1 = reinterpret_cast<RedScratch<K, Grp<Q>::WARPS, 1> *>(c); c += sizeof(*red1);
+        red = reinterpret_cast<RedScratch<K, Grp<Q>::WARPS, 2> *>(c); c += sizeof(*red);
+        c = base + align_up((size_t)(c - base), 4);
+        sdec = reinterpret_cast<int *>(c);
+    }
+};
+
+// in-place Q-point WHT of `n` vectors stored back to back in shared memory (buf[v*Q + x]); unnormalised
+template <int Q> __device__ inline void group_wht(double *buf, int n, int x, int gid) {
+    for (int bit = 1; bit < Q; bit <<= 1) {
+        Grp<Q>::sync(gid);
+        double mine[16], other[16];
+        for (int v = 0; v < n; ++v) { mine[v] = buf[v * Q + x]; other[v] = buf[v * Q + (x ^ bit)]; }
+        Grp<Q>::sync(gid);
+        for (int v = 0; v < n; ++v) buf[v * Q + x] = (x & bit) ? (other[v] - mine[v]) : (mine[v] + other[v]);
+    }
+    Grp<Q>::sync(gid);
+}
+
+template <typename T, int Q>
+__device__ void cn_qspa(QspaSmem<T, Q> &S, const DevGraph &g, int gid, int x, int e0, int dcn,
+                        T *__restrict__ c2v_out) {
+    // distributions in the syndrome domain, maximum normalised to 1 (the scale cancels in the LLR)
+    for (int d = 0; d < dcn; ++d) {
+        const double vmax = (double)S.V[d * Q + S.sdec[d]];
+        const int k = g.pinv[(size_t)(e0 + d) * Q + x];         // P[s] = p[h^-1 s]
+        S.F[d * Q + x] = exp((double)S.V[d * Q + k] - vmax);
+    }
+    group_wht<Q>(S.F, dcn, x, gid);
+    for (int d = 0; d < dcn; ++d) {
+        double r = 1.0;
+        for (int l = 0; l < dcn; ++l) if (l != d) r *= S.F[l * Q + x];
+        S.R[x] = r;
+        group_wht<Q>(S.R, 1, x, gid);
+        // The true inverse transform is a sum of non-negative products; entries whose probability is below
+        // the fp64 rounding noise of the transform (~2^-53 of the total) come out as noise of either sign,
+        // so they are floored there before the log (their LLR saturates near -37 relative to symbol 0).
+        const double tot = S.R[0];
+        const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
+        T out = T(0);
+        if (x != 0) {
+            const double a = S.R[g.pfwd[(size_t)(e0 + d) * Q + x]];
+            out = (T)(log(a > fl ? a : fl) - log(tot > fl ? tot : fl));
+        }
+        c2v_out[(size_t)(e0 + d) * Q + x] = out;
+        Grp<Q>::sync(gid);
+    }
+}
+
+}  // namespace nbl

@@ -1,0 +1,180 @@
+// T-EMS check node (trellis EMS in the delta domain), one group of Q threads per check row.
+//
+// Replaces CNBLDPC::TEMS_Get_Beta / TEMS_Get_deltaU / TEMS_Get_Min / TEMS_ConstructConf and the output
+// stage of Decoding_TEMS (reference NBLDPC.cpp:1055-1130, 1789-1944).  Same result, different algorithm:
+//   * the reference enumerates every configuration (<= n_c deviations, each eta deviating only in its n_r
+//     cheapest columns) with a recursive depth-first search, ~94 k leaves per GF(256) check;
+//   * here deltaW[s] = min(single deviation, best pair) is computed by all q threads at once as a
+//     min-plus XOR-convolution: for column d, thread s scans the compact list of deviations (b, dU[d][b])
+//     allowed in column d against P_d[s^b], the running minimum over the allowed deviations of the columns
+//     before d.  Same candidate set, so the same minimum; the winning path (two (column, eta) pairs) is kept
+//     for the output stage exactly as TEMS_Eta is.  n_c >= 3 uses the column DP in cn_tems_dp().
+// Tie-breaking among exactly equal path costs follows the scan order here (column, then eta ascending) and
+// the depth-first order in the reference; with continuous LLRs exact ties have probability zero
+// (see DESIGN.md "exact ties").
+#pragma once
+#include "dev_common.cuh"
+
+namespace nbl {
+
+template <typename T, int Q> struct TemsSmem {
+    using K = typename Real<T>::key_t;
+    T *V;        // [maxdc][Q] v2c of the row's edges; reused as Tout (per-column output trellis)
+    T *dU;       // [maxdc][Q]
+    T *P;        // [Q] running minimum over allowed deviations of earlier columns
+    T *dW;       // [Q]
+    T *lc;       // [Q] list: cost
+    T *W2;       // DP buffers (n_c >= 3): [2][n_c+1][Q], else unused
+    uint16_t *amask;  // [Q] bit d = eta may deviate in column d
+    uint8_t *lb;      // [Q] list: eta
+    uint8_t *c0, *c1; // [Q] cheapest / second cheapest column of eta
+    uint8_t *pb;      // [Q] path: eta of the later deviation
+    uint8_t *pcol;    // [Q] path: c_first | c_second << 4
+    uint8_t *pnd;     // [Q] path: number of deviations (0,1,2)
+    uint8_t *bp;      // DP back pointers [maxdc][n_c+1][Q]
+    int *wtot;        // [WARPS]
+    int *sdec;        // [maxdc] decide() of each input
+    RedScratch<K, Grp<Q>::WARPS, 2> *red;
+
+    __host__ __device__ static size_t bytes(int maxdc, int nc) {
+        size_t b = 0;
+        b += sizeof(T) * (size_t)Q * (2 * maxdc + 3);
+        if (nc >= 3) b += sizeof(T) * (size_t)Q * 2 * (nc + 1);
+        b = align_up(b, 8);
+        b += sizeof(RedScratch<K, Grp<Q>::WARPS, 2>);
+        b = align_up(b, 4);
+        b += sizeof(int) * (Grp<Q>::WARPS + maxdc);
+        b += sizeof(uint16_t) * Q;
+        b += 6 * (size_t)Q;
+        if (nc >= 3) b += (size_t)maxdc * (nc + 1) * Q;
+        return align_up(b, 16);
+    }
+    __device__ void carve(unsigned char *base, int maxdc, int nc) {
+        T *t = reinterpret_cast<T *>(base);
+        V = t; t += (size_t)maxdc * Q;
+        dU = t; t += (size_t)maxdc * Q;
+        P = t; t += Q; dW = t; t += Q; lc = t; t += Q;
+        W2 = t; if (nc >= 3) t += (size_t)2 * (nc + 1) * Q;
+        unsigned char *c = reinterpret_cast<unsigned char *>(t);
+        c = base + align_up((size_t)(c - base), 8);
+        red = reinterpret_cast<RedScratch<K, Grp<Q>::WARPS, 2> *>(c); c += sizeof(*red);
+        c = base + align_up((size_t)(c - base), 4);
+        wtot = reinterpret_cast<int *>(c); c += sizeof(int) * Grp<Q>::WARPS;
+        sdec = reinterpret_cast<int *>(c); c += sizeof(int) * maxdc;
+        amask = reinterpret_cast<uint16_t *>(c); c += sizeof(uint16_t) * Q;
+        lb = c; c += Q; c0 = c; c += Q; c1 = c; c += Q; pb = c; c += Q; pcol = c; c += Q; pnd = c; c += Q;
+        bp = c;
+    }
+};
+
+// Inputs: S.V[d][x] (final v2c, slot 0 == 0) and S.sdec[d] = decide(V_d) for d < dcn, visible to the group.
+// Output: c2v_out[(e0+d)*Q + x] for d < dcn.
+template <typename T, int Q>
+__device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, int e0, int dcn, int nr, int nc,
+                        T factor, T offset, T *__restrict__ c2v_out /* frame base, [E][Q] */) {
+    const T INF = Real<T>::inf();
+    // -- beta, syndrome of the most reliable symbols (TEMS_Get_Beta) --------------------------------
+    int syn = 0;
+    for (int d = 0; d < dcn; ++d) syn ^= g.pfwd[(size_t)(e0 + d) * Q + S.sdec[d]];
+    // -- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)] -----------------
+    for (int d = 0; d < dcn; ++d) {
+        const int sd = S.sdec[d];
+        const int beta = g.pfwd[(size_t)(e0 + d) * Q + sd];
+        const T vmax = S.V[d * Q + sd];                       // V[.][0] == 0 covers "nothing positive"
+        const int k = g.pinv[(size_t)(e0 + d) * Q + (x ^ beta)];
+        S.dU[d * Q + x] = vmax - S.V[d * Q + k];
+    }
+    Grp<Q>::sync(gid);
+    // -- column order per eta (TEMS_Get_Min): stable rank of each column by dU[.][x] ------------------
+    {
+        unsigned am = 0; int k0 = 0, k1 = 0;
+        for (int d = 0; d < dcn; ++d) {
+            const T ud = S.dU[d * Q + x];
+            int rank = 0;
+            for (int c = 0; c < dcn; ++c) {
+                const T uc = S.dU[c * Q + x];
+                rank += (uc < ud) || (uc == ud && c < d);
+            }
+            if (rank < nr) am |= 1u << d;
+            if (rank == 0) k0 = d;
+            if (rank == 1) k1 = d;
+        }
+        S.amask[x] = (uint16_t)am; S.c0[x] = (uint8_t)k0; S.c1[x] = (uint8_t)k1;
+        S.P[x] = INF;
+    }
+    // -- configuration search for n_c <= 2 ---------------------------------------------------------
+    T best = INF; int bb = 0, bd = 0;
+    if (nc >= 2) {
+        for (int d = 1; d < dcn; ++d) {
+            Grp<Q>::sync(gid);                                  // previous scan done with P / list
+            {   // fold column d-1 into the running minimum (strict '<': lower column wins ties)
+                const T u = (x != 0 && ((S.amask[x] >> (d - 1)) & 1)) ? S.dU[(d - 1) * Q + x] : INF;
+                if (u < S.P[x]) S.P[x] = u;
+            }
+            const bool in = x != 0 && ((S.amask[x] >> d) & 1);
+            int len;
+            const int pos = group_prefix_count<Q>(in, x, gid, S.wtot, len);
+            if (in) { S.lb[pos] = (uint8_t)x; S.lc[pos] = S.dU[d * Q + x]; }
+            Grp<Q>::sync(gid);
+            for (int i = 0; i < len; ++i) {
+                const int b = S.lb[i];
+                const T cand = S.P[x ^ b] + S.lc[i];
+                if (cand < best) { best = cand; bb = b; bd = d; }
+            }
+        }
+    }
+    // -- deltaW and the recorded path ------------------------------------------------------------------
+    {
+        const int k0 = S.c0[x];
+        const T m0 = S.dU[k0 * Q + x];
+        T w; int nd, pc = 0;
+        if (x == 0) { w = T(0); nd = 0; }
+        else if (best < m0) {
+            const int a = x ^ bb;                               // first deviation: cheapest allowed column before bd
+            T m = INF; int ca = 0;
+            const unsigned am = S.amask[a];
+            for (int c = 0; c < bd; ++c)
+                if ((am >> c) & 1) { const T u = S.dU[c * Q + a]; if (u < m) { m = u; ca = c; } }
+            w = best; nd = 2; pc = ca | (bd << 4);
+        } else { w = m0; nd = 1; pc = k0; }
+        S.dW[x] = w; S.pb[x] = (uint8_t)bb; S.pcol[x] = (uint8_t)pc; S.pnd[x] = (uint8_t)nd;
+    }
+    Grp<Q>::sync(gid);                                          // everyone is done with V and P
+    // -- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): identity entries first -----------------------
+    T *Tout = S.V;
+    {
+        const int nd = S.pnd[x], pc = S.pcol[x];
+        const int ca = pc & 15, cb = pc >> 4;
+        const T w = S.dW[x];
+        for (int d = 0; d < dcn; ++d) {
+            const bool uses = (nd == 1 && ca == d) || (nd == 2 && (ca == d || cb == d));
+            Tout[d * Q + x] = (x == 0) ? T(0) : (uses ? INF : w);
+        }
+    }
+    Grp<Q>::sync(gid);
+    if (S.pnd[x] == 2) {                                        // entries that land on another index
+        const int pc = S.pcol[x], ca = pc & 15, cb = pc >> 4, b = S.pb[x], a = x ^ b;
+        const T w = S.dW[x];
+        atomic_min_nonneg(&Tout[ca * Q + b], w - S.dU[ca * Q + a]);
+        atomic_min_nonneg(&Tout[cb * Q + a], w - S.dU[cb * Q + b]);
+    }
+    Grp<Q>::sync(gid);
+    // -- fill-in (NBLDPC.cpp:1095-1102), back to the normal domain, un-permute, correct (1105-1128) -----
+    for (int d = 0; d < dcn; ++d) {
+        const int e = e0 + d;
+        const int bs = syn ^ g.pfwd[(size_t)e * Q + S.sdec[d]];
+        auto getT = [&](int t) -> T {
+            T v = Tout[d * Q + t];
+            if (v == INF) { const int k0 = S.c0[t], k1 = S.c1[t]; v = (d == k0) ? S.dU[k1 * Q + t] : S.dU[k0 * Q + t]; }
+            return v;
+        };
+        T out = T(0);
+        if (x != 0) {
+            const int t = g.pfwd[(size_t)e * Q + x] ^ bs;
+            out = soft_threshold<T>(getT(bs) - getT(t), factor, offset);
+        }
+        c2v_out[(size_t)e * Q + x] = out;
+    }
+}
+
+}  // namespace nbl

@@ -1,0 +1,742 @@
+// B200 (sm_100a) decode path: kernels + the extern "C" decoder entry points of include/nbldpc_b200.h.
+//
+// Data layout in HBM (per decoder, frames-in-flight = max_batch; T = float or double):
+//   lch  [B][N][Q]   channel LLRs, slot 0 = 0 (the implicit LLR of symbol 0), Q = q
+//   v2c  [B][E][Q]   variable->check messages, edge ids check-major so a check row's dc vectors are contiguous
+//   c2v  [2][B][E][Q] check->variable messages, double buffered (iteration t reads t-1, writes t)
+//   vdec [B][E] u8   decide(v2c) of the previous iteration (the damping test's "before", NBLDPC.cpp:1038)
+//   dec  [B][N] u8   tentative hard decisions of the running iteration
+// One launch per decoding iteration processes every (frame, check row) pair: a group of Q threads
+// recomputes the posteriors of the row's variables, makes the decisions, accumulates the row syndrome,
+// forms the damped v2c messages (steps A-C of the reference loop, NBLDPC.cpp:977-1052) and runs the check
+// node (step D) on them while they are still in shared memory.  Messages stream HBM -> smem -> HBM once
+// per iteration, fully coalesced (thread x <-> element x).
+#include "internal.h"
+#include "dev_common.cuh"
+#include "cn_tems.cuh"
+#include "cn_ems.cuh"
+#include "cn_qspa.cuh"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace nbl;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            nbl_set_error(std::string(#call) + " failed: " + cudaGetErrorString(e_));              \
+            return NBL_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+// ======================================================================================================
+// kernels
+// ======================================================================================================
+template <typename T> struct IterParams {
+    DevGraph g;
+    int B, iter, first, early_stop, method, p0, p1;
+    T factor, offset, w_old, w_new;
+    const T *lch;
+    T *v2c;
+    const T *c2v_in;
+    T *c2v_out;
+    uint8_t *vdec, *dec;
+    int *flag;
+    const uint8_t *done;
+};
+
+// channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
+template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec * q) return;
+    size_t v = i / q; int x = (int)(i % q);
+    dst[i] = x == 0 ? T(0) : (T)src[v * (q - 1) + x - 1];
+}
+
+template <typename T, int Q, int METHOD>
+__global__ void __launch_bounds__(Grp<Q>::THREADS) k_iterate(const IterParams<T> P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevGraph &g = P.g;
+    const int gid = threadIdx.x / Q, x = threadIdx.x % Q;
+    const long long w = (long long)blockIdx.x * Grp<Q>::G + gid;
+    if (w >= (long long)P.B * g.M) return;
+    const int f = (int)(w / g.M), row = (int)(w % g.M);
+    if (P.early_stop && P.done[f]) return;
+
+    size_t per_group;
+    TemsSmem<T, Q> St; EmsSmem<T, Q> Se; QspaSmem<T, Q> Sq;
+    T *V; int *sdec; RedScratch<typename Real<T>::key_t, Grp<Q>::WARPS, 2> *red;
+    if (METHOD == NBL_METHOD_TEMS) {
+        per_group = TemsSmem<T, Q>::bytes(g.max_dc, P.p1);
+        St.carve(smem_raw + per_group * gid, g.max_dc, P.p1); V = St.V; sdec = St.sdec; red = St.red;
+    } else if (METHOD == NBL_METHOD_EMS) {
+        per_group = EmsSmem<T, Q>::bytes(g.max_dc, P.p0, P.p1);
+        Se.carve(smem_raw + per_group * gid, g.max_dc, P.p0, P.p1); V = Se.V; sdec = Se.sdec; red = Se.red;
+    } else {
+        per_group = QspaSmem<T, Q>::bytes(g.max_dc);
+        Sq.carve(smem_raw + per_group * gid, g.max_dc); V = Sq.V; sdec = Sq.sdec; red = Sq.red;
+    }
+
+    const int e0 = g.chk_ptr[row], dcn = g.chk_ptr[row + 1] - e0;
+    const size_t fE = (size_t)f * g.E, fN = (size_t)f * g.N;
+    int phase = 0, syn = 0;
+    // ---- steps A-C for the row's variables ------------------------------------------------------------
+    for (int d = 0; d < dcn; ++d) {
+        const int e = e0 + d, col = g.chk_var[e];
+        T post = P.lch[(fN + col) * Q + x];
+        T vnew = post;
+        if (!P.first) {
+            T own = T(0);
+            for (int s = g.var_ptr[col]; s < g.var_ptr[col + 1]; ++s) {      // file order = summation order
+                const int ee = g.var_edge[s];
+                const T m = P.c2v_in[(fE + ee) * Q + x];
+                post = post + m;
+                if (ee == e) own = m;
+            }
+            vnew = post - own;
+        }
+        T vals[2] = {post, vnew}; int ds[2];
+        group_decide<Q, T, 2>(vals, x, gid, red, phase, ds);
+        T vfin = vnew; int dfin = ds[1];
+        if (!P.first && P.w_old != T(0) && ds[1] != (int)P.vdec[fE + e]) {      // group-uniform branch
+            const T vold = P.v2c[(fE + e) * Q + x];
+            vfin = P.w_old * vold + P.w_new * vnew;                             // compiled with -fmad=false
+            T v1[2] = {vfin, T(0)}; int d1[2];
+            group_decide<Q, T, 2>(v1, x, gid, red, phase, d1);
+            dfin = d1[0];
+        }
+        P.v2c[(fE + e) * Q + x] = vfin;
+        V[d * Q + x] = vfin;
+        if (x == 0) { P.vdec[fE + e] = (uint8_t)dfin; P.dec[fN + col] = (uint8_t)ds[0]; sdec[d] = dfin; }
+        syn ^= g.pfwd[(size_t)e * Q + ds[0]];
+    }
+    if (x == 0 && syn != 0) P.flag[f] = 1;
+    Grp<Q>::sync(gid);
+    // ---- step D: check node ---------------------------------------------------------------------------
+    T *out = P.c2v_out + fE * Q;
+    if (METHOD == NBL_METHOD_TEMS) cn_tems<T, Q>(St, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, out);
+    else if (METHOD == NBL_METHOD_EMS) cn_ems<T, Q>(Se, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, phase, out);
+    else cn_qspa<T, Q>(Sq, g, gid, x, e0, dcn, out);
+}
+
+// posterior + decision only (the last iteration's steps A-B; also serves the L_post output).
+// group per (frame, variable).  want_post: write doubles [B][N][q-1] for frames with sel[f] != 0.
+template <typename T, int Q>
+__global__ void __launch_bounds__(Grp<Q>::THREADS) k_posterior(DevGraph g, int B, int first, int early_stop, const T *__restrict__ lch,
+                                                             const T *__restrict__ c2v_in, const uint8_t *__restrict__ done,
+                                                             uint8_t *dec, double *post_out, const uint8_t *__restrict__ sel) {
+    __shared__ RedScratch<typename Real<T>::key_t, Grp<Q>::WARPS, 2> red_all[Grp<Q>::G];
+    const int gid = threadIdx.x / Q, x = threadIdx.x % Q;
+    const long long w = (long long)blockIdx.x * Grp<Q>::G + gid;
+    if (w >= (long long)B * g.N) return;
+    const int f = (int)(w / g.N), col = (int)(w % g.N);
+    if (post_out) { if (!sel[f]) return; }
+    else if (early_stop && done[f]) return;
+    T post = lch[((size_t)f * g.N + col) * Q + x];
+    if (!first)
+        for (int s = g.var_ptr[col]; s < g.var_ptr[col + 1]; ++s) post = post + c2v_in[((size_t)f * g.E + g.var_edge[s]) * Q + x];
+    if (post_out) {
+        if (x != 0) post_out[((size_t)f * g.N + col) * (Q - 1) + x - 1] = (double)post;
+        return;
+    }
+    int phase = 0;
+    T vals[2] = {post, T(0)}; int ds[2];
+    group_decide<Q, T, 2>(vals, x, gid, &red_all[gid], phase, ds);
+    if (x == 0) dec[(size_t)f * g.N + col] = (uint8_t)ds[0];
+}
+
+// row syndromes from dec (thread per (frame,row)); sets flag[f] when any row is unsatisfied
+__global__ void k_syndrome(DevGraph g, int B, int early_stop, const uint8_t *__restrict__ done, const uint8_t *__restrict__ dec, int *flag) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (long long)B * g.M) return;
+    const int f = (int)(w / g.M), row = (int)(w % g.M);
+    if (early_stop && done[f]) return;
+    int syn = 0;
+    for (int e = g.chk_ptr[row]; e < g.chk_ptr[row + 1]; ++e) syn ^= g.pfwd[(size_t)e * g.q + dec[(size_t)f * g.N + g.chk_var[e]]];
+    if (syn) flag[f] = 1;
+}
+
+// per frame: latch the result at the first zero syndrome (or at max_iter), as the reference returns it
+__global__ void k_finalize(int B, int N, int iter, int max_iter, int *flag, uint8_t *done, int *iters, int *conv,
+                           const uint8_t *__restrict__ dec, int *out_sym, uint8_t *newly) {
+    const int f = blockIdx.x;
+    __shared__ int latch;
+    if (threadIdx.x == 0) {
+        int l = 0;
+        if (!done[f]) {
+            const bool ok = flag[f] == 0;
+            flag[f] = 0;
+            if (ok || iter == max_iter) { done[f] = 1; conv[f] = ok ? 1 : 0; iters[f] = ok ? iter : max_iter; l = 1; }
+        }
+        newly[f] = (uint8_t)l;
+        latch = l;
+    }
+    __syncthreads();
+    if (latch)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) out_sym[(size_t)f * N + i] = dec[(size_t)f * N + i];
+}
+
+// ---- soft demapper (CComm::Demodulate, Comm.cpp:340-407); fp64 in the reference's operation order -----
+// ysym[s] = offset of symbol s's first sample in the frame's y array, or -1 when punctured
+template <typename T>
+__global__ void k_demap_bpsk(int B, int N, int q, int p, int ylen, const double *__restrict__ y, double sigma,
+                             const int *__restrict__ ysym, T *lch /*[B][N][q] or null*/, double *out /*[B][N][q-1] or null*/) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * N * q) return;
+    const int x = (int)(i % q); const size_t fs = i / q; const int s = (int)(fs % N); const size_t f = fs / N;
+    double a = 0;
+    const int off = ysym[s];
+    if (off >= 0 && x != 0)
+        for (int b = 0; b < p; ++b)
+            if (x & (1 << b)) a += -2 * y[f * ylen + off + b] / (sigma * sigma);
+    if (lch) lch[i] = (T)a;
+    if (out && x != 0) out[fs * (q - 1) + x - 1] = a;
+}
+template <typename T>
+__global__ void k_demap_qam(int B, int N, int q, int ylen, const double *__restrict__ y, const double *__restrict__ cs, double sigma,
+                            const int *__restrict__ ysym, T *lch, double *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * N * q) return;
+    const int x = (int)(i % q); const size_t fs = i / q; const int s = (int)(fs % N); const size_t f = fs / N;
+    double a = 0;
+    const int off = ysym[s];
+    if (off >= 0 && x != 0) {
+        const double yr = y[(f * ylen + off) * 2], yi = y[(f * ylen + off) * 2 + 1];
+        a = ((2 * yr - cs[0] - cs[2 * x]) * (cs[2 * x] - cs[0]) + (2 * yi - cs[1] - cs[2 * x + 1]) * (cs[2 * x + 1] - cs[1])) /
+            (2 * sigma * sigma);
+    }
+    if (lch) lch[i] = (T)a;
+    if (out && x != 0) out[fs * (q - 1) + x - 1] = a;
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+struct nbl_decoder {
+    const nbl_code *code = nullptr;
+    nbl_decoder_config cfg{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevGraph g{};
+    size_t tsz = 4;
+    // device buffers
+    int *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr, *d_ysym = nullptr;
+    uint8_t *d_pfwd = nullptr, *d_pinv = nullptr;
+    void *d_lch = nullptr, *d_v2c = nullptr, *d_c2v[2] = {nullptr, nullptr};
+    uint8_t *d_vdec = nullptr, *d_dec = nullptr, *d_done = nullptr, *d_newly = nullptr;
+    int *d_flag = nullptr, *d_iters = nullptr, *d_conv = nullptr, *d_out = nullptr;
+    double *d_stage = nullptr;   size_t stage_bytes = 0;     // staging for host LLR inputs / outputs (doubles)
+    double *d_ystage = nullptr;  size_t ystage_bytes = 0;    // staging for host received samples
+    std::vector<int> punct_cache; int punct_mod = -1, punct_ylen = 0;
+    uint8_t *d_pool = nullptr; size_t pool_cap = 0;          // codeword pool of the Monte-Carlo path
+    unsigned long long *d_counters = nullptr;
+    bool timing_pending = false;
+    double *d_cons = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0; int last_launches = 0;
+    size_t smem_iter = 0;
+};
+
+extern "C" int nbl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T> static int upload(T **dst, const std::vector<T> &src) {
+    CK(cudaMalloc((void **)dst, std::max<size_t>(1, src.size()) * sizeof(T)));
+    CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return NBL_OK;
+}
+
+static size_t smem_for(const nbl_decoder *d, int Q) {
+    const int G = Q >= 128 ? 1 : 128 / Q;
+    const int mdc = d->code->max_dc;
+    size_t per = 0;
+    const bool f64 = d->cfg.precision == NBL_PREC_F64;
+#define PER(QQ)                                                                                              \
+    if (Q == QQ) {                                                                                           \
+        if (d->cfg.method == NBL_METHOD_TEMS) per = f64 ? TemsSmem<double, QQ>::bytes(mdc, d->cfg.p1) : TemsSmem<float, QQ>::bytes(mdc, d->cfg.p1); \
+        else if (d->cfg.method == NBL_METHOD_EMS) per = f64 ? EmsSmem<double, QQ>::bytes(mdc, d->cfg.p0, d->cfg.p1) : EmsSmem<float, QQ>::bytes(mdc, d->cfg.p0, d->cfg.p1); \
+        else per = f64 ? QspaSmem<double, QQ>::bytes(mdc) : QspaSmem<float, QQ>::bytes(mdc);              \
+    }
+    PER(16) PER(32) PER(64) PER(128) PER(256)
+#undef PER
+    return per * G;
+}
+
+extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
+    if (!d) return;
+    cudaSetDevice(d->cfg.device);
+    void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_pfwd, d->d_pinv, d->d_lch, d->d_v2c,
+                    d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
+                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const nbl_decoder_config *cfg, void *stream) {
+    if (!out || !code || !cfg) { nbl_set_error("nbl_decoder_create: null argument"); return NBL_ERR_ARG; }
+    if (cfg->method != NBL_METHOD_QSPA && cfg->method != NBL_METHOD_EMS && cfg->method != NBL_METHOD_TEMS) {
+        nbl_set_error("nbl_decoder_create: decode method not supported (1 QSPA, 2 EMS, 4 T-EMS)"); return NBL_ERR_ARG;
+    }
+    if (cfg->max_iter < 1 || cfg->max_batch < 1) { nbl_set_error("nbl_decoder_create: max_iter and max_batch must be >= 1"); return NBL_ERR_ARG; }
+    if (cfg->method == NBL_METHOD_EMS && (cfg->p0 < 1 || cfg->p0 > code->q || cfg->p1 < 1)) {
+        nbl_set_error("EMS configuration error! EMS_Nm is too large!"); return NBL_ERR_ARG;   // NBLDPC.cpp:282-286
+    }
+    if (cfg->method == NBL_METHOD_TEMS && (cfg->p0 < 1 || cfg->p1 < 1)) { nbl_set_error("T-EMS needs n_r >= 1 and n_c >= 1"); return NBL_ERR_ARG; }
+    if (cfg->method == NBL_METHOD_TEMS && cfg->p1 > 2) { nbl_set_error("T-EMS n_c > 2 is not implemented yet"); return NBL_ERR_ARG; }
+    if (cfg->method != NBL_METHOD_QSPA && cfg->factor == 0.0) { nbl_set_error("correction factor must be non-zero"); return NBL_ERR_ARG; }
+    if (nbl_device_count() <= cfg->device || cfg->device < 0) { nbl_set_error("no such CUDA device (this library has no CPU fallback)"); return NBL_ERR_CUDA; }
+    CK(cudaSetDevice(cfg->device));
+    nbl_decoder *d = new nbl_decoder;
+    d->code = code; d->cfg = *cfg;
+    d->tsz = cfg->precision == NBL_PREC_F64 ? 8 : 4;
+    int rc = NBL_OK;
+    auto fail = [&](int r) { nbl_decoder_destroy(d); return r; };
+    if (stream) d->stream = (cudaStream_t)stream;
+    else { if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) { nbl_set_error("cudaStreamCreate failed"); return fail(NBL_ERR_CUDA); } d->own_stream = true; }
+    const int q = code->q, E = code->E, N = code->N;
+    // permutation tables of every edge coefficient
+    std::vector<uint8_t> pf((size_t)E * q), pi((size_t)E * q);
+    for (int e = 0; e < E; ++e) {
+        const int h = code->chk_coef[e], hi = code->inv[h];
+        for (int x = 0; x < q; ++x) { pf[(size_t)e * q + x] = (uint8_t)code->mul[h * q + x]; pi[(size_t)e * q + x] = (uint8_t)code->mul[hi * q + x]; }
+    }
+    if ((rc = upload(&d->d_chk_ptr, code->chk_ptr)) || (rc = upload(&d->d_chk_var, code->chk_var)) ||
+        (rc = upload(&d->d_var_ptr, code->var_ptr)) || (rc = upload(&d->d_var_edge, code->var_edge)) ||
+        (rc = upload(&d->d_pfwd, pf)) || (rc = upload(&d->d_pinv, pi)))
+        return fail(rc);
+    d->g = DevGraph{q, code->p, N, code->M, E, code->max_dv, code->max_dc, d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_pfwd, d->d_pinv};
+    const size_t B = cfg->max_batch;
+#define ALLOC(ptr, bytes) if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { cudaGetLastError(); nbl_set_error("cudaMalloc failed for the decoder workspace"); return fail(NBL_ERR_ALLOC); }
+    ALLOC(d->d_lch, B * N * q * d->tsz);
+    ALLOC(d->d_v2c, B * E * q * d->tsz);
+    ALLOC(d->d_c2v[0], B * E * q * d->tsz);
+    ALLOC(d->d_c2v[1], B * E * q * d->tsz);
+    ALLOC(d->d_vdec, B * E); ALLOC(d->d_dec, B * N); ALLOC(d->d_done, B); ALLOC(d->d_newly, B);
+    ALLOC(d->d_flag, B * sizeof(int)); ALLOC(d->d_iters, B * sizeof(int)); ALLOC(d->d_conv, B * sizeof(int));
+    ALLOC(d->d_out, B * N * sizeof(int));
+    ALLOC(d->d_ysym, N * sizeof(int));
+    ALLOC(d->d_cons, 2 * q * sizeof(double));
+#undef ALLOC
+    if (cudaEventCreate(&d->ev0) != cudaSuccess || cudaEventCreate(&d->ev1) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
+    d->smem_iter = smem_for(d, q);
+    if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
+    *out = d;
+    return NBL_OK;
+}
+
+extern "C" void *nbl_decoder_stream(nbl_decoder *d) { return d ? (void *)d->stream : nullptr; }
+extern "C" int nbl_decoder_sync(nbl_decoder *d) {
+    if (!d) { nbl_set_error("null decoder"); return NBL_ERR_ARG; }
+    CK(cudaSetDevice(d->cfg.device));
+    CK(cudaStreamSynchronize(d->stream));
+    return NBL_OK;
+}
+extern "C" int nbl_decoder_last_timing(nbl_decoder *d, float *ms, int *launches) {
+    if (!d) { nbl_set_error("null decoder"); return NBL_ERR_ARG; }
+    if (d->timing_pending) {
+        CK(cudaSetDevice(d->cfg.device));
+        CK(cudaEventSynchronize(d->ev1));
+        CK(cudaEventElapsedTime(&d->last_ms, d->ev0, d->ev1));
+        d->timing_pending = false;
+    }
+    if (ms) *ms = d->last_ms;
+    if (launches) *launches = d->last_launches;
+    return NBL_OK;
+}
+
+static int ensure_buf(double **buf, size_t *have, size_t bytes) {
+    if (*have >= bytes) return NBL_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *have = 0;
+    if (cudaMalloc((void **)buf, bytes) != cudaSuccess) { cudaGetLastError(); nbl_set_error("cudaMalloc failed for a staging buffer"); return NBL_ERR_ALLOC; }
+    *have = bytes;
+    return NBL_OK;
+}
+static int ensure_stage(nbl_decoder *d, size_t bytes) { return ensure_buf(&d->d_stage, &d->stage_bytes, bytes); }
+static int ensure_ystage(nbl_decoder *d, size_t bytes) { return ensure_buf(&d->d_ystage, &d->ystage_bytes, bytes); }
+
+// ---- launch helpers (dispatch on precision, field size, method) ------------------------------------
+template <typename T, int Q, int METHOD> static int launch_iterate_tqm(nbl_decoder *d, const IterParams<T> &P) {
+    auto kern = k_iterate<T, Q, METHOD>;
+    if (d->smem_iter > 48 * 1024)
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem_iter));
+    const long long groups = (long long)P.B * P.g.M;
+    const unsigned grid = (unsigned)((groups + Grp<Q>::G - 1) / Grp<Q>::G);
+    kern<<<grid, Grp<Q>::THREADS, d->smem_iter, d->stream>>>(P);
+    CK(cudaGetLastError());
+    return NBL_OK;
+}
+template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const IterParams<T> &P) {
+    switch (d->cfg.method) {
+        case NBL_METHOD_TEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_TEMS>(d, P);
+        case NBL_METHOD_EMS: return launch_iterate_tqm<T, Q, NBL_METHOD_EMS>(d, P);
+        default: return launch_iterate_tqm<T, Q, NBL_METHOD_QSPA>(d, P);
+    }
+}
+template <typename T, int Q> static int launch_posterior_tq(nbl_decoder *d, int B, int first, const T *c2v_in, double *post_out, const uint8_t *sel) {
+    const long long groups = (long long)B * d->g.N;
+    const unsigned grid = (unsigned)((groups + Grp<Q>::G - 1) / Grp<Q>::G);
+    k_posterior<T, Q><<<grid, Grp<Q>::THREADS, 0, d->stream>>>(d->g, B, first, d->cfg.early_stop, (const T *)d->d_lch, c2v_in, d->d_done,
+                                                               d->d_dec, post_out, sel);
+    CK(cudaGetLastError());
+    return NBL_OK;
+}
+#define DISPATCH_Q(q, CALL)                                                                           \
+    switch (q) {                                                                                      \
+        case 16: { constexpr int QQ = 16; CALL; } break;                                              \
+        case 32: { constexpr int QQ = 32; CALL; } break;                                              \
+        case 64: { constexpr int QQ = 64; CALL; } break;                                              \
+        case 128: { constexpr int QQ = 128; CALL; } break;                                            \
+        case 256: { constexpr int QQ = 256; CALL; } break;                                            \
+        default: nbl_set_error("unsupported field size"); return NBL_ERR_ARG;                         \
+    }
+
+// Runs the iterations on the frames whose channel LLRs are already in d_lch.  Results stay on the device
+// (d_out, d_conv, d_iters); post_dev (device doubles) is optional.
+template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_dev) {
+    const nbl_decoder_config &c = d->cfg;
+    const int q = d->g.q;
+    d->last_launches = 0;
+    CK(cudaMemsetAsync(d->d_flag, 0, (size_t)B * sizeof(int), d->stream));
+    CK(cudaMemsetAsync(d->d_done, 0, (size_t)B, d->stream));
+    CK(cudaEventRecord(d->ev0, d->stream));
+    T w_old = 0, w_new = 1;
+    if (c.method == NBL_METHOD_QSPA) { w_old = (T)0.5; w_new = (T)0.5; }          // NBLDPC.cpp:739
+    if (c.method == NBL_METHOD_TEMS) { w_old = (T)0.25; w_new = (T)0.75; }        // NBLDPC.cpp:1046
+    for (int it = 1; it <= c.max_iter; ++it) {
+        const T *cin = (const T *)d->d_c2v[(it - 1) & 1];
+        T *cout = (T *)d->d_c2v[it & 1];
+        int rc;
+        if (it < c.max_iter) {
+            IterParams<T> P;
+            P.g = d->g; P.B = B; P.iter = it; P.first = it == 1; P.early_stop = c.early_stop; P.method = c.method;
+            P.p0 = c.p0; P.p1 = c.p1; P.factor = (T)c.factor; P.offset = (T)c.offset; P.w_old = w_old; P.w_new = w_new;
+            P.lch = (const T *)d->d_lch; P.v2c = (T *)d->d_v2c; P.c2v_in = cin; P.c2v_out = cout;
+            P.vdec = d->d_vdec; P.dec = d->d_dec; P.flag = d->d_flag; P.done = d->d_done;
+            DISPATCH_Q(q, rc = (launch_iterate_tq<T, QQ>(d, P)));
+            if (rc) return rc;
+            d->last_launches += 1;
+        } else {      // last iteration: the reference's final check-node pass cannot change any output
+            DISPATCH_Q(q, rc = (launch_posterior_tq<T, QQ>(d, B, it == 1, cin, nullptr, nullptr)));
+            if (rc) return rc;
+            const long long rows = (long long)B * d->g.M;
+            k_syndrome<<<(unsigned)((rows + 255) / 256), 256, 0, d->stream>>>(d->g, B, c.early_stop, d->d_done, d->d_dec, d->d_flag);
+            CK(cudaGetLastError());
+            d->last_launches += 2;
+        }
+        k_finalize<<<B, 64, 0, d->stream>>>(B, d->g.N, it, c.max_iter, d->d_flag, d->d_done, d->d_iters, d->d_conv, d->d_dec, d->d_out, d->d_newly);
+        CK(cudaGetLastError());
+        d->last_launches += 1;
+        if (post_dev) {
+            DISPATCH_Q(q, rc = (launch_posterior_tq<T, QQ>(d, B, it == 1, cin, post_dev, d->d_newly)));
+            if (rc) return rc;
+            d->last_launches += 1;
+        }
+    }
+    CK(cudaEventRecord(d->ev1, d->stream));
+    d->timing_pending = true;
+    return NBL_OK;
+}
+
+// copies an int result array to the caller (host or device pointer)
+static int give_ints(nbl_decoder *d, int *dst, const int *src_dev, size_t n) {
+    if (!dst) return NBL_OK;
+    CK(cudaMemcpyAsync(dst, src_dev, n * sizeof(int), is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, d->stream));
+    return NBL_OK;
+}
+
+static int decode_common(nbl_decoder *d, int B, int *out_sym, int *converged, int *iterations, double *L_post) {
+    const size_t nvec = (size_t)B * d->g.N, q1 = d->g.q - 1;
+    double *post_dev = nullptr;
+    int rc;
+    if (L_post) {
+        if (is_device_ptr(L_post)) post_dev = L_post;
+        else { if ((rc = ensure_stage(d, nvec * q1 * sizeof(double)))) return rc; post_dev = d->d_stage; }
+    }
+    rc = d->cfg.precision == NBL_PREC_F64 ? run_decode<double>(d, B, post_dev) : run_decode<float>(d, B, post_dev);
+    if (rc) return rc;
+    if ((rc = give_ints(d, out_sym, d->d_out, nvec)) || (rc = give_ints(d, converged, d->d_conv, B)) || (rc = give_ints(d, iterations, d->d_iters, B))) return rc;
+    if (L_post && post_dev != L_post) CK(cudaMemcpyAsync(L_post, post_dev, nvec * q1 * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+    const bool any_host = (out_sym && !is_device_ptr(out_sym)) || (converged && !is_device_ptr(converged)) ||
+                          (iterations && !is_device_ptr(iterations)) || (L_post && !is_device_ptr(L_post));
+    if (any_host) CK(cudaStreamSynchronize(d->stream));
+    return NBL_OK;
+}
+
+extern "C" int nbl_decode_batch(nbl_decoder *d, const double *L_ch, int B, int *out_sym, int *converged, int *iterations, double *L_post) {
+    if (!d || !L_ch || !out_sym) { nbl_set_error("nbl_decode_batch: null argument"); return NBL_ERR_ARG; }
+    if (B < 0 || B > d->cfg.max_batch) { nbl_set_error("nbl_decode_batch: B exceeds max_batch"); return NBL_ERR_ARG; }
+    if (B == 0) return NBL_OK;
+    CK(cudaSetDevice(d->cfg.device));
+    const size_t nvec = (size_t)B * d->g.N, q = d->g.q;
+    const double *src = L_ch;
+    int rc;
+    if (!is_device_ptr(L_ch)) {
+        if ((rc = ensure_stage(d, nvec * (q - 1) * sizeof(double)))) return rc;
+        CK(cudaMemcpyAsync(d->d_stage, L_ch, nvec * (q - 1) * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        src = d->d_stage;
+    }
+    const size_t tot = nvec * q;
+    if (d->cfg.precision == NBL_PREC_F64) k_convert_lch<double><<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(src, (double *)d->d_lch, nvec, (int)q);
+    else k_convert_lch<float><<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(src, (float *)d->d_lch, nvec, (int)q);
+    CK(cudaGetLastError());
+    return decode_common(d, B, out_sym, converged, iterations, L_post);
+}
+
+// ---- front end -------------------------------------------------------------------------------------
+static int setup_punct(nbl_decoder *d, int modulation, const int *punct_sym, int n_punct, int *ylen) {
+    const int N = d->g.N, per = modulation == 2 ? d->g.p : 1;
+    std::vector<int> ys(N);
+    std::vector<char> isp(N, 0);
+    for (int i = 0; i < n_punct; ++i) {
+        if (!punct_sym || punct_sym[i] < 0 || punct_sym[i] >= N) { nbl_set_error("bad puncture list"); return NBL_ERR_ARG; }
+        isp[punct_sym[i]] = 1;
+    }
+    int off = 0;
+    for (int s = 0; s < N; ++s) { if (isp[s]) ys[s] = -1; else { ys[s] = off; off += per; } }
+    *ylen = off;
+    if (d->punct_mod == modulation && d->punct_cache == ys) return NBL_OK;      // layout already on the device
+    CK(cudaMemcpyAsync(d->d_ysym, ys.data(), N * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    CK(cudaStreamSynchronize(d->stream));     // ys is a local
+    d->punct_cache = ys; d->punct_mod = modulation; d->punct_ylen = off;
+    return NBL_OK;
+}
+
+// demap into d_lch (T) and/or a double output
+static int demap_common(nbl_decoder *d, int modulation, const double *y, int B, const double *constellation, double sigma,
+                        const int *punct_sym, int n_punct, bool to_lch, double *out_dev) {
+    const int N = d->g.N, q = d->g.q;
+    if (modulation != 2 && modulation != q) {
+        nbl_set_error("This module ( code order ~= modulation order ) haven't been developed!");   // Comm.cpp:400-405
+        return NBL_ERR_ARG;
+    }
+    if (!(sigma > 0)) { nbl_set_error("sigma must be positive"); return NBL_ERR_ARG; }
+    int ylen, rc;
+    if ((rc = setup_punct(d, modulation, punct_sym, n_punct, &ylen))) return rc;
+    const size_t ydbl = (size_t)B * ylen * (modulation == 2 ? 1 : 2);
+    const double *ysrc = y;
+    if (!is_device_ptr(y)) {
+        if ((rc = ensure_ystage(d, ydbl * sizeof(double)))) return rc;
+        CK(cudaMemcpyAsync(d->d_ystage, y, ydbl * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        ysrc = d->d_ystage;
+    }
+    if (modulation != 2) {
+        if (!constellation) { nbl_set_error("QAM demapping needs a constellation"); return NBL_ERR_ARG; }
+        CK(cudaMemcpyAsync(d->d_cons, constellation, 2 * q * sizeof(double), is_device_ptr(constellation) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d->stream));
+    }
+    const size_t tot = (size_t)B * N * q;
+    const unsigned grid = (unsigned)((tot + 255) / 256);
+    const bool f64 = d->cfg.precision == NBL_PREC_F64;
+    if (modulation == 2) {
+        if (f64) k_demap_bpsk<double><<<grid, 256, 0, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
+        else k_demap_bpsk<float><<<grid, 256, 0, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
+    } else {
+        if (f64) k_demap_qam<double><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
+        else k_demap_qam<float><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
+    }
+    CK(cudaGetLastError());
+    return NBL_OK;
+}
+
+static int demap_api(nbl_decoder *d, int modulation, const double *y, int B, const double *cons, double sigma, const int *ps, int np, double *L_ch) {
+    if (!d || !y || !L_ch) { nbl_set_error("nbl_demap: null argument"); return NBL_ERR_ARG; }
+    if (B < 0 || B > d->cfg.max_batch) { nbl_set_error("nbl_demap: B exceeds max_batch"); return NBL_ERR_ARG; }
+    if (B == 0) return NBL_OK;
+    CK(cudaSetDevice(d->cfg.device));
+    const size_t out_bytes = (size_t)B * d->g.N * (d->g.q - 1) * sizeof(double);
+    const bool host_out = !is_device_ptr(L_ch);
+    int rc;
+    if (host_out && (rc = ensure_stage(d, out_bytes))) return rc;
+    rc = demap_common(d, modulation, y, B, cons, sigma, ps, np, false, host_out ? d->d_stage : L_ch);
+    if (rc) return rc;
+    if (host_out) {
+        CK(cudaMemcpyAsync(L_ch, d->d_stage, out_bytes, cudaMemcpyDeviceToHost, d->stream));
+        CK(cudaStreamSynchronize(d->stream));
+    }
+    return NBL_OK;
+}
+extern "C" int nbl_demap_bpsk(nbl_decoder *d, const double *y_re, int B, double sigma, const int *ps, int np, double *L_ch) {
+    return demap_api(d, 2, y_re, B, nullptr, sigma, ps, np, L_ch);
+}
+extern "C" int nbl_demap_qam(nbl_decoder *d, const double *y, int B, const double *cons, double sigma, const int *ps, int np, double *L_ch) {
+    if (!d) { nbl_set_error("null decoder"); return NBL_ERR_ARG; }
+    return demap_api(d, d->g.q, y, B, cons, sigma, ps, np, L_ch);
+}
+
+extern "C" int nbl_demap_decode_batch(nbl_decoder *d, int modulation, const double *y, int B, const double *cons, double sigma,
+                                      const int *ps, int np, int *out_sym, int *converged, int *iterations) {
+    if (!d || !y || !out_sym) { nbl_set_error("nbl_demap_decode_batch: null argument"); return NBL_ERR_ARG; }
+    if (B < 0 || B > d->cfg.max_batch) { nbl_set_error("nbl_demap_decode_batch: B exceeds max_batch"); return NBL_ERR_ARG; }
+    if (B == 0) return NBL_OK;
+    CK(cudaSetDevice(d->cfg.device));
+    int rc = demap_common(d, modulation, y, B, cons, sigma, ps, np, true, nullptr);
+    if (rc) return rc;
+    return decode_common(d, B, out_sym, converged, iterations, nullptr);
+}
+
+// ======================================================================================================
+// device Monte-Carlo: source -> map -> AWGN -> demap -> decode -> error counters
+// (the frame loop of the reference's main.cpp:43-55 with CComm::Transmission / CComm::Err per frame)
+// ======================================================================================================
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: the noise of a frame depends only on
+// (seed, global frame index, sample index), never on batch size, stream or GPU.
+__device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// two independent N(0,1) from one Philox block (Box-Muller, 53-bit radius uniform => tails to ~8.5 sigma)
+__device__ inline void normal_pair(uint64_t seed, uint64_t frame, uint32_t idx, double &z0, double &z1) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), idx, 0x4E424Cu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u1 = ((double)((((uint64_t)r[0] << 32) | r[1]) >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0,1]
+    const double u2 = (double)((((uint64_t)r[2] << 32) | r[3]) >> 11) * (1.0 / 9007199254740992.0);          // [0,1)
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = rad * c; z1 = rad * s;
+}
+
+// received samples of B frames.  BPSK: y[f][N*p] = (1 - 2 bit) + sigma n  (0 -> +1, 1 -> -1, BPSK.txt; bit b of
+// symbol s is sample s*p+b, Comm.cpp:272-279).  QAM: y[f][N][2] = constellation[symbol] + sigma (n_re, n_im).
+__global__ void k_sim_channel(int B, int N, int p, int modulation, uint64_t seed, uint64_t first_frame, double sigma,
+                              const uint8_t *__restrict__ pool, int n_pool, const double *__restrict__ cs, double *__restrict__ y) {
+    const int per = modulation == 2 ? (N * p + 1) / 2 : N;          // Philox blocks per frame (2 normals each)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * per) return;
+    const int f = (int)(i / per), j = (int)(i % per);
+    const uint64_t gf = first_frame + (uint64_t)f;
+    const uint8_t *cw = n_pool ? pool + (size_t)(gf % (uint64_t)n_pool) * N : nullptr;
+    double z0, z1;
+    normal_pair(seed, gf, (uint32_t)j, z0, z1);
+    if (modulation == 2) {
+        const int L = N * p;
+        for (int h = 0; h < 2; ++h) {
+            const int b = 2 * j + h;
+            if (b >= L) break;
+            const int bit = cw ? (cw[b / p] >> (b % p)) & 1 : 0;
+            y[(size_t)f * L + b] = (bit ? -1.0 : 1.0) + sigma * (h ? z1 : z0);
+        }
+    } else {
+        const int sym = cw ? cw[j] : 0;
+        y[((size_t)f * N + j) * 2] = cs[2 * sym] + sigma * z0;
+        y[((size_t)f * N + j) * 2 + 1] = cs[2 * sym + 1] + sigma * z1;
+    }
+}
+
+// CComm::Err (Comm.cpp:446-503) per frame on the first K symbols, accumulated into uint64 counters
+__global__ void k_sim_count(int B, int N, int K, uint64_t first_frame, const uint8_t *__restrict__ pool, int n_pool,
+                            const int *__restrict__ out_sym, const int *__restrict__ conv, const int *__restrict__ iters,
+                            unsigned long long *counters) {
+    __shared__ unsigned long long acc[NBL_NUM_COUNTERS];
+    if (threadIdx.x < NBL_NUM_COUNTERS) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < B) {
+        const uint64_t gf = first_frame + (uint64_t)f;
+        const uint8_t *cw = n_pool ? pool + (size_t)(gf % (uint64_t)n_pool) * N : nullptr;
+        int es = 0, eb = 0;
+        for (int s = 0; s < K; ++s) {
+            const int diff = out_sym[(size_t)f * N + s] ^ (cw ? cw[s] : 0);
+            es += diff != 0; eb += __popc(diff);
+        }
+        atomicAdd(&acc[NBL_CNT_FRAMES], 1ULL);
+        if (es) { atomicAdd(&acc[NBL_CNT_ERR_FRAMES], 1ULL); atomicAdd(&acc[NBL_CNT_ERR_SYMS], (unsigned long long)es); atomicAdd(&acc[NBL_CNT_ERR_BITS], (unsigned long long)eb); }
+        if (conv[f]) atomicAdd(&acc[NBL_CNT_CONVERGED], 1ULL);
+        if (conv[f] && es) atomicAdd(&acc[NBL_CNT_UNDETECTED], 1ULL);
+        atomicAdd(&acc[NBL_CNT_ITERATIONS], (unsigned long long)iters[f]);
+    }
+    __syncthreads();
+    if (threadIdx.x < NBL_NUM_COUNTERS && acc[threadIdx.x]) atomicAdd(&counters[threadIdx.x], acc[threadIdx.x]);
+}
+
+static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned long long *dev_counters) {
+    const int N = d->g.N, q = d->g.q, p = d->g.p, K = N - d->g.M;
+    if (cfg->modulation != 2 && cfg->modulation != q) {
+        nbl_set_error("This module ( code order ~= modulation order ) haven't been developed!"); return NBL_ERR_ARG;
+    }
+    if (cfg->modulation != 2 && !cfg->constellation) { nbl_set_error("nbl_simulate: QAM needs a constellation"); return NBL_ERR_ARG; }
+    if (cfg->n_codewords < 0 || (cfg->n_codewords > 0 && !cfg->codewords)) { nbl_set_error("nbl_simulate: bad codeword pool"); return NBL_ERR_ARG; }
+    const double mbits = cfg->modulation == 2 ? 1.0 : (double)p;
+    const double rate = (double)K / (double)N;
+    const double sigma = 1.0 / sqrt(2.0 * mbits * rate * pow(10.0, cfg->ebn0_db / 10.0));      // Comm.cpp:176-177
+    int rc, ylen;
+    if ((rc = setup_punct(d, cfg->modulation, nullptr, 0, &ylen))) return rc;
+    // codeword pool -> device bytes
+    if (cfg->n_codewords) {
+        const size_t n = (size_t)cfg->n_codewords * N;
+        if (d->pool_cap < n) { if (d->d_pool) cudaFree(d->d_pool); d->d_pool = nullptr; CK(cudaMalloc((void **)&d->d_pool, n)); d->pool_cap = n; }
+        std::vector<uint8_t> bytes(n);
+        for (size_t i = 0; i < n; ++i) {
+            if (cfg->codewords[i] < 0 || cfg->codewords[i] >= q) { nbl_set_error("nbl_simulate: codeword symbol out of range"); return NBL_ERR_ARG; }
+            bytes[i] = (uint8_t)cfg->codewords[i];
+        }
+        CK(cudaMemcpyAsync(d->d_pool, bytes.data(), n, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaStreamSynchronize(d->stream));
+    }
+    if (cfg->modulation != 2) CK(cudaMemcpyAsync(d->d_cons, cfg->constellation, 2 * q * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    const size_t ydbl = (size_t)d->cfg.max_batch * ylen * (cfg->modulation == 2 ? 1 : 2);
+    if ((rc = ensure_ystage(d, ydbl * sizeof(double)))) return rc;
+    float ms_total = 0; int launches = 0;
+    for (uint64_t done = 0; done < cfg->frames;) {
+        const int B = (int)std::min<uint64_t>(d->cfg.max_batch, cfg->frames - done);
+        const int per = cfg->modulation == 2 ? (N * p + 1) / 2 : N;
+        const long long nthr = (long long)B * per;
+        k_sim_channel<<<(unsigned)((nthr + 255) / 256), 256, 0, d->stream>>>(B, N, p, cfg->modulation, cfg->seed, cfg->first_frame + done, sigma,
+                                                                            d->d_pool, cfg->n_codewords, d->d_cons, d->d_ystage);
+        CK(cudaGetLastError());
+        if ((rc = demap_common(d, cfg->modulation, d->d_ystage, B, d->d_cons, sigma, nullptr, 0, true, nullptr))) return rc;
+        rc = d->cfg.precision == NBL_PREC_F64 ? run_decode<double>(d, B, nullptr) : run_decode<float>(d, B, nullptr);
+        if (rc) return rc;
+        k_sim_count<<<(B + 127) / 128, 128, 0, d->stream>>>(B, N, K, cfg->first_frame + done, d->d_pool, cfg->n_codewords, d->d_out, d->d_conv,
+                                                           d->d_iters, dev_counters);
+        CK(cudaGetLastError());
+        launches += d->last_launches + 3;
+        done += B;
+        (void)ms_total;
+    }
+    d->last_launches = launches;
+    return NBL_OK;
+}
+
+extern "C" int nbl_simulate_async(nbl_decoder *d, const nbl_sim_config *cfg, uint64_t *dev_counters) {
+    if (!d || !cfg || !dev_counters) { nbl_set_error("nbl_simulate_async: null argument"); return NBL_ERR_ARG; }
+    if (!is_device_ptr(dev_counters)) { nbl_set_error("nbl_simulate_async: counters must be device memory"); return NBL_ERR_ARG; }
+    CK(cudaSetDevice(d->cfg.device));
+    return simulate_impl(d, cfg, (unsigned long long *)dev_counters);
+}
+
+extern "C" int nbl_simulate(nbl_decoder *d, const nbl_sim_config *cfg, uint64_t *counters) {
+    if (!d || !cfg || !counters) { nbl_set_error("nbl_simulate: null argument"); return NBL_ERR_ARG; }
+    CK(cudaSetDevice(d->cfg.device));
+    if (!d->d_counters) CK(cudaMalloc((void **)&d->d_counters, NBL_NUM_COUNTERS * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d->d_counters, 0, NBL_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
+    int rc = simulate_impl(d, cfg, d->d_counters);
+    if (rc) return rc;
+    unsigned long long host[NBL_NUM_COUNTERS];
+    CK(cudaMemcpyAsync(host, d->d_counters, sizeof host, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    for (int i = 0; i < NBL_NUM_COUNTERS; ++i) counters[i] += host[i];
+    return NBL_OK;
+}

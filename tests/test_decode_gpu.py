@@ -1,0 +1,127 @@
+"""GPU parity tests proper: the CUDA decode path, called through the C ABI, against the golden vectors dumped
+from the real reference and against the C oracle on the same inputs."""
+import numpy as np
+import pytest
+
+from conftest import golden_lch, golden_names, load_golden, load_product_code
+
+pytestmark = pytest.mark.gpu
+
+
+def _decoder(code, meta, precision, max_batch, early_stop=1):
+    from nbldpc_b200 import capi
+    return capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                        precision=precision, early_stop=early_stop, max_batch=max_batch)
+
+
+def _post_tolerance(meta):
+    # QSPA runs as a Walsh-Hadamard transform in the probability domain: entries whose probability is below the
+    # fp64 noise floor of the transform saturate, so only the reliable part is compared tightly.
+    return 1e-6 if meta["method"] == 1 else 1e-8
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp64_matches_reference_decisions_and_iterations(name, code_files):
+    """fp64 parity mode: return code, iteration count and every hard decision bit-exact with the reference."""
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    F = len(z["ret"])
+    dec = _decoder(code, meta, capi.PREC_F64, F)
+    lch = golden_lch(z, meta)
+    r = dec.decode(lch, want_post=True)
+    assert np.array_equal(r["converged"], z["ret"].astype(np.int32))
+    assert np.array_equal(r["iterations"], z["iters"].astype(np.int32))
+    assert np.array_equal(r["sym"], z["dec_sym"].astype(np.int32))
+    got = r["post"][:, :, z["lpost_idx"]]
+    ref = z["lpost_sample"]
+    sel = ref > -25.0 if meta["method"] == 1 else np.ones_like(ref, bool)
+    err = np.abs(got - ref)[sel] / np.maximum(np.abs(ref[sel]), 1.0)
+    assert err.max() < _post_tolerance(meta), err.max()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp32_fast_mode_within_tolerance(name, code_files):
+    """fp32 fast mode: posterior LLRs within 1e-4 relative (|d| <= 1e-4 * max(|ref|, 1)) on frames whose
+    decisions agree; decisions agree on (almost) every frame -- fp32 rounding may flip a near-tie."""
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    F = len(z["ret"])
+    dec = _decoder(code, meta, capi.PREC_F32, F)
+    r = dec.decode(golden_lch(z, meta), want_post=True)
+    same = (r["iterations"] == z["iters"]) & (r["converged"] == z["ret"]) & (r["sym"] == z["dec_sym"]).all(axis=1)
+    assert same.mean() >= 0.8, same
+    got = r["post"][:, :, z["lpost_idx"]][same]
+    ref = z["lpost_sample"][same]
+    sel = ref > -25.0 if meta["method"] == 1 else np.ones_like(ref, bool)
+    err = np.abs(got - ref)[sel] / np.maximum(np.abs(ref[sel]), 1.0)
+    assert err.max() < 1e-4, err.max()
+
+
+@pytest.mark.parametrize("name", ["cfg5_tems_hbit256", "cfg2_ems_gf64", "cfg1_qspa_gf16"])
+def test_no_early_stop_gives_same_outputs(name, code_files):
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    F = len(z["ret"])
+    lch = golden_lch(z, meta)
+    a = _decoder(code, meta, capi.PREC_F64, F, early_stop=1).decode(lch)
+    b = _decoder(code, meta, capi.PREC_F64, F, early_stop=0).decode(lch)
+    for k in ("sym", "converged", "iterations"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_batch_of_one_and_ragged_batches(code_files):
+    """B = 1 (the reference's own call shape) and batches smaller than max_batch give identical results."""
+    from nbldpc_b200 import capi
+    z, meta = load_golden("cfg5_tems_hbit256")
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)
+    dec = _decoder(code, meta, capi.PREC_F64, 7)
+    for lo in range(0, len(lch), 7):
+        r = dec.decode(lch[lo:lo + 7])
+        assert np.array_equal(r["sym"], z["dec_sym"][lo:lo + 7])
+    one = _decoder(code, meta, capi.PREC_F64, 1).decode(lch[3:4])
+    assert one["iterations"][0] == z["iters"][3]
+
+
+def test_demapper_bit_exact(code_files):
+    """device soft demapper == reference demapper (fp64, same operation order) for BPSK and 256-QAM"""
+    from nbldpc_b200 import capi
+    from conftest import constellation
+    for name in ("cfg3_tems_gf256", "cfg4_qspa_gf256_qam", "cfg1_qspa_gf16"):
+        z, meta = load_golden(name)
+        code = load_product_code(code_files, meta["code"])
+        F = min(4, len(z["ret"]))
+        dec = _decoder(code, meta, capi.PREC_F64, F)
+        want = golden_lch(z, meta, F)
+        if meta["nqam"] == 2:
+            got = dec.demap_bpsk(z["rx"][:F, :, 0], meta["sigma"])
+        else:
+            got = dec.demap_qam(z["rx"][:F], constellation(meta["constellation"]), meta["sigma"])
+        assert np.array_equal(got, want), name
+        assert np.allclose(got.sum(axis=2), z["lch_sum"][:F], rtol=0, atol=1e-9)
+
+
+def test_fused_demap_decode_equals_two_step(code_files):
+    from nbldpc_b200 import capi
+    z, meta = load_golden("cfg3_tems_gf256")
+    code = load_product_code(code_files, meta["code"])
+    F = len(z["ret"])
+    dec = _decoder(code, meta, capi.PREC_F64, F)
+    r = dec.demap_decode(2, z["rx"][:, :, 0], meta["sigma"])
+    assert np.array_equal(r["sym"], z["dec_sym"])
+    assert np.array_equal(r["iterations"], z["iters"])
+
+
+def test_noiseless_all_zero_returns_at_iteration_one(code_files):
+    """SURVEY section 4 fixture 7: all-zero codeword + noiseless LLRs => converged at iteration 1, all-zero output"""
+    from nbldpc_b200 import capi
+    for code_name, method, p0, p1 in [("divsalar.UNBLDPC.128.64.GF.16", 1, 0, 0), ("BDS.576.288.GF.64", 2, 8, 3),
+                                      ("divsalar.UNBLDPC.512.256.GF.256", 4, 2, 2)]:
+        code = load_product_code(code_files, code_name)
+        lch = np.full((2, code.N, code.q - 1), -10.0)
+        dec = capi.Decoder(code, method, 10, p0, p1, 1.0, 0.5, precision=capi.PREC_F32, max_batch=2)
+        r = dec.decode(lch)
+        assert (r["sym"] == 0).all() and (r["converged"] == 1).all() and (r["iterations"] == 1).all()
