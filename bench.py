@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline benchmark: decoded Mbit/s, GF(256) (512,256) T-EMS @ 10 iterations, BPSK/AWGN, random codewords.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (B200, CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU decoder on the host cores
+
+Our arm.  One process per GPU (torchrun for N > 1).  A STEP is one pass of the hot path over one batch of
+`--frames` synthetic frames:
+  value : device Monte-Carlo step (nbl_simulate_async): Philox AWGN on a resident codeword pool -> soft demapper
+          -> 10 fixed T-EMS iterations (early stop OFF, every frame pays all 10) -> error counters in HBM.
+          Nothing crosses PCIe inside the timed region.  N > 1: frames are sharded by global frame index
+          (weak scaling), no data-path collective; the 8 x u64 counter vector is all-reduced (NCCL) once at the
+          end of the timed region.
+  e2e   : the reference-facing call with HOST buffers (nbl_demap_decode_batch, the batched drop-in for
+          CComm::Demodulate + CNBLDPC::Decoding): received samples in pinned host memory -> H2D -> demap ->
+          10 fixed iterations -> hard decisions, return codes and iteration counts D2H, every step.
+Timing: CUDA events on the launching stream (the decoder launches on torch's current stream), barrier +
+synchronize on both sides, max over ranks.  The message working set of one step (~0.45 MB per frame, GBs per
+batch) is far larger than the 126 MB L2, so every launch streams from HBM.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CODE = "divsalar.UNBLDPC.512.256.GF.256"
+EBN0_DB = 2.5
+TEMS = dict(method=4, max_iter=10, p0=2, p1=2, factor=1.0, offset=0.5)
+METRIC = "decoded Mbit/s per GPU & 8xB200, GF(256) (512,256) T-EMS @10 iters"
+WORKLOAD = "configs[2]: %s T-EMS n_r=2 n_c=2 offset 0.5, BPSK AWGN Eb/N0 %.1f dB, random codewords" % (CODE, EBN0_DB)
+
+
+# ------------------------------------------------------------------------------------------------------
+def bundle_code_text(name):
+    """the code in the reference's text format, from the committed bundle (no /root/reference at run time)"""
+    c = json.load(open(os.path.join(ROOT, "tests", "golden", "codes.json")))["codes"][name]
+    out = ["%d %d %d" % (c["N"], c["M"], c["q"]), "%d %d" % (max(map(len, c["var"])), max(map(len, c["chk"])))]
+    out.append(" ".join(str(len(l)) for l in c["var"]) + " ")
+    out.append(" ".join(str(len(l)) for l in c["chk"]) + " ")
+    for l in c["var"]:
+        out.append(" ".join("%d %d" % (r + 1, g) for r, g in l) + " ")
+    for l in c["chk"]:
+        out.append(" ".join("%d %d" % (v + 1, g) for v, g in l) + " ")
+    return "\n".join(out) + "\n"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        smax = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax[0] if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def reference_run(threads, frames_per_thread, workdir):
+    """the UNMODIFIED reference decoder (oracle/_ref/ref_bench) on `threads` host cores; returns its JSON"""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    exe = os.path.join(ref, "ref_bench")
+    if not os.path.exists(exe):
+        return None
+    os.makedirs(workdir, exist_ok=True)
+    for f in os.listdir(os.path.join(ref, "data")):
+        dst = os.path.join(workdir, f)
+        if not os.path.lexists(dst):
+            os.symlink(os.path.join(ref, "data", f), dst)
+    from oracle.refprofile import profile_text
+    prof = profile_text(dict(GFq=256, code_file=CODE + ".txt", method=4, snr=EBN0_DB, random_msg=1, parallel=threads))
+    open(os.path.join(workdir, "prof.txt"), "w").write(prof)
+    out = subprocess.run([exe, "prof.txt", str(threads), str(frames_per_thread)], cwd=workdir, capture_output=True, text=True, timeout=1200)
+    for line in out.stdout.splitlines():
+        if line.startswith("{"):
+            return json.loads(line)
+    return None
+
+
+def port_run(frames):
+    """fallback CPU baseline: the C oracle (single thread) on `frames` frames of the same workload"""
+    import numpy as np
+    from oracle import pyoracle as po
+    c = json.load(open(os.path.join(ROOT, "tests", "golden", "codes.json")))["codes"][CODE]
+    code = dict(N=c["N"], M=c["M"], q=c["q"], vdeg=[len(l) for l in c["var"]], cdeg=[len(l) for l in c["chk"]],
+                var=[[tuple(e) for e in l] for l in c["var"]], chk=[[tuple(e) for e in l] for l in c["chk"]])
+    oc = po.OracleCode(code)
+    rng = np.random.RandomState(1)
+    sigma = 1.0 / np.sqrt(2 * 0.5 * 10 ** (EBN0_DB / 10))
+    t = 0.0
+    for _ in range(frames):
+        y = 1.0 + sigma * rng.randn(code["N"] * 8)
+        L = po.demap_bpsk(256, code["N"], y, sigma)
+        t0 = time.perf_counter()
+        oc.decode(4, 10, 2, 2, 1.0, 0.5, L)
+        t += time.perf_counter() - t0
+    return {"frames": frames, "seconds": t, "threads": 1, "info_bits_per_frame": 256}
+
+
+def cpu_baseline(threads, frames_per_thread, tag):
+    r = reference_run(threads, frames_per_thread, "/tmp/nbldpc_ref_bench_%s" % tag)
+    kind = "reference"
+    if r is None:
+        r, kind = port_run(8), "port"
+    mbps = r["frames"] * r["info_bits_per_frame"] / r["seconds"] / 1e6
+    return {"value": mbps, "unit": "Mbit/s", "cores": r["threads"], "kind": kind,
+            "sample": "%d frames of the same workload (%d threads x %d, max 10 iterations with the reference's early stop), %.1f s"
+                      % (r["frames"], r["threads"], r["frames"] // r["threads"], r["seconds"]),
+            "frames_per_s": r["frames"] / r["seconds"]}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    fpt = args.ref_frames_per_thread
+    for _ in range(args.warmup):
+        cpu_baseline(threads, 1, "warm")
+    tot_frames, tot_s, last = 0, 0.0, None
+    for _ in range(args.steps):
+        last = cpu_baseline(threads, fpt, "step")
+        tot_frames += threads * fpt
+        tot_s += threads * fpt / last["frames_per_s"]
+    value = tot_frames * 256 / tot_s / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": threads * fpt, "iterations": "max 10, reference early stop",
+                       "host": "%d threads" % threads},
+            "cpu_baseline": {"value": value, "unit": "Mbit/s", "cores": threads, "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": value, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nbldpc_b200 import capi, gfcode
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the decode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    code_path = "/tmp/nbldpc_bench_code_%d.txt" % rank
+    open(code_path, "w").write(bundle_code_text(CODE))
+    code = capi.Code.from_file(code_path)
+    B = args.frames
+    stream = torch.cuda.current_stream().cuda_stream
+    dec = capi.Decoder(code, precision=capi.PREC_F32, early_stop=0, max_batch=B, device=local, stream=stream, **TEMS)
+    dec_es = capi.Decoder(code, precision=capi.PREC_F32, early_stop=1, max_batch=B, device=local, stream=stream, **TEMS)
+    pool = gfcode.random_codewords(code, 1024, seed=1)
+    counters = torch.zeros(capi.NUM_COUNTERS, dtype=torch.int64, device="cuda")
+    info_bits, coded_bits = code.K * code.p, code.N * code.p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def sim_step(d, step):
+        first = (step * world + rank) * B                      # disjoint global frame indices per rank and step
+        d.simulate_async(EBN0_DB, B, counters, seed=args.seed, first_frame=first, codewords=pool)
+
+    def timed(fn, steps, warmup, after=None):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        if after:
+            after()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def reduce_counters():
+        if world > 1:
+            dist.all_reduce(counters, op=dist.ReduceOp.SUM)    # the only collective of the path (8 x u64)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- value: device-resident Monte-Carlo, fixed 10 iterations ----
+    counters.zero_()
+    ms = timed(lambda i: sim_step(dec, i), args.steps, args.warmup, after=reduce_counters)
+    cnt = counters.cpu().numpy().astype(np.int64)
+    launches_per_step = dec.last_timing()[1]
+    it_ms = dec.iter_timing()
+    frames_total = B * args.steps * world
+    value = frames_total * info_bits / (ms * 1e-3) / 1e6
+    # ---- same with the reference's early-stop rule ----
+    counters.zero_()
+    ms_es = timed(lambda i: sim_step(dec_es, i), args.steps, args.warmup, after=reduce_counters)
+    cnt_es = counters.cpu().numpy().astype(np.int64)
+    # ---- e2e: host buffers through the reference-facing call ----
+    L = code.N * code.p
+    sigma = 1.0 / np.sqrt(2.0 * (code.K / code.N) * 10 ** (EBN0_DB / 10))
+    rng = np.random.RandomState(100 + rank)
+    tx = pool[rng.randint(0, len(pool), size=B)]
+    bits = ((tx[:, :, None] >> np.arange(code.p)) & 1).reshape(B, L)
+    y_host = torch.from_numpy((1.0 - 2.0 * bits) + sigma * rng.standard_normal((B, L))).pin_memory()
+    out_host = torch.zeros((B, code.N), dtype=torch.int32).pin_memory()
+    conv_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+    iters_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step(d):
+        d.demap_decode_raw(2, y_host, B, sigma, out_host, conv_host, iters_host)   # synchronous: results are on the host
+
+    ms_e2e = timed(lambda i: e2e_step(dec), args.steps, args.warmup)
+    e2e_launches = dec.last_timing()[1]
+    e2e_fer = float((out_host.numpy()[:, :code.K] != tx[:, :code.K]).any(axis=1).mean())
+    ms_e2e_es = timed(lambda i: e2e_step(dec_es), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d, d2h = y_host.numel() * 8, out_host.numel() * 4 + conv_host.numel() * 4 + iters_host.numel() * 4
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        E, N, q = code.E, code.N, code.q
+        bytes_iter = 4 * q * (4 * E + N)                       # algorithmic bytes per frame-iteration, fp32
+        leaves = 93.6e3                                        # reference's own leaf counter per check
+        ops_iter = code.M * leaves * 2
+        k_ms = sum(it_ms) / max(1, len(it_ms))
+        achieved = bytes_iter * B / (k_ms * 1e-3) / 1e9
+        alu_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": None, "kernel": "k_iterate<float,256,T-EMS>", "kernel_ms": k_ms, "launches_timed": len(it_ms),
+                    "peak_source": peak_src,
+                    "alu": {"note": "T-EMS check node is FP32-issue bound (SURVEY 8d): reference leaf count x 2 lane-ops",
+                            "achieved_tlaneops": ops_iter * B / (k_ms * 1e-3) / 1e12, "peak_tlaneops": alu_peak / 1e12,
+                            "frac": ops_iter * B / (k_ms * 1e-3) / alu_peak}}
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(os.cpu_count() or 1, args.ref_frames_per_thread, "main")
+            cb.pop("frames_per_s", None)
+        line = {"metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "iterations": "fixed 10 (early stop off)",
+                           "l2": "working set %.1f GB per step >> 126 MB L2" % (B * (q * 4 * (3 * E + N)) / 1e9),
+                           "sharding": "frames by global index, no data-path collective; one 8 x u64 all-reduce per timed region"},
+                "coded_mbit_s": value * coded_bits / info_bits, "frames_per_s": frames_total / (ms * 1e-3),
+                "fer": float(cnt[1]) / max(1, cnt[0]), "frames_counted": int(cnt[0]),
+                "e2e": {"value": B * args.steps * world * info_bits / (ms_e2e * 1e-3) / 1e6, "unit": "Mbit/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "call": "nbl_demap_decode_batch (host y -> host decisions)",
+                        "fer": e2e_fer},
+                "early_stop": {"value": frames_total * info_bits / (ms_es * 1e-3) / 1e6, "unit": "Mbit/s",
+                               "mean_iterations": float(cnt_es[6]) / max(1, cnt_es[0]), "fer": float(cnt_es[1]) / max(1, cnt_es[0]),
+                               "e2e": B * args.steps * world * info_bits / (ms_e2e_es * 1e-3) / 1e6},
+                "gpu_launches": int(launches_per_step * args.steps), "e2e_gpu_launches": int(e2e_launches * args.steps),
+                "roofline": roofline, "clocks": clocks}
+        if cb:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=148 * 64, help="frames per step per GPU")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--ref-frames-per-thread", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

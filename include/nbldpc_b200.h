@@ -12,7 +12,8 @@
  *   - "LLR vector" layout is the reference's: q-1 doubles per symbol, entry k-1 = ln P(x=k)/P(x=0)
  *     (NBLDPC.cpp:1542-1562, Comm.cpp:360-398).  Batched arrays are dense [B][N][q-1].
  *   - data pointers may be HOST or DEVICE pointers (detected with cudaPointerGetAttributes); device
- *     pointers must belong to the decoder's device.  Host pointers are staged through pinned buffers.
+ *     pointers must belong to the decoder's device.  Host data is staged through device buffers on the
+ *     decoder's stream (pass pinned host memory for asynchronous copies).
  *   - handles are not thread-safe; distinct decoder handles are independent (one CUDA stream each).
  *   - there is no CPU fallback: every compute entry point fails with NBL_ERR_CUDA when no B200 is present.
  */
@@ -165,6 +166,9 @@ int nbl_simulate_async(nbl_decoder *dec, const nbl_sim_config *cfg, uint64_t *de
  * nbl_demap_decode_batch / nbl_simulate call on this decoder (CUDA events on the decoder's stream),
  * and the number of kernel launches it made. */
 int nbl_decoder_last_timing(nbl_decoder *dec, float *kernel_ms, int *launches);
+/* per-launch duration (ms) of the fused iteration kernel in the last decode on this decoder: ms[i] is
+ * iteration i+1.  Synchronises the stream.  Returns the number of entries written (<= capacity). */
+int nbl_decoder_iter_timing(nbl_decoder *dec, float *ms, int capacity);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ def lib():
         L.nbl_simulate.argtypes = [vp, C.POINTER(SimConfig), vp]
         L.nbl_simulate_async.argtypes = [vp, C.POINTER(SimConfig), vp]
         L.nbl_decoder_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.nbl_decoder_iter_timing.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
         _lib = L
     return _lib
 
@@ -259,6 +260,11 @@ class Decoder:
         ms = C.c_float(); n = C.c_int()
         _check(lib().nbl_decoder_last_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def iter_timing(self):
+        ms = (C.c_float * 64)()
+        n = _check(lib().nbl_decoder_iter_timing(self._h, ms, 64))
+        return [ms[i] for i in range(n)]
 
     def close(self):
         if self._h:

@@ -32,6 +32,7 @@ template <typename T, int Q> struct TemsSmem {
     uint8_t *pcol;    // [Q] path: c_first | c_second << 4
     uint8_t *pnd;     // [Q] path: number of deviations (0,1,2)
     uint8_t *bp;      // DP back pointers [maxdc][n_c+1][Q]
+    uint8_t *eta;     // DP recorded path [maxdc][Q]
     int *wtot;        // [WARPS]
     int *sdec;        // [maxdc] decide() of each input
     RedScratch<K, Grp<Q>::WARPS, 2> *red;
@@ -46,7 +47,7 @@ template <typename T, int Q> struct TemsSmem {
         b += sizeof(int) * (Grp<Q>::WARPS + maxdc);
         b += sizeof(uint16_t) * Q;
         b += 6 * (size_t)Q;
-        if (nc >= 3) b += (size_t)maxdc * (nc + 1) * Q;
+        if (nc >= 3) b += (size_t)maxdc * (nc + 2) * Q;
         return align_up(b, 16);
     }
     __device__ void carve(unsigned char *base, int maxdc, int nc) {
@@ -63,9 +64,65 @@ template <typename T, int Q> struct TemsSmem {
         sdec = reinterpret_cast<int *>(c); c += sizeof(int) * maxdc;
         amask = reinterpret_cast<uint16_t *>(c); c += sizeof(uint16_t) * Q;
         lb = c; c += Q; c0 = c; c += Q; c1 = c; c += Q; pb = c; c += Q; pcol = c; c += Q; pnd = c; c += Q;
-        bp = c;
+        bp = c; eta = c + (size_t)maxdc * (nc + 1) * Q;
     }
 };
+
+// Configuration search for n_c >= 3: column DP over (syndrome s, number of deviations j) with back pointers.
+// W_d[j][s] = min cost of a prefix (eta_0..eta_d) with XOR s and j non-zero deviations; the prefix sums are
+// formed left to right over the columns as the reference's recursion forms them.  Paths that repeat a
+// non-zero eta (which the reference skips, NBLDPC.cpp:1910-1922) cancel in the XOR and cost >= 0 extra, so
+// they never beat the path without the repeated pair.  Ends by building the output trellis Tout.
+template <typename T, int Q>
+__device__ void cn_tems_dp(TemsSmem<T, Q> &S, int gid, int x, int dcn, int nc, T *Tout) {
+    const T INF = Real<T>::inf();
+    const int nj = nc + 1;
+    T *Wa = S.W2, *Wb = S.W2 + (size_t)nj * Q;
+    for (int j = 0; j < nj; ++j) Wa[j * Q + x] = (j == 0 && x == 0) ? T(0) : INF;
+    for (int d = 0; d < dcn; ++d) {
+        Grp<Q>::sync(gid);
+        const bool in = x != 0 && ((S.amask[x] >> d) & 1);
+        int len;
+        const int pos = group_prefix_count<Q>(in, x, gid, S.wtot, len);
+        if (in) { S.lb[pos] = (uint8_t)x; S.lc[pos] = S.dU[d * Q + x]; }
+        Grp<Q>::sync(gid);
+        for (int j = 0; j < nj; ++j) {
+            T w = Wa[j * Q + x]; int b0 = 0;                      // eta_d = 0 first, then ascending eta
+            if (j > 0)
+                for (int i = 0; i < len; ++i) {
+                    const int b = S.lb[i];
+                    const T cand = Wa[(j - 1) * Q + (x ^ b)] + S.lc[i];
+                    if (cand < w) { w = cand; b0 = b; }
+                }
+            Wb[j * Q + x] = w;
+            S.bp[((size_t)d * nj + j) * Q + x] = (uint8_t)b0;
+        }
+        T *t = Wa; Wa = Wb; Wb = t;
+    }
+    // deltaW[s] = best over the deviation counts; walk the back pointers to recover Eta[s][.]
+    {
+        T w = Wa[x]; int j = 0;
+        for (int jj = 1; jj < nj; ++jj) { const T c = Wa[jj * Q + x]; if (c < w) { w = c; j = jj; } }
+        S.dW[x] = w;
+        int s = x;
+        for (int d = dcn - 1; d >= 0; --d) {
+            const int b = S.bp[((size_t)d * nj + j) * Q + s];
+            S.eta[d * Q + x] = (uint8_t)b;
+            if (b) { s ^= b; --j; }
+        }
+    }
+    Grp<Q>::sync(gid);                                          // V is free from here on
+    for (int d = 0; d < dcn; ++d) Tout[d * Q + x] = INF;
+    Grp<Q>::sync(gid);
+    {
+        const T w = S.dW[x];
+        for (int d = 0; d < dcn; ++d) {
+            const int dev = S.eta[d * Q + x];
+            atomic_min_nonneg(&Tout[d * Q + (x ^ dev)], w - S.dU[d * Q + dev]);
+        }
+    }
+    Grp<Q>::sync(gid);
+}
 
 // Inputs: S.V[d][x] (final v2c, slot 0 == 0) and S.sdec[d] = decide(V_d) for d < dcn, visible to the group.
 // Output: c2v_out[(e0+d)*Q + x] for d < dcn.
@@ -102,63 +159,67 @@ __device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, in
         S.amask[x] = (uint16_t)am; S.c0[x] = (uint8_t)k0; S.c1[x] = (uint8_t)k1;
         S.P[x] = INF;
     }
-    // -- configuration search for n_c <= 2 ---------------------------------------------------------
-    T best = INF; int bb = 0, bd = 0;
-    if (nc >= 2) {
-        for (int d = 1; d < dcn; ++d) {
-            Grp<Q>::sync(gid);                                  // previous scan done with P / list
-            {   // fold column d-1 into the running minimum (strict '<': lower column wins ties)
-                const T u = (x != 0 && ((S.amask[x] >> (d - 1)) & 1)) ? S.dU[(d - 1) * Q + x] : INF;
-                if (u < S.P[x]) S.P[x] = u;
-            }
-            const bool in = x != 0 && ((S.amask[x] >> d) & 1);
-            int len;
-            const int pos = group_prefix_count<Q>(in, x, gid, S.wtot, len);
-            if (in) { S.lb[pos] = (uint8_t)x; S.lc[pos] = S.dU[d * Q + x]; }
-            Grp<Q>::sync(gid);
-            for (int i = 0; i < len; ++i) {
-                const int b = S.lb[i];
-                const T cand = S.P[x ^ b] + S.lc[i];
-                if (cand < best) { best = cand; bb = b; bd = d; }
-            }
-        }
-    }
-    // -- deltaW and the recorded path ------------------------------------------------------------------
-    {
-        const int k0 = S.c0[x];
-        const T m0 = S.dU[k0 * Q + x];
-        T w; int nd, pc = 0;
-        if (x == 0) { w = T(0); nd = 0; }
-        else if (best < m0) {
-            const int a = x ^ bb;                               // first deviation: cheapest allowed column before bd
-            T m = INF; int ca = 0;
-            const unsigned am = S.amask[a];
-            for (int c = 0; c < bd; ++c)
-                if ((am >> c) & 1) { const T u = S.dU[c * Q + a]; if (u < m) { m = u; ca = c; } }
-            w = best; nd = 2; pc = ca | (bd << 4);
-        } else { w = m0; nd = 1; pc = k0; }
-        S.dW[x] = w; S.pb[x] = (uint8_t)bb; S.pcol[x] = (uint8_t)pc; S.pnd[x] = (uint8_t)nd;
-    }
-    Grp<Q>::sync(gid);                                          // everyone is done with V and P
-    // -- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): identity entries first -----------------------
     T *Tout = S.V;
-    {
-        const int nd = S.pnd[x], pc = S.pcol[x];
-        const int ca = pc & 15, cb = pc >> 4;
-        const T w = S.dW[x];
-        for (int d = 0; d < dcn; ++d) {
-            const bool uses = (nd == 1 && ca == d) || (nd == 2 && (ca == d || cb == d));
-            Tout[d * Q + x] = (x == 0) ? T(0) : (uses ? INF : w);
+    if (nc <= 2) {
+        // -- configuration search for n_c <= 2 ---------------------------------------------------------
+        T best = INF; int bb = 0, bd = 0;
+        if (nc >= 2) {
+            for (int d = 1; d < dcn; ++d) {
+                Grp<Q>::sync(gid);                                  // previous scan done with P / list
+                {   // fold column d-1 into the running minimum (strict '<': lower column wins ties)
+                    const T u = (x != 0 && ((S.amask[x] >> (d - 1)) & 1)) ? S.dU[(d - 1) * Q + x] : INF;
+                    if (u < S.P[x]) S.P[x] = u;
+                }
+                const bool in = x != 0 && ((S.amask[x] >> d) & 1);
+                int len;
+                const int pos = group_prefix_count<Q>(in, x, gid, S.wtot, len);
+                if (in) { S.lb[pos] = (uint8_t)x; S.lc[pos] = S.dU[d * Q + x]; }
+                Grp<Q>::sync(gid);
+                for (int i = 0; i < len; ++i) {
+                    const int b = S.lb[i];
+                    const T cand = S.P[x ^ b] + S.lc[i];
+                    if (cand < best) { best = cand; bb = b; bd = d; }
+                }
+            }
         }
+        // -- deltaW and the recorded path ------------------------------------------------------------------
+        {
+            const int k0 = S.c0[x];
+            const T m0 = S.dU[k0 * Q + x];
+            T w; int nd, pc = 0;
+            if (x == 0) { w = T(0); nd = 0; }
+            else if (best < m0) {
+                const int a = x ^ bb;                               // first deviation: cheapest allowed column before bd
+                T m = INF; int ca = 0;
+                const unsigned am = S.amask[a];
+                for (int c = 0; c < bd; ++c)
+                    if ((am >> c) & 1) { const T u = S.dU[c * Q + a]; if (u < m) { m = u; ca = c; } }
+                w = best; nd = 2; pc = ca | (bd << 4);
+            } else { w = m0; nd = 1; pc = k0; }
+            S.dW[x] = w; S.pb[x] = (uint8_t)bb; S.pcol[x] = (uint8_t)pc; S.pnd[x] = (uint8_t)nd;
+        }
+        Grp<Q>::sync(gid);                                          // everyone is done with V and P
+        // -- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): identity entries first -----------------------
+        {
+            const int nd = S.pnd[x], pc = S.pcol[x];
+            const int ca = pc & 15, cb = pc >> 4;
+            const T w = S.dW[x];
+            for (int d = 0; d < dcn; ++d) {
+                const bool uses = (nd == 1 && ca == d) || (nd == 2 && (ca == d || cb == d));
+                Tout[d * Q + x] = (x == 0) ? T(0) : (uses ? INF : w);
+            }
+        }
+        Grp<Q>::sync(gid);
+        if (S.pnd[x] == 2) {                                        // entries that land on another index
+            const int pc = S.pcol[x], ca = pc & 15, cb = pc >> 4, b = S.pb[x], a = x ^ b;
+            const T w = S.dW[x];
+            atomic_min_nonneg(&Tout[ca * Q + b], w - S.dU[ca * Q + a]);
+            atomic_min_nonneg(&Tout[cb * Q + a], w - S.dU[cb * Q + b]);
+        }
+        Grp<Q>::sync(gid);
+    } else {
+        cn_tems_dp<T, Q>(S, gid, x, dcn, nc, Tout);
     }
-    Grp<Q>::sync(gid);
-    if (S.pnd[x] == 2) {                                        // entries that land on another index
-        const int pc = S.pcol[x], ca = pc & 15, cb = pc >> 4, b = S.pb[x], a = x ^ b;
-        const T w = S.dW[x];
-        atomic_min_nonneg(&Tout[ca * Q + b], w - S.dU[ca * Q + a]);
-        atomic_min_nonneg(&Tout[cb * Q + a], w - S.dU[cb * Q + b]);
-    }
-    Grp<Q>::sync(gid);
     // -- fill-in (NBLDPC.cpp:1095-1102), back to the normal domain, un-permute, correct (1105-1128) -----
     for (int d = 0; d < dcn; ++d) {
         const int e = e0 + d;

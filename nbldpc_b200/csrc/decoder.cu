@@ -232,10 +232,13 @@ struct nbl_decoder {
     double *d_ystage = nullptr;  size_t ystage_bytes = 0;    // staging for host received samples
     std::vector<int> punct_cache; int punct_mod = -1, punct_ylen = 0;
     uint8_t *d_pool = nullptr; size_t pool_cap = 0;          // codeword pool of the Monte-Carlo path
+    std::vector<int> pool_host;
     unsigned long long *d_counters = nullptr;
     bool timing_pending = false;
     double *d_cons = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> it_ev;                          // [2*max_iter] start/stop around each k_iterate launch
+    int it_recorded = 0;
     float last_ms = 0; int last_launches = 0;
     size_t smem_iter = 0;
 };
@@ -282,6 +285,7 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
                     d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : d->it_ev) if (e) cudaEventDestroy(e);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
@@ -298,7 +302,6 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
         nbl_set_error("EMS configuration error! EMS_Nm is too large!"); return NBL_ERR_ARG;   // NBLDPC.cpp:282-286
     }
     if (cfg->method == NBL_METHOD_TEMS && (cfg->p0 < 1 || cfg->p1 < 1)) { nbl_set_error("T-EMS needs n_r >= 1 and n_c >= 1"); return NBL_ERR_ARG; }
-    if (cfg->method == NBL_METHOD_TEMS && cfg->p1 > 2) { nbl_set_error("T-EMS n_c > 2 is not implemented yet"); return NBL_ERR_ARG; }
     if (cfg->method != NBL_METHOD_QSPA && cfg->factor == 0.0) { nbl_set_error("correction factor must be non-zero"); return NBL_ERR_ARG; }
     if (nbl_device_count() <= cfg->device || cfg->device < 0) { nbl_set_error("no such CUDA device (this library has no CPU fallback)"); return NBL_ERR_CUDA; }
     CK(cudaSetDevice(cfg->device));
@@ -334,6 +337,8 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     ALLOC(d->d_cons, 2 * q * sizeof(double));
 #undef ALLOC
     if (cudaEventCreate(&d->ev0) != cudaSuccess || cudaEventCreate(&d->ev1) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
+    d->it_ev.assign(2 * (size_t)cfg->max_iter, nullptr);
+    for (auto &e : d->it_ev) if (cudaEventCreate(&e) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
     d->smem_iter = smem_for(d, q);
     if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
     *out = d;
@@ -358,6 +363,16 @@ extern "C" int nbl_decoder_last_timing(nbl_decoder *d, float *ms, int *launches)
     if (ms) *ms = d->last_ms;
     if (launches) *launches = d->last_launches;
     return NBL_OK;
+}
+
+// duration of each check-node iteration kernel of the last decode (ms[i] for iteration i+1); returns the count
+extern "C" int nbl_decoder_iter_timing(nbl_decoder *d, float *ms, int capacity) {
+    if (!d) { nbl_set_error("null decoder"); return NBL_ERR_ARG; }
+    CK(cudaSetDevice(d->cfg.device));
+    CK(cudaStreamSynchronize(d->stream));
+    int n = d->it_recorded < capacity ? d->it_recorded : capacity;
+    for (int i = 0; i < n; ++i) CK(cudaEventElapsedTime(&ms[i], d->it_ev[2 * i], d->it_ev[2 * i + 1]));
+    return n;
 }
 
 static int ensure_buf(double **buf, size_t *have, size_t bytes) {
@@ -412,7 +427,7 @@ template <typename T, int Q> static int launch_posterior_tq(nbl_decoder *d, int 
 template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_dev) {
     const nbl_decoder_config &c = d->cfg;
     const int q = d->g.q;
-    d->last_launches = 0;
+    d->last_launches = 0; d->it_recorded = 0;
     CK(cudaMemsetAsync(d->d_flag, 0, (size_t)B * sizeof(int), d->stream));
     CK(cudaMemsetAsync(d->d_done, 0, (size_t)B, d->stream));
     CK(cudaEventRecord(d->ev0, d->stream));
@@ -429,8 +444,11 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
             P.p0 = c.p0; P.p1 = c.p1; P.factor = (T)c.factor; P.offset = (T)c.offset; P.w_old = w_old; P.w_new = w_new;
             P.lch = (const T *)d->d_lch; P.v2c = (T *)d->d_v2c; P.c2v_in = cin; P.c2v_out = cout;
             P.vdec = d->d_vdec; P.dec = d->d_dec; P.flag = d->d_flag; P.done = d->d_done;
+            CK(cudaEventRecord(d->it_ev[2 * (it - 1)], d->stream));
             DISPATCH_Q(q, rc = (launch_iterate_tq<T, QQ>(d, P)));
             if (rc) return rc;
+            CK(cudaEventRecord(d->it_ev[2 * (it - 1) + 1], d->stream));
+            d->it_recorded = it;
             d->last_launches += 1;
         } else {      // last iteration: the reference's final check-node pass cannot change any output
             DISPATCH_Q(q, rc = (launch_posterior_tq<T, QQ>(d, B, it == 1, cin, nullptr, nullptr)));
@@ -684,7 +702,8 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
     int rc, ylen;
     if ((rc = setup_punct(d, cfg->modulation, nullptr, 0, &ylen))) return rc;
     // codeword pool -> device bytes
-    if (cfg->n_codewords) {
+    if (cfg->n_codewords && !(d->pool_host.size() == (size_t)cfg->n_codewords * N &&
+                              memcmp(d->pool_host.data(), cfg->codewords, d->pool_host.size() * sizeof(int)) == 0)) {
         const size_t n = (size_t)cfg->n_codewords * N;
         if (d->pool_cap < n) { if (d->d_pool) cudaFree(d->d_pool); d->d_pool = nullptr; CK(cudaMalloc((void **)&d->d_pool, n)); d->pool_cap = n; }
         std::vector<uint8_t> bytes(n);
@@ -694,11 +713,12 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
         }
         CK(cudaMemcpyAsync(d->d_pool, bytes.data(), n, cudaMemcpyHostToDevice, d->stream));
         CK(cudaStreamSynchronize(d->stream));
+        d->pool_host.assign(cfg->codewords, cfg->codewords + n);        // same pool next call: nothing to upload
     }
     if (cfg->modulation != 2) CK(cudaMemcpyAsync(d->d_cons, cfg->constellation, 2 * q * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     const size_t ydbl = (size_t)d->cfg.max_batch * ylen * (cfg->modulation == 2 ? 1 : 2);
     if ((rc = ensure_ystage(d, ydbl * sizeof(double)))) return rc;
-    float ms_total = 0; int launches = 0;
+    int launches = 0;
     for (uint64_t done = 0; done < cfg->frames;) {
         const int B = (int)std::min<uint64_t>(d->cfg.max_batch, cfg->frames - done);
         const int per = cfg->modulation == 2 ? (N * p + 1) / 2 : N;
@@ -714,7 +734,6 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
         CK(cudaGetLastError());
         launches += d->last_launches + 3;
         done += B;
-        (void)ms_total;
     }
     d->last_launches = launches;
     return NBL_OK;

@@ -42,8 +42,10 @@ def test_fp64_matches_reference_decisions_and_iterations(name, code_files):
 
 @pytest.mark.parametrize("name", golden_names())
 def test_fp32_fast_mode_within_tolerance(name, code_files):
-    """fp32 fast mode: posterior LLRs within 1e-4 relative (|d| <= 1e-4 * max(|ref|, 1)) on frames whose
-    decisions agree; decisions agree on (almost) every frame -- fp32 rounding may flip a near-tie."""
+    """fp32 fast mode: posterior LLRs within 1e-4 relative on frames whose decisions agree; decisions agree on
+    (almost) every frame -- fp32 rounding may flip a near-tie.  "Relative" is the definition SURVEY.md section 4
+    recommends: |d| <= 1e-4 * max(1, max-norm of the symbol's posterior vector) -- near-zero entries of a vector
+    whose other entries are ~30 cannot carry 1e-4 of their own magnitude in fp32."""
     from nbldpc_b200 import capi
     z, meta = load_golden(name)
     code = load_product_code(code_files, meta["code"])
@@ -55,7 +57,8 @@ def test_fp32_fast_mode_within_tolerance(name, code_files):
     got = r["post"][:, :, z["lpost_idx"]][same]
     ref = z["lpost_sample"][same]
     sel = ref > -25.0 if meta["method"] == 1 else np.ones_like(ref, bool)
-    err = np.abs(got - ref)[sel] / np.maximum(np.abs(ref[sel]), 1.0)
+    norm = np.maximum(np.abs(ref).max(axis=2, keepdims=True), 1.0) * np.ones_like(ref)
+    err = np.abs(got - ref)[sel] / norm[sel]
     assert err.max() < 1e-4, err.max()
 
 
