@@ -191,7 +191,11 @@ def main_ours(args):
     open(code_path, "w").write(bundle_code_text(CODE))
     code = capi.Code.from_file(code_path)
     B = args.frames
-    stream = torch.cuda.current_stream().cuda_stream
+    # the decoder launches on a torch-owned stream so that torch.cuda.Event brackets its kernels
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     dec = capi.Decoder(code, precision=capi.PREC_F32, early_stop=0, max_batch=B, device=local, stream=stream, **TEMS)
     dec_es = capi.Decoder(code, precision=capi.PREC_F32, early_stop=1, max_batch=B, device=local, stream=stream, **TEMS)
     pool = gfcode.random_codewords(code, 1024, seed=1)
