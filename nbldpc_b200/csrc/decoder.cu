@@ -17,6 +17,7 @@
 #include "cn_ems.cuh"
 #include "cn_qspa.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,6 +48,8 @@ template <typename T> struct IterParams {
     int *flag;
     const uint8_t *done;
 };
+
+#include "tems_warp.cuh"
 
 // channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
 template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
@@ -241,6 +244,7 @@ struct nbl_decoder {
     int it_recorded = 0;
     float last_ms = 0; int last_launches = 0;
     size_t smem_iter = 0;
+    bool warp_path = false;      // T-EMS n_c <= 2, dc <= 4, q >= 32: one warp per check row (tems_warp.cuh)
 };
 
 extern "C" int nbl_device_count(void) {
@@ -340,6 +344,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     d->it_ev.assign(2 * (size_t)cfg->max_iter, nullptr);
     for (auto &e : d->it_ev) if (cudaEventCreate(&e) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
     d->smem_iter = smem_for(d, q);
+    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && code->max_dc <= TW_DC && q >= 32 && !getenv("NBLDPC_FORCE_GENERIC");
     if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
     *out = d;
     return NBL_OK;
@@ -397,7 +402,22 @@ template <typename T, int Q, int METHOD> static int launch_iterate_tqm(nbl_decod
     CK(cudaGetLastError());
     return NBL_OK;
 }
+template <typename T, int Q> static int launch_iterate_warp(nbl_decoder *d, const IterParams<T> &P) {
+    if constexpr (Q >= 32) {
+        auto kern = k_iterate_tems_warp<T, Q>;
+        constexpr size_t smem = TwSmem<T, Q>::bytes;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long rows = (long long)P.B * P.g.M;
+        kern<<<(unsigned)((rows + TW_WARPS - 1) / TW_WARPS), 32 * TW_WARPS, smem, d->stream>>>(P);
+        CK(cudaGetLastError());
+        return NBL_OK;
+    } else {
+        nbl_set_error("internal: warp path needs q >= 32");
+        return NBL_ERR_ARG;
+    }
+}
 template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const IterParams<T> &P) {
+    if (d->warp_path) return launch_iterate_warp<T, Q>(d, P);
     switch (d->cfg.method) {
         case NBL_METHOD_TEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_TEMS>(d, P);
         case NBL_METHOD_EMS: return launch_iterate_tqm<T, Q, NBL_METHOD_EMS>(d, P);

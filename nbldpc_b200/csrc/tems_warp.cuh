@@ -1,0 +1,402 @@
+// Fast path of the fused iteration kernel for T-EMS with n_c <= 2 (the headline configuration):
+// ONE WARP per (frame, check row), VEC = Q/32 consecutive field elements per lane.
+//
+// Same arithmetic and the same scan order (column, then eta ascending) as the generic group kernel in
+// decoder.cu / cn_tems.cuh -- so the two produce identical bits -- but organised for the issue-bound search:
+//   * no block-level barriers: every exchange between lanes is a __syncwarp on the warp's private smem slab;
+//   * the pair search is a register-tiled min-plus XOR-convolution.  Lane t owns deltaW candidates for
+//     s = VEC*t .. VEC*t+VEC-1 in registers.  For column d and eta-block bh it loads the VEC running minima
+//     P_d[VEC*(t^bh) ..] once (conflict-free 128-bit loads) and the VEC masked costs C_d[VEC*bh ..] (uniform
+//     broadcast loads); entry bl of the block then serves all VEC outputs from registers:
+//         best[r] = min(best[r], p[r ^ bl] + c[bl])          -> 1 FADD + 1 FMNMX per leaf, no per-leaf load.
+//     Deviations that are not allowed in column d are skipped with a warp-uniform branch on a ballot mask.
+//   * arg-min bookkeeping is done per chunk of TW_CH eta-blocks (3 instructions per output per chunk); the
+//     winning (column, chunk) is re-scanned once at the end to recover the exact eta of the recorded path.
+//   * everything outside the search is written as short loops over the row's edges with 128-bit shared-memory
+//     accesses, to keep the kernel inside the instruction cache and free of bank conflicts.
+#pragma once
+#include "dev_common.cuh"
+
+namespace nbl {
+
+constexpr int TW_DC = 4;      // maximum check degree served by the fast path
+constexpr int TW_WARPS = 4;   // warps (= check rows) per CTA
+constexpr int TW_CH = 2;      // eta-blocks per arg-min chunk
+
+template <typename T, int Q> struct TwSmem {
+    // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> masked costs C (search) -> output trellis Tout
+    //                 dU [TW_DC][Q]
+    //                 P  [TW_DC-1][Q] running minima, "split" layout (PLayout)
+    //                 bytes c01[Q] (c0 | c1 << 4), amask[Q];  ints meta[2*TW_DC] (decide, beta per edge)
+    static constexpr size_t t_elems = (size_t)Q * (2 * TW_DC + (TW_DC - 1));
+    static constexpr size_t bytes_per_warp = ((t_elems * sizeof(T) + 2 * (size_t)Q + 2 * TW_DC * sizeof(int) + 15) / 16) * 16;
+    static constexpr size_t bytes = bytes_per_warp * TW_WARPS;
+};
+
+// P is stored so that a lane's VEC values come out of conflict-free 16-byte loads: the vector of block k is cut
+// into 16-byte pieces and piece h of all blocks is contiguous:  index(k, j) = (j / E16) * (32 * E16) + k * E16 + j % E16
+// with E16 = elements per 16 bytes (4 floats / 2 doubles), or VEC when the whole block is <= 16 bytes.
+template <typename T, int VEC> struct PLayout {
+    static constexpr int E16 = (int)(16 / sizeof(T)) < VEC ? (int)(16 / sizeof(T)) : VEC;
+    __device__ static int index(int k, int j) { return (j / E16) * (32 * E16) + k * E16 + (j % E16); }
+};
+
+template <typename T, int N> __device__ __forceinline__ void ld_vec(const T *__restrict__ p, T (&v)[N]) {
+    constexpr int E16 = (int)(16 / sizeof(T));
+    if constexpr (N >= E16) {
+#pragma unroll
+        for (int i = 0; i < N / E16; ++i) {
+            const int4 w = *reinterpret_cast<const int4 *>(p + i * E16);
+            T tmp[E16];
+            *reinterpret_cast<int4 *>(tmp) = w;
+#pragma unroll
+            for (int k = 0; k < E16; ++k) v[i * E16 + k] = tmp[k];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = p[i];
+    }
+}
+template <typename T, int N> __device__ __forceinline__ void st_vec(T *__restrict__ p, const T (&v)[N]) {
+    constexpr int E16 = (int)(16 / sizeof(T));
+    if constexpr (N >= E16) {
+#pragma unroll
+        for (int i = 0; i < N / E16; ++i) {
+            T tmp[E16];
+#pragma unroll
+            for (int k = 0; k < E16; ++k) tmp[k] = v[i * E16 + k];
+            *reinterpret_cast<int4 *>(p + i * E16) = *reinterpret_cast<int4 *>(tmp);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = v[i];
+    }
+}
+// VEC consecutive table bytes starting at a VEC-aligned offset, as one little-endian word
+template <int VEC> __device__ __forceinline__ unsigned long long ld_bytes(const uint8_t *__restrict__ p) {
+    if constexpr (VEC == 8) return *reinterpret_cast<const unsigned long long *>(p);
+    else if constexpr (VEC == 4) return *reinterpret_cast<const unsigned *>(p);
+    else if constexpr (VEC == 2) return *reinterpret_cast<const unsigned short *>(p);
+    else return *p;
+}
+template <int VEC> __device__ __forceinline__ void st_bytes(uint8_t *p, unsigned long long w) {
+    if constexpr (VEC == 8) *reinterpret_cast<unsigned long long *>(p) = w;
+    else if constexpr (VEC == 4) *reinterpret_cast<unsigned *>(p) = (unsigned)w;
+    else if constexpr (VEC == 2) *reinterpret_cast<unsigned short *>(p) = (unsigned short)w;
+    else *p = (uint8_t)w;
+}
+__device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (int)((w >> (8 * i)) & 255ull); }
+
+// DecideLLRVector over a vector spread VEC-per-lane across the warp (x = VEC*lane + j)
+template <typename T, int VEC> __device__ __forceinline__ int warp_decide(const T (&v)[VEC], int lane) {
+    using K = typename Real<T>::key_t;
+    K bk = 0; int bj = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { const K k = pos_key<T>(v[j]); if (k > bk) { bk = k; bj = j; } }
+    K kmax; int src;
+    warp_argmax<true>(bk, 0xffffffffu, kmax, src);
+    const int x = __shfl_sync(0xffffffffu, VEC * lane + bj, src);
+    return kmax == K(0) ? 0 : x;
+}
+
+// recover the recorded two-deviation path of output s from the winning (column, chunk) tag:
+// returns a | b << 8 | c_a << 16 | c_b << 20
+template <typename T, int Q>
+__device__ __noinline__ unsigned tw_recover_path(const T *__restrict__ R1, const T *__restrict__ sP, const T *__restrict__ sdU,
+                                                 const uint8_t *__restrict__ amask, int s, T best, int tag) {
+    constexpr int VEC = Q / 32;
+    using PL = PLayout<T, VEC>;
+    const T INF = Real<T>::inf();
+    const int bd = tag >> 5, blk = (tag & 31) - (TW_CH - 1);
+    const T *Pd = sP + (size_t)(bd - 1) * Q;
+    const T *Cd = R1 + (size_t)bd * Q;
+    int bb = -1;
+#pragma unroll 1
+    for (int i = TW_CH * VEC - 1; i >= 0; --i) {                    // descending, so the smallest matching eta remains
+        const int b = VEC * blk + i;
+        const T cc = Cd[b];
+        const int a = s ^ b;
+        const T cand = Pd[PL::index(a / VEC, a % VEC)] + cc;
+        if (cc < INF && cand == best) bb = b;
+    }
+    const int a = s ^ bb;
+    T m = INF; int ca = 0;
+    const unsigned am = amask[a];
+#pragma unroll 1
+    for (int c = 0; c < bd; ++c)
+        if ((am >> c) & 1) { const T uu = sdU[c * Q + a]; if (uu < m) { m = uu; ca = c; } }
+    return (unsigned)a | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)bd << 20);
+}
+
+template <typename T, int Q>
+__global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterParams<T> P) {
+    constexpr int VEC = Q / 32;
+    using PL = PLayout<T, VEC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevGraph &g = P.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * TW_WARPS + warp;
+    if (w >= (long long)P.B * g.M) return;
+    const int f = (int)(w / g.M), row = (int)(w % g.M);
+    if (P.early_stop && P.done[f]) return;
+
+    T *R1 = reinterpret_cast<T *>(smem_raw + TwSmem<T, Q>::bytes_per_warp * warp);
+    T *sdU = R1 + (size_t)TW_DC * Q;
+    T *sP = sdU + (size_t)TW_DC * Q;
+    uint8_t *c01 = reinterpret_cast<uint8_t *>(sP + (size_t)(TW_DC - 1) * Q);
+    uint8_t *amask = c01 + Q;
+    int *meta = reinterpret_cast<int *>(amask + Q);                 // [0..TW_DC) decide(v2c_d), [TW_DC..) beta_d
+    const T INF = Real<T>::inf();
+    const unsigned FULL = 0xffffffffu;
+
+    const int e0 = g.chk_ptr[row], dcn = g.chk_ptr[row + 1] - e0;
+    const size_t fE = (size_t)f * g.E, fN = (size_t)f * g.N;
+    const int x0 = VEC * lane;
+    int syn_dec = 0, syn = 0;
+    // ---- steps A-C for the row's variables (NBLDPC.cpp:977-1052) ---------------------------------------
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        const int e = e0 + d, col = g.chk_var[e];
+        T post[VEC], vnew[VEC];
+        ld_vec<T, VEC>(P.lch + (fN + col) * Q + x0, post);
+        if (!P.first) {
+            T own[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) own[j] = T(0);
+#pragma unroll 1
+            for (int s = g.var_ptr[col]; s < g.var_ptr[col + 1]; ++s) {
+                const int ee = g.var_edge[s];
+                T m[VEC];
+                ld_vec<T, VEC>(P.c2v_in + (fE + ee) * Q + x0, m);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { post[j] = post[j] + m[j]; if (ee == e) own[j] = m[j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) vnew[j] = post[j] - own[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) vnew[j] = post[j];
+        }
+        const int dpost = warp_decide<T, VEC>(post, lane);
+        int dfin = warp_decide<T, VEC>(vnew, lane);
+        if (!P.first && P.w_old != T(0) && dfin != (int)P.vdec[fE + e]) {            // warp-uniform
+            T vold[VEC];
+            ld_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vold);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) vnew[j] = P.w_old * vold[j] + P.w_new * vnew[j];       // -fmad=false
+            dfin = warp_decide<T, VEC>(vnew, lane);
+        }
+        st_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vnew);
+        st_vec<T, VEC>(R1 + d * Q + x0, vnew);
+        const int bt = g.pfwd[(size_t)e * Q + dfin];
+        if (lane == 0) { P.vdec[fE + e] = (uint8_t)dfin; P.dec[fN + col] = (uint8_t)dpost; meta[d] = dfin; meta[TW_DC + d] = bt; }
+        syn ^= bt;
+        syn_dec ^= g.pfwd[(size_t)e * Q + dpost];
+    }
+    if (lane == 0 && syn_dec != 0) P.flag[f] = 1;
+    __syncwarp();
+    // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)] ------------------------
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        const int sd = meta[d], bt = meta[TW_DC + d];
+        const T vmax = R1[d * Q + sd];
+        const int bh = bt / VEC, bl = bt % VEC;
+        const unsigned long long kk = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + VEC * (lane ^ bh));
+        T u[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) u[j] = vmax - R1[d * Q + byte_of(kk, j ^ bl)];   // eta^beta = VEC*(lane^bh) + (j^bl)
+        st_vec<T, VEC>(sdU + d * Q + x0, u);
+    }
+    __syncwarp();                                                  // all reads of v2c in R1 are done
+    // ---- column order per eta (TEMS_Get_Min), masked costs C, running minima P ---------------------------------
+    T m0[VEC], m1[VEC]; unsigned long long c01w = 0;
+    {
+        T u[TW_DC][VEC];
+#pragma unroll
+        for (int d = 0; d < TW_DC; ++d) {
+            if (d < dcn) ld_vec<T, VEC>(sdU + d * Q + x0, u[d]);
+            else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) u[d][j] = INF;
+            }
+        }
+        unsigned long long amw = 0;
+        T cv[TW_DC][VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            int k0 = 0, k1 = 0; unsigned am = 0;
+#pragma unroll
+            for (int d = 0; d < TW_DC; ++d) {
+                int rank = 0;
+#pragma unroll
+                for (int c = 0; c < TW_DC; ++c) {
+                    if (c < d) rank += (c < dcn) && (u[c][j] <= u[d][j]);           // stable: the lower column wins ties
+                    if (c > d) rank += (c < dcn) && (u[c][j] < u[d][j]);
+                }
+                if (d < dcn) {
+                    if (rank < P.p0) am |= 1u << d;
+                    if (rank == 0) k0 = d;
+                    if (rank == 1) k1 = d;
+                }
+            }
+            c01w |= (unsigned long long)(k0 | (k1 << 4)) << (8 * j);
+            amw |= (unsigned long long)am << (8 * j);
+            m0[j] = INF; m1[j] = INF;
+#pragma unroll
+            for (int d = 0; d < TW_DC; ++d) {
+                cv[d][j] = (x0 + j != 0 && ((am >> d) & 1)) ? u[d][j] : INF;
+                if (k0 == d) m0[j] = u[d][j];
+                if (k1 == d) m1[j] = u[d][j];
+            }
+        }
+        st_bytes<VEC>(c01 + x0, c01w);
+        st_bytes<VEC>(amask + x0, amw);
+        T run[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) run[j] = INF;
+#pragma unroll
+        for (int d = 0; d < TW_DC; ++d) {
+            if (d < dcn) {
+                st_vec<T, VEC>(R1 + d * Q + x0, cv[d]);             // C_d
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) if (cv[d][j] < run[j]) run[j] = cv[d][j];     // strict '<'
+                if (d < TW_DC - 1) {                                // P_{d+1} = min over columns <= d, split layout
+                    constexpr int E16 = PL::E16;
+#pragma unroll
+                    for (int h = 0; h < VEC / E16; ++h) {
+                        T tmp[E16];
+#pragma unroll
+                        for (int i = 0; i < E16; ++i) tmp[i] = run[h * E16 + i];
+                        st_vec<T, E16>(sP + d * Q + h * (32 * E16) + lane * E16, tmp);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- pair search ----------------------------------------------------------------------------------------------
+    T best[VEC], prev[VEC]; int tag[VEC];
+#pragma unroll
+    for (int r = 0; r < VEC; ++r) { best[r] = INF; prev[r] = INF; tag[r] = 0; }
+    if (P.p1 >= 2) {
+#pragma unroll 1
+        for (int d = 1; d < dcn; ++d) {
+            const T *Pd = sP + (size_t)(d - 1) * Q;
+            const T *Cd = R1 + (size_t)d * Q;
+#pragma unroll 1
+            for (int bh = 0; bh < 32; ++bh) {
+                // bit i of `live` = entry i of this eta-block may deviate in column d (same value in every lane)
+                const unsigned live = __ballot_sync(FULL, Cd[VEC * bh + (lane & (VEC - 1))] < INF);
+                T p[VEC], c[VEC];
+                {
+                    const int k = lane ^ bh;
+                    constexpr int E16 = PL::E16;
+#pragma unroll
+                    for (int h = 0; h < VEC / E16; ++h) {
+                        T tmp[E16];
+                        ld_vec<T, E16>(Pd + h * (32 * E16) + k * E16, tmp);
+#pragma unroll
+                        for (int i = 0; i < E16; ++i) p[h * E16 + i] = tmp[i];
+                    }
+                }
+                ld_vec<T, VEC>(Cd + VEC * bh, c);
+#pragma unroll
+                for (int bl = 0; bl < VEC; ++bl) {
+                    if (live & (1u << bl)) {
+#pragma unroll
+                        for (int r = 0; r < VEC; ++r) best[r] = fmin(best[r], p[r ^ bl] + c[bl]);
+                    }
+                }
+                if ((bh & (TW_CH - 1)) == TW_CH - 1) {
+                    const int id = d * 32 + bh;                     // last block of the chunk
+#pragma unroll
+                    for (int r = 0; r < VEC; ++r)
+                        if (best[r] < prev[r]) { prev[r] = best[r]; tag[r] = id; }
+                }
+            }
+        }
+    }
+    // ---- deltaW and the recorded path of each owned s: path = a | b << 8 | c_a << 16 | c_b << 20 | ndev << 24 ------
+    T dw[VEC]; unsigned path[VEC];
+#pragma unroll
+    for (int r = 0; r < VEC; ++r) {
+        const int s = x0 + r;
+        dw[r] = m0[r];
+        path[r] = (unsigned)s | ((unsigned)byte_of(c01w, r) & 15u) << 16 | (1u << 24);
+        if (s == 0) { dw[r] = T(0); path[r] = 0; }
+        else if (best[r] < m0[r]) {
+            dw[r] = best[r];
+            path[r] = tw_recover_path<T, Q>(R1, sP, sdU, amask, s, best[r], tag[r]) | (2u << 24);
+        }
+    }
+    __syncwarp();                                                  // everyone is done with C and P
+    // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
+    T *Tout = R1;
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        T tv[VEC];
+#pragma unroll
+        for (int r = 0; r < VEC; ++r) {
+            const int nd = path[r] >> 24, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
+            const bool uses = (nd == 1 && ca == d) || (nd == 2 && (ca == d || cb == d));
+            tv[r] = (nd == 0) ? T(0) : (uses ? INF : dw[r]);
+        }
+        st_vec<T, VEC>(Tout + d * Q + x0, tv);
+    }
+    __syncwarp();
+    {   // ... then the entries of two-deviation paths, which land on another index: conflict-safe min-store
+        unsigned pending = 0;                                       // bits 2r, 2r+1: the two entries of output r
+#pragma unroll
+        for (int r = 0; r < VEC; ++r) if ((path[r] >> 24) == 2) pending |= 3u << (2 * r);
+        while (__any_sync(FULL, pending != 0)) {
+#pragma unroll
+            for (int r = 0; r < VEC; ++r) {
+                if (pending & (3u << (2 * r))) {
+                    const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
+                    const T va = dw[r] - sdU[ca * Q + a], vb = dw[r] - sdU[cb * Q + b];
+                    if (pending & (1u << (2 * r))) { if (va < Tout[ca * Q + b]) Tout[ca * Q + b] = va; }
+                    if (pending & (2u << (2 * r))) { if (vb < Tout[cb * Q + a]) Tout[cb * Q + a] = vb; }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < VEC; ++r) {
+                if (pending & (3u << (2 * r))) {
+                    const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
+                    const T va = dw[r] - sdU[ca * Q + a], vb = dw[r] - sdU[cb * Q + b];
+                    if (!(va < Tout[ca * Q + b])) pending &= ~(1u << (2 * r));
+                    if (!(vb < Tout[cb * Q + a])) pending &= ~(2u << (2 * r));
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // ---- fill-in (NBLDPC.cpp:1095-1102), normal domain, un-permute, correct (1105-1128) ---------------------------------
+    T *cout = P.c2v_out + fE * Q;
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        {   // indices no path landed on take the smallest dU of the other columns; the owner of t knows it
+            T tv[VEC];
+            ld_vec<T, VEC>(Tout + d * Q + x0, tv);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (tv[j] == INF) tv[j] = ((byte_of(c01w, j) & 15) == d) ? m1[j] : m0[j];
+            st_vec<T, VEC>(Tout + d * Q + x0, tv);
+        }
+        __syncwarp();
+        const int e = e0 + d;
+        const int bs = syn ^ meta[TW_DC + d];
+        const T Tb = Tout[d * Q + bs];
+        const unsigned long long tt = ld_bytes<VEC>(g.pfwd + (size_t)e * Q + x0);
+        T out[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            T v = Tb - Tout[d * Q + (byte_of(tt, j) ^ bs)];
+            if (P.factor != T(1)) v = v / P.factor;                 // x / 1 == x exactly; skips the IEEE division routine
+            out[j] = (x0 + j == 0) ? T(0) : (v < -P.offset ? v + P.offset : (v > P.offset ? v - P.offset : T(0)));
+        }
+        st_vec<T, VEC>(cout + (size_t)e * Q + x0, out);
+    }
+}
+
+}  // namespace nbl
