@@ -16,12 +16,13 @@
 //     accesses, to keep the kernel inside the instruction cache and free of bank conflicts.
 #pragma once
 #include "dev_common.cuh"
+#include <type_traits>
 
 namespace nbl {
 
 constexpr int TW_DC = 4;      // maximum check degree served by the fast path
 constexpr int TW_WARPS = 4;   // warps (= check rows) per CTA
-constexpr int TW_CH = 2;      // eta-blocks per arg-min chunk
+constexpr int TW_CH = 4;      // eta-blocks per arg-min chunk
 
 template <typename T, int Q> struct TwSmem {
     // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> masked costs C (search) -> output trellis Tout
@@ -99,32 +100,42 @@ template <typename T, int VEC> __device__ __forceinline__ int warp_decide(const 
     return kmax == K(0) ? 0 : x;
 }
 
-// recover the recorded two-deviation path of output s from the winning (column, chunk) tag:
-// returns a | b << 8 | c_a << 16 | c_b << 20
-template <typename T, int Q>
-__device__ __noinline__ unsigned tw_recover_path(const T *__restrict__ R1, const T *__restrict__ sP, const T *__restrict__ sdU,
-                                                 const uint8_t *__restrict__ amask, int s, T best, int tag) {
+// Recover the recorded two-deviation path of output s = VEC*lane + R from the winning (column, chunk) tag by
+// re-scanning that chunk with the same register tile as the search (R is a compile-time index, so p[R ^ bl] is a
+// register).  Returns a | b << 8 | c_a << 16 | c_b << 20.
+template <typename T, int Q, int R>
+__device__ __forceinline__ unsigned tw_recover_path(const T *__restrict__ R1, const T *__restrict__ sP, const T *__restrict__ sdU,
+                                                    const uint8_t *__restrict__ amask, int lane, T best, int tag) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
+    constexpr int E16 = PL::E16;
     const T INF = Real<T>::inf();
     const int bd = tag >> 5, blk = (tag & 31) - (TW_CH - 1);
     const T *Pd = sP + (size_t)(bd - 1) * Q;
     const T *Cd = R1 + (size_t)bd * Q;
-    int bb = -1;
-#pragma unroll 1
-    for (int i = TW_CH * VEC - 1; i >= 0; --i) {                    // descending, so the smallest matching eta remains
-        const int b = VEC * blk + i;
-        const T cc = Cd[b];
-        const int a = s ^ b;
-        const T cand = Pd[PL::index(a / VEC, a % VEC)] + cc;
-        if (cc < INF && cand == best) bb = b;
+    int bb = 0;
+#pragma unroll
+    for (int cbk = TW_CH - 1; cbk >= 0; --cbk) {                    // descending, so the smallest matching eta remains
+        const int bh = blk + cbk, k = lane ^ bh;
+        T p[VEC], c[VEC];
+#pragma unroll
+        for (int h = 0; h < VEC / E16; ++h) {
+            T tmp[E16];
+            ld_vec<T, E16>(Pd + h * (32 * E16) + k * E16, tmp);
+#pragma unroll
+            for (int i = 0; i < E16; ++i) p[h * E16 + i] = tmp[i];
+        }
+        ld_vec<T, VEC>(Cd + VEC * bh, c);
+#pragma unroll
+        for (int bl = VEC - 1; bl >= 0; --bl)
+            if (c[bl] < INF && p[R ^ bl] + c[bl] == best) bb = VEC * bh + bl;
     }
-    const int a = s ^ bb;
+    const int a = (VEC * lane + R) ^ bb;
     T m = INF; int ca = 0;
     const unsigned am = amask[a];
-#pragma unroll 1
-    for (int c = 0; c < bd; ++c)
-        if ((am >> c) & 1) { const T uu = sdU[c * Q + a]; if (uu < m) { m = uu; ca = c; } }
+#pragma unroll
+    for (int c = 0; c < TW_DC - 1; ++c)
+        if (c < bd && ((am >> c) & 1)) { const T uu = sdU[c * Q + a]; if (uu < m) { m = uu; ca = c; } }
     return (unsigned)a | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)bd << 20);
 }
 
@@ -318,16 +329,23 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
     }
     // ---- deltaW and the recorded path of each owned s: path = a | b << 8 | c_a << 16 | c_b << 20 | ndev << 24 ------
     T dw[VEC]; unsigned path[VEC];
-#pragma unroll
-    for (int r = 0; r < VEC; ++r) {
+    auto finish = [&](auto RC) {
+        constexpr int r = decltype(RC)::value;
         const int s = x0 + r;
         dw[r] = m0[r];
         path[r] = (unsigned)s | ((unsigned)byte_of(c01w, r) & 15u) << 16 | (1u << 24);
         if (s == 0) { dw[r] = T(0); path[r] = 0; }
         else if (best[r] < m0[r]) {
             dw[r] = best[r];
-            path[r] = tw_recover_path<T, Q>(R1, sP, sdU, amask, s, best[r], tag[r]) | (2u << 24);
+            path[r] = tw_recover_path<T, Q, r>(R1, sP, sdU, amask, lane, best[r], tag[r]) | (2u << 24);
         }
+    };
+    finish(std::integral_constant<int, 0>{});
+    if constexpr (VEC > 1) finish(std::integral_constant<int, 1>{});
+    if constexpr (VEC > 2) { finish(std::integral_constant<int, 2>{}); finish(std::integral_constant<int, 3>{}); }
+    if constexpr (VEC > 4) {
+        finish(std::integral_constant<int, 4>{}); finish(std::integral_constant<int, 5>{});
+        finish(std::integral_constant<int, 6>{}); finish(std::integral_constant<int, 7>{});
     }
     __syncwarp();                                                  // everyone is done with C and P
     // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
