@@ -29,5 +29,26 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(PKG, "host")
+HOST_COMMON = ["link_chain.cpp", "codec.cpp", "gf_field.cpp", "sim_control.cpp"]
+HOST_PROGRAMS = {"nbldpc_sim": "driver.cpp", "harness_dump": "harness_dump.cpp"}
+
+
+def build_host(force=False):
+    """C++ harness (the reference's CSimulation / CComm / CNBLDPC call surface on top of the C ABI)"""
+    build()
+    out = []
+    for exe, main in HOST_PROGRAMS.items():
+        path = os.path.join(HOST, exe)
+        srcs = [os.path.join(HOST, f) for f in [main] + HOST_COMMON]
+        deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [LIB]
+        if force or not os.path.exists(path) or any(os.path.getmtime(d) > os.path.getmtime(path) for d in deps):
+            subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", "-o", path] + srcs +
+                                  ["-L" + PKG, "-lnbldpc_b200", "-Wl,-rpath,$ORIGIN/.."])
+        out.append(path)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))
