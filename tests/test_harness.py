@@ -97,5 +97,6 @@ def test_simulation_driver_reproduces_reference_fer_point(tmp_path):
     out = subprocess.run([exe, "prof.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=600).stdout
     rows = [l for l in out.replace("\r", "\n").splitlines() if l.startswith("3\t")]
     last = rows[-1].split("\t")
-    assert float(last[1]) == 51, rows[-1]
-    assert abs(float(last[5]) - 51 / 3380) < 1e-9, rows[-1]
+    # the row the compiled reference prints for this profile (oracle/_ref/nbldpc_ref, 83 s on one CPU core):
+    #   3  51  0  1.872226e-03  5.491864e-03  1.508876e-02  0.000000e+00
+    assert last[:7] == ["3", "51", "0", "1.872226e-03", "5.491864e-03", "1.508876e-02", "0.000000e+00"], rows[-1]
