@@ -226,7 +226,7 @@ struct nbl_decoder {
     DevGraph g{};
     size_t tsz = 4;
     // device buffers
-    int *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr, *d_ysym = nullptr;
+    int *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr, *d_ysym = nullptr, *d_rowdesc = nullptr;
     uint8_t *d_pfwd = nullptr, *d_pinv = nullptr;
     void *d_lch = nullptr, *d_v2c = nullptr, *d_c2v[2] = {nullptr, nullptr};
     uint8_t *d_vdec = nullptr, *d_dec = nullptr, *d_done = nullptr, *d_newly = nullptr;
@@ -285,7 +285,7 @@ static size_t smem_for(const nbl_decoder *d, int Q) {
 extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
     if (!d) return;
     cudaSetDevice(d->cfg.device);
-    void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_pfwd, d->d_pinv, d->d_lch, d->d_v2c,
+    void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_rowdesc, d->d_pfwd, d->d_pinv, d->d_lch, d->d_v2c,
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
                     d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -327,7 +327,23 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
         (rc = upload(&d->d_var_ptr, code->var_ptr)) || (rc = upload(&d->d_var_edge, code->var_edge)) ||
         (rc = upload(&d->d_pfwd, pf)) || (rc = upload(&d->d_pinv, pi)))
         return fail(rc);
-    d->g = DevGraph{q, code->p, N, code->M, E, code->max_dv, code->max_dc, d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_pfwd, d->d_pinv};
+    // row descriptors of the warp fast path: 32 ints per check row, TW_DSC per edge
+    const bool desc_ok = code->max_dc <= TW_DC && code->max_dv <= TW_DSC - 3;
+    if (desc_ok) {
+        std::vector<int> rd((size_t)code->M * 32, 0);
+        for (int r = 0; r < code->M; ++r) {
+            rd[(size_t)r * 32 + TW_DSC - 1] = code->chk_ptr[r];
+            rd[(size_t)r * 32 + 2 * TW_DSC - 1] = code->chk_ptr[r + 1] - code->chk_ptr[r];
+            for (int e = code->chk_ptr[r]; e < code->chk_ptr[r + 1]; ++e) {
+                int *slot = &rd[(size_t)r * 32 + TW_DSC * (e - code->chk_ptr[r])];
+                const int v = code->chk_var[e];
+                slot[0] = v; slot[1] = code->var_ptr[v + 1] - code->var_ptr[v];
+                for (int s = code->var_ptr[v]; s < code->var_ptr[v + 1]; ++s) slot[2 + s - code->var_ptr[v]] = code->var_edge[s];
+            }
+        }
+        if ((rc = upload(&d->d_rowdesc, rd))) return fail(rc);
+    }
+    d->g = DevGraph{q, code->p, N, code->M, E, code->max_dv, code->max_dc, d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_pfwd, d->d_pinv, d->d_rowdesc};
     const size_t B = cfg->max_batch;
 #define ALLOC(ptr, bytes) if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) { cudaGetLastError(); nbl_set_error("cudaMalloc failed for the decoder workspace"); return fail(NBL_ERR_ALLOC); }
     ALLOC(d->d_lch, B * N * q * d->tsz);
@@ -344,7 +360,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     d->it_ev.assign(2 * (size_t)cfg->max_iter, nullptr);
     for (auto &e : d->it_ev) if (cudaEventCreate(&e) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
     d->smem_iter = smem_for(d, q);
-    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && code->max_dc <= TW_DC && q >= 32 && !getenv("NBLDPC_FORCE_GENERIC");
+    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && !getenv("NBLDPC_FORCE_GENERIC");
     if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
     *out = d;
     return NBL_OK;

@@ -19,6 +19,7 @@ struct DevGraph {
     const int *var_edge;     // [E]   edge ids of a variable, in the code file's order (= summation order)
     const uint8_t *pfwd;     // [E][q] h_e * x
     const uint8_t *pinv;     // [E][q] h_e^-1 * x
+    const int *rowdesc;      // [M][32] warp fast path: per edge {variable, degree, edge ids...} (or null)
 };
 
 template <typename T> struct Real;

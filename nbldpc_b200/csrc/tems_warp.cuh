@@ -23,6 +23,8 @@ namespace nbl {
 constexpr int TW_DC = 4;      // maximum check degree served by the fast path
 constexpr int TW_WARPS = 4;   // warps (= check rows) per CTA
 constexpr int TW_CH = 4;      // eta-blocks per arg-min chunk
+constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, degree, up to 5 edge ids, 1 spare
+                              // (spare of edge 0 = first edge id of the row, spare of edge 1 = row degree)
 
 template <typename T, int Q> struct TwSmem {
     // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> masked costs C (search) -> output trellis Tout
@@ -160,49 +162,73 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
     const T INF = Real<T>::inf();
     const unsigned FULL = 0xffffffffu;
 
-    const int e0 = g.chk_ptr[row], dcn = g.chk_ptr[row + 1] - e0;
+    // One coalesced 128-byte load brings the whole row descriptor (per edge: variable, its degree, the edge ids of
+    // its messages in summation order), so the message loads below do not wait on a chain of index loads.
+    const int dsc = g.rowdesc[(size_t)row * 32 + lane];
+    const int e0 = __shfl_sync(FULL, dsc, TW_DSC - 1), dcn = __shfl_sync(FULL, dsc, 2 * TW_DSC - 1);
     const size_t fE = (size_t)f * g.E, fN = (size_t)f * g.N;
     const int x0 = VEC * lane;
     int syn_dec = 0, syn = 0;
     // ---- steps A-C for the row's variables (NBLDPC.cpp:977-1052) ---------------------------------------
 #pragma unroll 1
     for (int d = 0; d < dcn; ++d) {
-        const int e = e0 + d, col = g.chk_var[e];
+        const int e = e0 + d;
+        const int col = __shfl_sync(FULL, dsc, TW_DSC * d), nv = __shfl_sync(FULL, dsc, TW_DSC * d + 1);
         T post[VEC], vnew[VEC];
         ld_vec<T, VEC>(P.lch + (fN + col) * Q + x0, post);
         if (!P.first) {
+            constexpr int HOIST = 3;                               // messages loaded before the first add
+            T m[HOIST][VEC]; int ee[HOIST];
+#pragma unroll
+            for (int j = 0; j < HOIST; ++j) {
+                ee[j] = __shfl_sync(FULL, dsc, TW_DSC * d + 2 + j);
+                if (j < nv) ld_vec<T, VEC>(P.c2v_in + (fE + ee[j]) * Q + x0, m[j]);
+            }
+            const int before = (int)P.vdec[fE + e];
             T own[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) own[j] = T(0);
-#pragma unroll 1
-            for (int s = g.var_ptr[col]; s < g.var_ptr[col + 1]; ++s) {
-                const int ee = g.var_edge[s];
-                T m[VEC];
-                ld_vec<T, VEC>(P.c2v_in + (fE + ee) * Q + x0, m);
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) { post[j] = post[j] + m[j]; if (ee == e) own[j] = m[j]; }
+            for (int j = 0; j < HOIST; ++j) {
+                if (j < nv) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { post[i] = post[i] + m[j][i]; if (ee[j] == e) own[i] = m[j][i]; }
+                }
+            }
+#pragma unroll 1
+            for (int j = HOIST; j < nv; ++j) {                      // variables of degree > HOIST
+                const int ej = __shfl_sync(FULL, dsc, TW_DSC * d + 2 + j);
+                T mj[VEC];
+                ld_vec<T, VEC>(P.c2v_in + (fE + ej) * Q + x0, mj);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { post[i] = post[i] + mj[i]; if (ej == e) own[i] = mj[i]; }
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j) vnew[j] = post[j] - own[j];
-        } else {
+            const int dpost = warp_decide<T, VEC>(post, lane);
+            int dfin = warp_decide<T, VEC>(vnew, lane);
+            if (P.w_old != T(0) && dfin != before) {                 // warp-uniform
+                T vold[VEC];
+                ld_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vold);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) vnew[j] = post[j];
+                for (int j = 0; j < VEC; ++j) vnew[j] = P.w_old * vold[j] + P.w_new * vnew[j];   // -fmad=false
+                dfin = warp_decide<T, VEC>(vnew, lane);
+            }
+            st_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vnew);
+            st_vec<T, VEC>(R1 + d * Q + x0, vnew);
+            const int bt = g.pfwd[(size_t)e * Q + dfin];
+            if (lane == 0) { P.vdec[fE + e] = (uint8_t)dfin; P.dec[fN + col] = (uint8_t)dpost; meta[d] = dfin; meta[TW_DC + d] = bt; }
+            syn ^= bt;
+            syn_dec ^= g.pfwd[(size_t)e * Q + dpost];
+        } else {                                                  // iteration 1: c2v == 0, v2c == L_ch, no damping
+            const int dpost = warp_decide<T, VEC>(post, lane);
+            st_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, post);
+            st_vec<T, VEC>(R1 + d * Q + x0, post);
+            const int bt = g.pfwd[(size_t)e * Q + dpost];
+            if (lane == 0) { P.vdec[fE + e] = (uint8_t)dpost; P.dec[fN + col] = (uint8_t)dpost; meta[d] = dpost; meta[TW_DC + d] = bt; }
+            syn ^= bt;
+            syn_dec ^= bt;
         }
-        const int dpost = warp_decide<T, VEC>(post, lane);
-        int dfin = warp_decide<T, VEC>(vnew, lane);
-        if (!P.first && P.w_old != T(0) && dfin != (int)P.vdec[fE + e]) {            // warp-uniform
-            T vold[VEC];
-            ld_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vold);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) vnew[j] = P.w_old * vold[j] + P.w_new * vnew[j];       // -fmad=false
-            dfin = warp_decide<T, VEC>(vnew, lane);
-        }
-        st_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vnew);
-        st_vec<T, VEC>(R1 + d * Q + x0, vnew);
-        const int bt = g.pfwd[(size_t)e * Q + dfin];
-        if (lane == 0) { P.vdec[fE + e] = (uint8_t)dfin; P.dec[fN + col] = (uint8_t)dpost; meta[d] = dfin; meta[TW_DC + d] = bt; }
-        syn ^= bt;
-        syn_dec ^= g.pfwd[(size_t)e * Q + dpost];
     }
     if (lane == 0 && syn_dec != 0) P.flag[f] = 1;
     __syncwarp();
