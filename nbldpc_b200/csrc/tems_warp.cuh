@@ -1,17 +1,21 @@
 // Fast path of the fused iteration kernel for T-EMS with n_c <= 2 (the headline configuration):
 // ONE WARP per (frame, check row), VEC = Q/32 consecutive field elements per lane.
 //
-// Same arithmetic and the same scan order (column, then eta ascending) as the generic group kernel in
-// decoder.cu / cn_tems.cuh -- so the two produce identical bits -- but organised for the issue-bound search:
+// Same results as the generic group kernel (decoder.cu / cn_tems.cuh), organised for the issue-bound search:
 //   * no block-level barriers: every exchange between lanes is a __syncwarp on the warp's private smem slab;
-//   * the pair search is a register-tiled min-plus XOR-convolution.  Lane t owns deltaW candidates for
-//     s = VEC*t .. VEC*t+VEC-1 in registers.  For column d and eta-block bh it loads the VEC running minima
-//     P_d[VEC*(t^bh) ..] once (conflict-free 128-bit loads) and the VEC masked costs C_d[VEC*bh ..] (uniform
-//     broadcast loads); entry bl of the block then serves all VEC outputs from registers:
-//         best[r] = min(best[r], p[r ^ bl] + c[bl])          -> 1 FADD + 1 FMNMX per leaf, no per-leaf load.
-//     Deviations that are not allowed in column d are skipped with a warp-uniform branch on a ballot mask.
+//   * the pair search uses the structure of the allowed sets.  Let c0(x), c1(x) be the cheapest / second cheapest
+//     column of eta = x and m0(x) <= m1(x) their costs (TEMS_Min).  For a pair (a, b) with a ^ b = s the cheapest
+//     valid assignment of two DIFFERENT columns is m0(a) + m0(b) when c0(a) != c0(b), else
+//     min(m0(a) + m1(b), m1(a) + m0(b)); columns beyond the second never win (c1(b) != c0(b) is always available).
+//     So with  D_c[x] = (c0(x) == c ? m1(x) : m0(x))  -- the cheapest column of x other than c --
+//         deltaW2[s] = min over a != 0 of  m0(a) + D_{c0(a)}[s ^ a] ,
+//     255 x q leaves instead of the ~94 k configurations the reference enumerates (or the 98 k of a per-column
+//     scan), every leaf useful.  (n_r = 1: D_c[x] = +inf where c0(x) == c.  n_r >= 2 all give this minimum.)
+//   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; entry a = VEC*bh + bl loads the VEC values
+//     D_c[VEC*(t^bh) ..] with conflict-free 128-bit loads and serves all VEC outputs from registers:
+//         best[r] = min(best[r], d[r ^ bl] + m0(a))          -> 1 FADD + 1 FMNMX per leaf, no branches.
 //   * arg-min bookkeeping is done per chunk of TW_CH eta-blocks (3 instructions per output per chunk); the
-//     winning (column, chunk) is re-scanned once at the end to recover the exact eta of the recorded path.
+//     winning chunk is re-scanned once at the end to recover the exact pair of the recorded path.
 //   * everything outside the search is written as short loops over the row's edges with 128-bit shared-memory
 //     accesses, to keep the kernel inside the instruction cache and free of bank conflicts.
 #pragma once
@@ -22,17 +26,17 @@ namespace nbl {
 
 constexpr int TW_DC = 4;      // maximum check degree served by the fast path
 constexpr int TW_WARPS = 4;   // warps (= check rows) per CTA
-constexpr int TW_CH = 4;      // eta-blocks per arg-min chunk
+constexpr int TW_CH = 2;      // eta-blocks per arg-min chunk
 constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, degree, up to 5 edge ids, 1 spare
                               // (spare of edge 0 = first edge id of the row, spare of edge 1 = row degree)
 
 template <typename T, int Q> struct TwSmem {
-    // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> masked costs C (search) -> output trellis Tout
+    // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> D_c, split layout (search) -> output trellis Tout
     //                 dU [TW_DC][Q]
-    //                 P  [TW_DC-1][Q] running minima, "split" layout (PLayout)
-    //                 bytes c01[Q] (c0 | c1 << 4), amask[Q];  ints meta[2*TW_DC] (decide, beta per edge)
-    static constexpr size_t t_elems = (size_t)Q * (2 * TW_DC + (TW_DC - 1));
-    static constexpr size_t bytes_per_warp = ((t_elems * sizeof(T) + 2 * (size_t)Q + 2 * TW_DC * sizeof(int) + 15) / 16) * 16;
+    //                 M0 [Q]          m0(x), +inf at x = 0 (uniform operand of the search)
+    //                 bytes c01[Q] (c0 | c1 << 4);  ints meta[2*TW_DC] (decide, beta per edge)
+    static constexpr size_t t_elems = (size_t)Q * (2 * TW_DC + 1);
+    static constexpr size_t bytes_per_warp = ((t_elems * sizeof(T) + (size_t)Q + 2 * TW_DC * sizeof(int) + 15) / 16) * 16;
     static constexpr size_t bytes = bytes_per_warp * TW_WARPS;
 };
 
@@ -102,43 +106,23 @@ template <typename T, int VEC> __device__ __forceinline__ int warp_decide(const 
     return kmax == K(0) ? 0 : x;
 }
 
-// Recover the recorded two-deviation path of output s = VEC*lane + R from the winning (column, chunk) tag by
-// re-scanning that chunk with the same register tile as the search (R is a compile-time index, so p[R ^ bl] is a
-// register).  Returns a | b << 8 | c_a << 16 | c_b << 20.
-template <typename T, int Q, int R>
-__device__ __forceinline__ unsigned tw_recover_path(const T *__restrict__ R1, const T *__restrict__ sP, const T *__restrict__ sdU,
-                                                    const uint8_t *__restrict__ amask, int lane, T best, int tag) {
+// Recover the recorded two-deviation path of output s from the winning chunk tag (= its last eta-block) by re-scanning
+// the chunk's entries in the search order.  Returns a | b << 8 | c_a << 16 | c_b << 20.
+template <typename T, int Q>
+__device__ __forceinline__ unsigned tw_recover_path(const T *__restrict__ sD, const T *__restrict__ sM0,
+                                                    const uint8_t *__restrict__ c01, int s, T best, int tag) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
-    constexpr int E16 = PL::E16;
-    const T INF = Real<T>::inf();
-    const int bd = tag >> 5, blk = (tag & 31) - (TW_CH - 1);
-    const T *Pd = sP + (size_t)(bd - 1) * Q;
-    const T *Cd = R1 + (size_t)bd * Q;
-    int bb = 0;
-#pragma unroll
-    for (int cbk = TW_CH - 1; cbk >= 0; --cbk) {                    // descending, so the smallest matching eta remains
-        const int bh = blk + cbk, k = lane ^ bh;
-        T p[VEC], c[VEC];
-#pragma unroll
-        for (int h = 0; h < VEC / E16; ++h) {
-            T tmp[E16];
-            ld_vec<T, E16>(Pd + h * (32 * E16) + k * E16, tmp);
-#pragma unroll
-            for (int i = 0; i < E16; ++i) p[h * E16 + i] = tmp[i];
-        }
-        ld_vec<T, VEC>(Cd + VEC * bh, c);
-#pragma unroll
-        for (int bl = VEC - 1; bl >= 0; --bl)
-            if (c[bl] < INF && p[R ^ bl] + c[bl] == best) bb = VEC * bh + bl;
+    int aa = 0;
+#pragma unroll 1
+    for (int a = VEC * (tag + 1) - 1; a >= VEC * (tag + 1 - TW_CH); --a) {      // descending: the smallest matching eta remains
+        const int c = c01[a] & 15, b = s ^ a;
+        const T cand = sD[(size_t)c * Q + PL::index(b / VEC, b % VEC)] + sM0[a];
+        if (cand == best) aa = a;
     }
-    const int a = (VEC * lane + R) ^ bb;
-    T m = INF; int ca = 0;
-    const unsigned am = amask[a];
-#pragma unroll
-    for (int c = 0; c < TW_DC - 1; ++c)
-        if (c < bd && ((am >> c) & 1)) { const T uu = sdU[c * Q + a]; if (uu < m) { m = uu; ca = c; } }
-    return (unsigned)a | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)bd << 20);
+    const int bb = s ^ aa, ca = c01[aa] & 15, kb = c01[bb];
+    const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
+    return (unsigned)aa | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 20);
 }
 
 template <typename T, int Q>
@@ -155,10 +139,9 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
 
     T *R1 = reinterpret_cast<T *>(smem_raw + TwSmem<T, Q>::bytes_per_warp * warp);
     T *sdU = R1 + (size_t)TW_DC * Q;
-    T *sP = sdU + (size_t)TW_DC * Q;
-    uint8_t *c01 = reinterpret_cast<uint8_t *>(sP + (size_t)(TW_DC - 1) * Q);
-    uint8_t *amask = c01 + Q;
-    int *meta = reinterpret_cast<int *>(amask + Q);                 // [0..TW_DC) decide(v2c_d), [TW_DC..) beta_d
+    T *sM0 = sdU + (size_t)TW_DC * Q;
+    uint8_t *c01 = reinterpret_cast<uint8_t *>(sM0 + Q);
+    int *meta = reinterpret_cast<int *>(c01 + Q);                   // [0..TW_DC) decide(v2c_d), [TW_DC..) beta_d
     const T INF = Real<T>::inf();
     const unsigned FULL = 0xffffffffu;
 
@@ -245,7 +228,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
         st_vec<T, VEC>(sdU + d * Q + x0, u);
     }
     __syncwarp();                                                  // all reads of v2c in R1 are done
-    // ---- column order per eta (TEMS_Get_Min), masked costs C, running minima P ---------------------------------
+    // ---- column order per eta (TEMS_Get_Min): c0, c1, m0, m1;  D_c for the search ---------------------------------
     T m0[VEC], m1[VEC]; unsigned long long c01w = 0;
     {
         T u[TW_DC][VEC];
@@ -257,11 +240,9 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
                 for (int j = 0; j < VEC; ++j) u[d][j] = INF;
             }
         }
-        unsigned long long amw = 0;
-        T cv[TW_DC][VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            int k0 = 0, k1 = 0; unsigned am = 0;
+            int k0 = 0, k1 = 0;
 #pragma unroll
             for (int d = 0; d < TW_DC; ++d) {
                 int rank = 0;
@@ -270,110 +251,87 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
                     if (c < d) rank += (c < dcn) && (u[c][j] <= u[d][j]);           // stable: the lower column wins ties
                     if (c > d) rank += (c < dcn) && (u[c][j] < u[d][j]);
                 }
-                if (d < dcn) {
-                    if (rank < P.p0) am |= 1u << d;
-                    if (rank == 0) k0 = d;
-                    if (rank == 1) k1 = d;
-                }
+                if (d < dcn) { if (rank == 0) k0 = d; if (rank == 1) k1 = d; }
             }
             c01w |= (unsigned long long)(k0 | (k1 << 4)) << (8 * j);
-            amw |= (unsigned long long)am << (8 * j);
             m0[j] = INF; m1[j] = INF;
 #pragma unroll
-            for (int d = 0; d < TW_DC; ++d) {
-                cv[d][j] = (x0 + j != 0 && ((am >> d) & 1)) ? u[d][j] : INF;
-                if (k0 == d) m0[j] = u[d][j];
-                if (k1 == d) m1[j] = u[d][j];
-            }
+            for (int d = 0; d < TW_DC; ++d) { if (k0 == d) m0[j] = u[d][j]; if (k1 == d) m1[j] = u[d][j]; }
         }
         st_bytes<VEC>(c01 + x0, c01w);
-        st_bytes<VEC>(amask + x0, amw);
-        T run[VEC];
+        {
+            T mm[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) run[j] = INF;
+            for (int j = 0; j < VEC; ++j) mm[j] = (x0 + j == 0) ? INF : m0[j];
+            st_vec<T, VEC>(sM0 + x0, mm);
+        }
+        const T second_ok = P.p0 >= 2 ? T(0) : INF;                 // n_r = 1: only the cheapest column may deviate
 #pragma unroll
-        for (int d = 0; d < TW_DC; ++d) {
-            if (d < dcn) {
-                st_vec<T, VEC>(R1 + d * Q + x0, cv[d]);             // C_d
+        for (int c = 0; c < TW_DC; ++c) {
+            if (c < dcn) {                                          // D_c[x]: cheapest allowed column of x other than c
+                constexpr int E16 = PL::E16;
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) if (cv[d][j] < run[j]) run[j] = cv[d][j];     // strict '<'
-                if (d < TW_DC - 1) {                                // P_{d+1} = min over columns <= d, split layout
-                    constexpr int E16 = PL::E16;
+                for (int h = 0; h < VEC / E16; ++h) {
+                    T tmp[E16];
 #pragma unroll
-                    for (int h = 0; h < VEC / E16; ++h) {
-                        T tmp[E16];
-#pragma unroll
-                        for (int i = 0; i < E16; ++i) tmp[i] = run[h * E16 + i];
-                        st_vec<T, E16>(sP + d * Q + h * (32 * E16) + lane * E16, tmp);
+                    for (int i = 0; i < E16; ++i) {
+                        const int j = h * E16 + i;
+                        const T v = ((byte_of(c01w, j) & 15) == c) ? (m1[j] + second_ok) : m0[j];
+                        tmp[i] = (x0 + j == 0) ? INF : v;
                     }
+                    st_vec<T, E16>(R1 + (size_t)c * Q + h * (32 * E16) + lane * E16, tmp);
                 }
             }
         }
     }
     __syncwarp();
-    // ---- pair search ----------------------------------------------------------------------------------------------
+    // ---- pair search: best[s] = min_a m0(a) + D_{c0(a)}[s ^ a] ----------------------------------------------------------
     T best[VEC], prev[VEC]; int tag[VEC];
 #pragma unroll
     for (int r = 0; r < VEC; ++r) { best[r] = INF; prev[r] = INF; tag[r] = 0; }
     if (P.p1 >= 2) {
 #pragma unroll 1
-        for (int d = 1; d < dcn; ++d) {
-            const T *Pd = sP + (size_t)(d - 1) * Q;
-            const T *Cd = R1 + (size_t)d * Q;
-#pragma unroll 1
-            for (int bh = 0; bh < 32; ++bh) {
-                // bit i of `live` = entry i of this eta-block may deviate in column d (same value in every lane)
-                const unsigned live = __ballot_sync(FULL, Cd[VEC * bh + (lane & (VEC - 1))] < INF);
-                T p[VEC], c[VEC];
-                {
-                    const int k = lane ^ bh;
-                    constexpr int E16 = PL::E16;
+        for (int bh = 0; bh < 32; ++bh) {
+            const unsigned long long cw = ld_bytes<VEC>(c01 + VEC * bh);           // columns of the block's entries (uniform)
+            T cost[VEC];
+            ld_vec<T, VEC>(sM0 + VEC * bh, cost);                                  // their costs (uniform)
+            const int k = lane ^ bh;
 #pragma unroll
-                    for (int h = 0; h < VEC / E16; ++h) {
-                        T tmp[E16];
-                        ld_vec<T, E16>(Pd + h * (32 * E16) + k * E16, tmp);
+            for (int bl = 0; bl < VEC; ++bl) {
+                const T *Dc = R1 + (size_t)(byte_of(cw, bl) & 15) * Q;
+                T p[VEC];
+                constexpr int E16 = PL::E16;
 #pragma unroll
-                        for (int i = 0; i < E16; ++i) p[h * E16 + i] = tmp[i];
-                    }
+                for (int h = 0; h < VEC / E16; ++h) {
+                    T tmp[E16];
+                    ld_vec<T, E16>(Dc + h * (32 * E16) + k * E16, tmp);
+#pragma unroll
+                    for (int i = 0; i < E16; ++i) p[h * E16 + i] = tmp[i];
                 }
-                ld_vec<T, VEC>(Cd + VEC * bh, c);
 #pragma unroll
-                for (int bl = 0; bl < VEC; ++bl) {
-                    if (live & (1u << bl)) {
+                for (int r = 0; r < VEC; ++r) best[r] = fmin(best[r], p[r ^ bl] + cost[bl]);
+            }
+            if ((bh & (TW_CH - 1)) == TW_CH - 1) {
 #pragma unroll
-                        for (int r = 0; r < VEC; ++r) best[r] = fmin(best[r], p[r ^ bl] + c[bl]);
-                    }
-                }
-                if ((bh & (TW_CH - 1)) == TW_CH - 1) {
-                    const int id = d * 32 + bh;                     // last block of the chunk
-#pragma unroll
-                    for (int r = 0; r < VEC; ++r)
-                        if (best[r] < prev[r]) { prev[r] = best[r]; tag[r] = id; }
-                }
+                for (int r = 0; r < VEC; ++r)
+                    if (best[r] < prev[r]) { prev[r] = best[r]; tag[r] = bh; }     // last block of the winning chunk
             }
         }
     }
     // ---- deltaW and the recorded path of each owned s: path = a | b << 8 | c_a << 16 | c_b << 20 | ndev << 24 ------
     T dw[VEC]; unsigned path[VEC];
-    auto finish = [&](auto RC) {
-        constexpr int r = decltype(RC)::value;
+#pragma unroll
+    for (int r = 0; r < VEC; ++r) {
         const int s = x0 + r;
         dw[r] = m0[r];
         path[r] = (unsigned)s | ((unsigned)byte_of(c01w, r) & 15u) << 16 | (1u << 24);
         if (s == 0) { dw[r] = T(0); path[r] = 0; }
         else if (best[r] < m0[r]) {
             dw[r] = best[r];
-            path[r] = tw_recover_path<T, Q, r>(R1, sP, sdU, amask, lane, best[r], tag[r]) | (2u << 24);
+            path[r] = tw_recover_path<T, Q>(R1, sM0, c01, s, best[r], tag[r]) | (2u << 24);
         }
-    };
-    finish(std::integral_constant<int, 0>{});
-    if constexpr (VEC > 1) finish(std::integral_constant<int, 1>{});
-    if constexpr (VEC > 2) { finish(std::integral_constant<int, 2>{}); finish(std::integral_constant<int, 3>{}); }
-    if constexpr (VEC > 4) {
-        finish(std::integral_constant<int, 4>{}); finish(std::integral_constant<int, 5>{});
-        finish(std::integral_constant<int, 6>{}); finish(std::integral_constant<int, 7>{});
     }
-    __syncwarp();                                                  // everyone is done with C and P
+    __syncwarp();                                                  // everyone is done with D
     // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
     T *Tout = R1;
 #pragma unroll 1
