@@ -14,8 +14,9 @@
 //   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; entry a = VEC*bh + bl loads the VEC values
 //     D_c[VEC*(t^bh) ..] with conflict-free 128-bit loads and serves all VEC outputs from registers:
 //         best[r] = min(best[r], d[r ^ bl] + m0(a))          -> 1 FADD + 1 FMNMX per leaf, no branches.
-//   * arg-min bookkeeping is done per chunk of TW_CH eta-blocks (3 instructions per output per chunk); the
-//     winning chunk is re-scanned once at the end to recover the exact pair of the recorded path.
+//   * arg-min bookkeeping is done per eta-block (2 instructions per output per block: the running minima alternate
+//     between two register sets, so "did this block improve it" is one compare); the winning block is re-scanned
+//     once at the end to recover the exact pair of the recorded path.
 //   * everything outside the search is written as short loops over the row's edges with 128-bit shared-memory
 //     accesses, to keep the kernel inside the instruction cache and free of bank conflicts.
 #pragma once
@@ -26,7 +27,6 @@ namespace nbl {
 
 constexpr int TW_DC = 4;      // maximum check degree served by the fast path
 constexpr int TW_WARPS = 4;   // warps (= check rows) per CTA
-constexpr int TW_CH = 2;      // eta-blocks per arg-min chunk
 constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, degree, up to 5 edge ids, 1 spare
                               // (spare of edge 0 = first edge id of the row, spare of edge 1 = row degree)
 
@@ -106,21 +106,24 @@ template <typename T, int VEC> __device__ __forceinline__ int warp_decide(const 
     return kmax == K(0) ? 0 : x;
 }
 
-// Recover the recorded two-deviation path of output s from the winning chunk tag (= its last eta-block) by re-scanning
-// the chunk's entries in the search order.  Returns a | b << 8 | c_a << 16 | c_b << 20.
-template <typename T, int Q>
+// Recover the recorded two-deviation path of output s = VEC*lane + R from the winning eta-block `bh` by re-scanning its
+// VEC entries in the search order.  Returns a | b << 8 | c_a << 16 | c_b << 20.
+template <typename T, int Q, int R>
 __device__ __forceinline__ unsigned tw_recover_path(const T *__restrict__ sD, const T *__restrict__ sM0,
-                                                    const uint8_t *__restrict__ c01, int s, T best, int tag) {
+                                                    const uint8_t *__restrict__ c01, int lane, T best, int bh) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
-    int aa = 0;
-#pragma unroll 1
-    for (int a = VEC * (tag + 1) - 1; a >= VEC * (tag + 1 - TW_CH); --a) {      // descending: the smallest matching eta remains
-        const int c = c01[a] & 15, b = s ^ a;
-        const T cand = sD[(size_t)c * Q + PL::index(b / VEC, b % VEC)] + sM0[a];
-        if (cand == best) aa = a;
+    const unsigned long long cw = ld_bytes<VEC>(c01 + VEC * bh);
+    T cost[VEC];
+    ld_vec<T, VEC>(sM0 + VEC * bh, cost);
+    const int k = lane ^ bh;
+    int bl0 = 0;
+#pragma unroll
+    for (int bl = VEC - 1; bl >= 0; --bl) {                         // descending: the smallest matching eta remains
+        const T cand = sD[(size_t)(byte_of(cw, bl) & 15) * Q + PL::index(k, R ^ bl)] + cost[bl];
+        if (cand == best) bl0 = bl;
     }
-    const int bb = s ^ aa, ca = c01[aa] & 15, kb = c01[bb];
+    const int aa = VEC * bh + bl0, bb = (VEC * lane + R) ^ aa, ca = byte_of(cw, bl0) & 15, kb = c01[bb];
     const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
     return (unsigned)aa | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 20);
 }
@@ -286,12 +289,12 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
     }
     __syncwarp();
     // ---- pair search: best[s] = min_a m0(a) + D_{c0(a)}[s ^ a] ----------------------------------------------------------
-    T best[VEC], prev[VEC]; int tag[VEC];
+    T best[VEC], alt[VEC]; int tag[VEC];
 #pragma unroll
-    for (int r = 0; r < VEC; ++r) { best[r] = INF; prev[r] = INF; tag[r] = 0; }
+    for (int r = 0; r < VEC; ++r) { best[r] = INF; alt[r] = INF; tag[r] = 0; }
     if (P.p1 >= 2) {
-#pragma unroll 1
-        for (int bh = 0; bh < 32; ++bh) {
+        // one eta-block: `to` = min(`from`, candidates of the block); tag the block where it got smaller
+        auto block = [&](int bh, const T (&from)[VEC], T (&to)[VEC]) {
             const unsigned long long cw = ld_bytes<VEC>(c01 + VEC * bh);           // columns of the block's entries (uniform)
             T cost[VEC];
             ld_vec<T, VEC>(sM0 + VEC * bh, cost);                                  // their costs (uniform)
@@ -309,27 +312,33 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
                     for (int i = 0; i < E16; ++i) p[h * E16 + i] = tmp[i];
                 }
 #pragma unroll
-                for (int r = 0; r < VEC; ++r) best[r] = fmin(best[r], p[r ^ bl] + cost[bl]);
+                for (int r = 0; r < VEC; ++r) to[r] = fmin(bl == 0 ? from[r] : to[r], p[r ^ bl] + cost[bl]);
             }
-            if ((bh & (TW_CH - 1)) == TW_CH - 1) {
 #pragma unroll
-                for (int r = 0; r < VEC; ++r)
-                    if (best[r] < prev[r]) { prev[r] = best[r]; tag[r] = bh; }     // last block of the winning chunk
-            }
-        }
+            for (int r = 0; r < VEC; ++r) if (to[r] < from[r]) tag[r] = bh;
+        };
+#pragma unroll 1
+        for (int bh = 0; bh < 32; bh += 2) { block(bh, best, alt); block(bh + 1, alt, best); }
     }
     // ---- deltaW and the recorded path of each owned s: path = a | b << 8 | c_a << 16 | c_b << 20 | ndev << 24 ------
     T dw[VEC]; unsigned path[VEC];
-#pragma unroll
-    for (int r = 0; r < VEC; ++r) {
+    auto finish = [&](auto RC) {
+        constexpr int r = decltype(RC)::value;
         const int s = x0 + r;
         dw[r] = m0[r];
         path[r] = (unsigned)s | ((unsigned)byte_of(c01w, r) & 15u) << 16 | (1u << 24);
         if (s == 0) { dw[r] = T(0); path[r] = 0; }
         else if (best[r] < m0[r]) {
             dw[r] = best[r];
-            path[r] = tw_recover_path<T, Q>(R1, sM0, c01, s, best[r], tag[r]) | (2u << 24);
+            path[r] = tw_recover_path<T, Q, r>(R1, sM0, c01, lane, best[r], tag[r]) | (2u << 24);
         }
+    };
+    finish(std::integral_constant<int, 0>{});
+    if constexpr (VEC > 1) finish(std::integral_constant<int, 1>{});
+    if constexpr (VEC > 2) { finish(std::integral_constant<int, 2>{}); finish(std::integral_constant<int, 3>{}); }
+    if constexpr (VEC > 4) {
+        finish(std::integral_constant<int, 4>{}); finish(std::integral_constant<int, 5>{});
+        finish(std::integral_constant<int, 6>{}); finish(std::integral_constant<int, 7>{});
     }
     __syncwarp();                                                  // everyone is done with D
     // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
