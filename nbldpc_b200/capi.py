@@ -45,7 +45,7 @@ def lib():
     """Load (building first if the sources are newer) the shared library; raises if it cannot be had."""
     global _lib
     if _lib is None:
-        path = _build.build() if os.path.isdir(_build.CSRC) else _build.LIB
+        path = os.environ.get("NBLDPC_LIB") or (_build.build() if os.path.isdir(_build.CSRC) else _build.LIB)   # override: A/B builds
         L = C.CDLL(path)
         vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.c_void_p   # data pointers may be device addresses
         L.nbl_last_error.restype = C.c_char_p

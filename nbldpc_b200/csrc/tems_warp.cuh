@@ -32,10 +32,9 @@ constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, 
 
 template <typename T, int Q> struct TwSmem {
     // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> D_c, split layout (search) -> output trellis Tout
-    //                 dU [TW_DC][Q]
     //                 M0 [Q]          m0(x), +inf at x = 0 (uniform operand of the search)
     //                 bytes c01[Q] (c0 | c1 << 4);  ints meta[2*TW_DC] (decide, beta per edge)
-    static constexpr size_t t_elems = (size_t)Q * (2 * TW_DC + 1);
+    static constexpr size_t t_elems = (size_t)Q * (TW_DC + 1);
     static constexpr size_t bytes_per_warp = ((t_elems * sizeof(T) + (size_t)Q + 2 * TW_DC * sizeof(int) + 15) / 16) * 16;
     static constexpr size_t bytes = bytes_per_warp * TW_WARPS;
 };
@@ -107,21 +106,22 @@ template <typename T, int VEC> __device__ __forceinline__ int warp_decide(const 
 }
 
 // Recover the recorded two-deviation path of output s = VEC*lane + R from the winning eta-block `bh` by re-scanning its
-// VEC entries in the search order.  Returns a | b << 8 | c_a << 16 | c_b << 20.
+// VEC entries in the search order.  Returns a | b << 8 | c_a << 16 | c_b << 20 and the two deviation costs
+// dU[c_a][a] (= m0(a)) and dU[c_b][b] (= D_{c_a}[b]).
 template <typename T, int Q, int R>
 __device__ __forceinline__ unsigned tw_recover_path(const T *__restrict__ sD, const T *__restrict__ sM0,
-                                                    const uint8_t *__restrict__ c01, int lane, T best, int bh) {
+                                                    const uint8_t *__restrict__ c01, int lane, T best, int bh, T &ua, T &ub) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
     const unsigned long long cw = ld_bytes<VEC>(c01 + VEC * bh);
     T cost[VEC];
     ld_vec<T, VEC>(sM0 + VEC * bh, cost);
     const int k = lane ^ bh;
-    int bl0 = 0;
+    int bl0 = 0; ua = T(0); ub = T(0);
 #pragma unroll
     for (int bl = VEC - 1; bl >= 0; --bl) {                         // descending: the smallest matching eta remains
-        const T cand = sD[(size_t)(byte_of(cw, bl) & 15) * Q + PL::index(k, R ^ bl)] + cost[bl];
-        if (cand == best) bl0 = bl;
+        const T dv = sD[(size_t)(byte_of(cw, bl) & 15) * Q + PL::index(k, R ^ bl)];
+        if (dv + cost[bl] == best) { bl0 = bl; ua = cost[bl]; ub = dv; }
     }
     const int aa = VEC * bh + bl0, bb = (VEC * lane + R) ^ aa, ca = byte_of(cw, bl0) & 15, kb = c01[bb];
     const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
@@ -141,8 +141,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
     if (P.early_stop && P.done[f]) return;
 
     T *R1 = reinterpret_cast<T *>(smem_raw + TwSmem<T, Q>::bytes_per_warp * warp);
-    T *sdU = R1 + (size_t)TW_DC * Q;
-    T *sM0 = sdU + (size_t)TW_DC * Q;
+    T *sM0 = R1 + (size_t)TW_DC * Q;
     uint8_t *c01 = reinterpret_cast<uint8_t *>(sM0 + Q);
     int *meta = reinterpret_cast<int *>(c01 + Q);                   // [0..TW_DC) decide(v2c_d), [TW_DC..) beta_d
     const T INF = Real<T>::inf();
@@ -218,31 +217,26 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
     }
     if (lane == 0 && syn_dec != 0) P.flag[f] = 1;
     __syncwarp();
-    // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)] ------------------------
-#pragma unroll 1
-    for (int d = 0; d < dcn; ++d) {
-        const int sd = meta[d], bt = meta[TW_DC + d];
-        const T vmax = R1[d * Q + sd];
-        const int bh = bt / VEC, bl = bt % VEC;
-        const unsigned long long kk = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + VEC * (lane ^ bh));
-        T u[VEC];
+    // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)], own etas in registers -------
+    T u[TW_DC][VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) u[j] = vmax - R1[d * Q + byte_of(kk, j ^ bl)];   // eta^beta = VEC*(lane^bh) + (j^bl)
-        st_vec<T, VEC>(sdU + d * Q + x0, u);
+    for (int d = 0; d < TW_DC; ++d) {
+        if (d < dcn) {
+            const int sd = meta[d], bt = meta[TW_DC + d];
+            const T vmax = R1[d * Q + sd];
+            const int bh = bt / VEC, bl = bt % VEC;
+            const unsigned long long kk = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + VEC * (lane ^ bh));
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) u[d][j] = vmax - R1[d * Q + byte_of(kk, j ^ bl)];   // eta^beta = VEC*(lane^bh) + (j^bl)
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) u[d][j] = INF;
+        }
     }
     __syncwarp();                                                  // all reads of v2c in R1 are done
     // ---- column order per eta (TEMS_Get_Min): c0, c1, m0, m1;  D_c for the search ---------------------------------
     T m0[VEC], m1[VEC]; unsigned long long c01w = 0;
     {
-        T u[TW_DC][VEC];
-#pragma unroll
-        for (int d = 0; d < TW_DC; ++d) {
-            if (d < dcn) ld_vec<T, VEC>(sdU + d * Q + x0, u[d]);
-            else {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) u[d][j] = INF;
-            }
-        }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             int k0 = 0, k1 = 0;
@@ -321,16 +315,16 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
         for (int bh = 0; bh < 32; bh += 2) { block(bh, best, alt); block(bh + 1, alt, best); }
     }
     // ---- deltaW and the recorded path of each owned s: path = a | b << 8 | c_a << 16 | c_b << 20 | ndev << 24 ------
-    T dw[VEC]; unsigned path[VEC];
+    T dw[VEC], ua[VEC], ub[VEC]; unsigned path[VEC];
     auto finish = [&](auto RC) {
         constexpr int r = decltype(RC)::value;
         const int s = x0 + r;
-        dw[r] = m0[r];
+        dw[r] = m0[r]; ua[r] = T(0); ub[r] = T(0);
         path[r] = (unsigned)s | ((unsigned)byte_of(c01w, r) & 15u) << 16 | (1u << 24);
         if (s == 0) { dw[r] = T(0); path[r] = 0; }
         else if (best[r] < m0[r]) {
             dw[r] = best[r];
-            path[r] = tw_recover_path<T, Q, r>(R1, sM0, c01, lane, best[r], tag[r]) | (2u << 24);
+            path[r] = tw_recover_path<T, Q, r>(R1, sM0, c01, lane, best[r], tag[r], ua[r], ub[r]) | (2u << 24);
         }
     };
     finish(std::integral_constant<int, 0>{});
@@ -364,7 +358,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
             for (int r = 0; r < VEC; ++r) {
                 if (pending & (3u << (2 * r))) {
                     const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
-                    const T va = dw[r] - sdU[ca * Q + a], vb = dw[r] - sdU[cb * Q + b];
+                    const T va = dw[r] - ua[r], vb = dw[r] - ub[r];
                     if (pending & (1u << (2 * r))) { if (va < Tout[ca * Q + b]) Tout[ca * Q + b] = va; }
                     if (pending & (2u << (2 * r))) { if (vb < Tout[cb * Q + a]) Tout[cb * Q + a] = vb; }
                 }
@@ -374,7 +368,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
             for (int r = 0; r < VEC; ++r) {
                 if (pending & (3u << (2 * r))) {
                     const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
-                    const T va = dw[r] - sdU[ca * Q + a], vb = dw[r] - sdU[cb * Q + b];
+                    const T va = dw[r] - ua[r], vb = dw[r] - ub[r];
                     if (!(va < Tout[ca * Q + b])) pending &= ~(1u << (2 * r));
                     if (!(vb < Tout[cb * Q + a])) pending &= ~(2u << (2 * r));
                 }
