@@ -245,6 +245,7 @@ struct nbl_decoder {
     float last_ms = 0; int last_launches = 0;
     size_t smem_iter = 0;
     bool warp_path = false;      // T-EMS n_c <= 2, dc <= 4, q >= 32: one warp per check row (tems_warp.cuh)
+    bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
 };
 
 extern "C" int nbl_device_count(void) {
@@ -328,7 +329,15 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
         (rc = upload(&d->d_pfwd, pf)) || (rc = upload(&d->d_pinv, pi)))
         return fail(rc);
     // row descriptors of the warp fast path: 32 ints per check row, TW_DSC per edge
-    const bool desc_ok = code->max_dc <= TW_DC && code->max_dv <= TW_DSC - 3;
+    bool desc_ok = code->max_dc <= TW_DC && code->max_dv <= TW_DSC - 3;
+    bool all_full = true;
+    for (int r = 0; r < code->M; ++r) {
+        const int deg = code->chk_ptr[r + 1] - code->chk_ptr[r];
+        desc_ok = desc_ok && deg >= 2;
+        all_full = all_full && deg == TW_DC;
+    }
+    for (int v = 0; v < code->N; ++v) all_full = all_full && code->var_ptr[v + 1] - code->var_ptr[v] == TW_HOIST;
+    d->warp_regular = all_full && !getenv("NBLDPC_WARP_GENERIC");
     if (desc_ok) {
         std::vector<int> rd((size_t)code->M * 32, 0);
         for (int r = 0; r < code->M; ++r) {
@@ -418,15 +427,18 @@ template <typename T, int Q, int METHOD> static int launch_iterate_tqm(nbl_decod
     CK(cudaGetLastError());
     return NBL_OK;
 }
+template <typename T, int Q, int DC, int DV> static int launch_iterate_warp_dc(nbl_decoder *d, const IterParams<T> &P) {
+    auto kern = k_iterate_tems_warp<T, Q, DC, DV>;
+    constexpr size_t smem = TwSmem<T, Q>::bytes;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long rows = (long long)P.B * P.g.M;
+    kern<<<(unsigned)((rows + TW_WARPS - 1) / TW_WARPS), 32 * TW_WARPS, smem, d->stream>>>(P);
+    CK(cudaGetLastError());
+    return NBL_OK;
+}
 template <typename T, int Q> static int launch_iterate_warp(nbl_decoder *d, const IterParams<T> &P) {
     if constexpr (Q >= 32) {
-        auto kern = k_iterate_tems_warp<T, Q>;
-        constexpr size_t smem = TwSmem<T, Q>::bytes;
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const long long rows = (long long)P.B * P.g.M;
-        kern<<<(unsigned)((rows + TW_WARPS - 1) / TW_WARPS), 32 * TW_WARPS, smem, d->stream>>>(P);
-        CK(cudaGetLastError());
-        return NBL_OK;
+        return d->warp_regular ? launch_iterate_warp_dc<T, Q, TW_DC, TW_HOIST>(d, P) : launch_iterate_warp_dc<T, Q, 0, 0>(d, P);
     } else {
         nbl_set_error("internal: warp path needs q >= 32");
         return NBL_ERR_ARG;

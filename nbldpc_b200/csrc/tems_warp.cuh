@@ -12,13 +12,18 @@
 //     255 x q leaves instead of the ~94 k configurations the reference enumerates (or the 98 k of a per-column
 //     scan), every leaf useful.  (n_r = 1: D_c[x] = +inf where c0(x) == c.  n_r >= 2 all give this minimum.)
 //   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; entry a = VEC*bh + bl loads the VEC values
-//     D_c[VEC*(t^bh) ..] with conflict-free 128-bit loads and serves all VEC outputs from registers:
-//         best[r] = min(best[r], d[r ^ bl] + m0(a))          -> 1 FADD + 1 FMNMX per leaf, no branches.
+//     D_c[VEC*(t^bh) ..] with conflict-free 128-bit loads and serves all VEC outputs from registers.  Two entries
+//     share one 3-input minimum:   best[r] = min3(best[r], d[r ^ bl] + m0(a), d'[r ^ bl'] + m0(a'))
+//     -> 2 FADD + 1 FMNMX3 per two leaves, no branches.  The per-entry operands (cost, byte offset of its D_c)
+//     come from one 8/16-byte record, so an entry costs one integer add of address arithmetic;
 //   * arg-min bookkeeping is done per eta-block (2 instructions per output per block: the running minima alternate
 //     between two register sets, so "did this block improve it" is one compare); the winning block is re-scanned
-//     once at the end to recover the exact pair of the recorded path.
-//   * everything outside the search is written as short loops over the row's edges with 128-bit shared-memory
-//     accesses, to keep the kernel inside the instruction cache and free of bank conflicts.
+//     once at the end to recover the exact pair of the recorded path;
+//   * table bytes (h x, h^-1 x of the row's edges) are fetched once at the top, for the lane's own elements only:
+//     h^-1 (eta ^ beta) = h^-1 eta ^ decide(v2c)  and  h (x) ^ (syn ^ beta)  need no data-dependent table row, and the
+//     scalar look-ups beta = h * decide(.) are two shuffles out of the same registers;
+//   * everything outside the search is written for instruction count (3-input min/max, select chains instead of
+//     rank counting, shared-memory atomics for the trellis scatter) and 128-bit shared-memory accesses.
 #pragma once
 #include "dev_common.cuh"
 #include <type_traits>
@@ -29,21 +34,42 @@ constexpr int TW_DC = 4;      // maximum check degree served by the fast path
 constexpr int TW_WARPS = 4;   // warps (= check rows) per CTA
 constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, degree, up to 5 edge ids, 1 spare
                               // (spare of edge 0 = first edge id of the row, spare of edge 1 = row degree)
+constexpr int TW_HOIST = 2;   // messages of a variable fetched ahead (its degree may be larger: slow loop)
+#ifndef TW_MIN_CTAS_VALUE
+#define TW_MIN_CTAS_VALUE 5
+#endif
+constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident CTAs per SM the register allocation aims for (6 x 4 warps)
+
+template <typename T> struct TwRec;                                // search operand of one entry a
+template <> struct __align__(8) TwRec<float> { float cost; int off; };
+template <> struct __align__(16) TwRec<double> { double cost; int off; int pad; };
 
 template <typename T, int Q> struct TwSmem {
     // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> D_c, split layout (search) -> output trellis Tout
-    //                 M0 [Q]          m0(x), +inf at x = 0 (uniform operand of the search)
-    //                 bytes c01[Q] (c0 | c1 << 4);  ints meta[2*TW_DC] (decide, beta per edge)
-    static constexpr size_t t_elems = (size_t)Q * (TW_DC + 1);
-    static constexpr size_t bytes_per_warp = ((t_elems * sizeof(T) + (size_t)Q + 2 * TW_DC * sizeof(int) + 15) / 16) * 16;
+    //                 REC [Q]         {m0(x) (+inf at x = 0), c0(x)}: uniform operands of the search;
+    //                                 the VEC records of an eta-block are followed by 16 bytes of padding so that the
+    //                                 per-lane reads of the path recovery (every lane another block) spread over the banks
+    //                 M1 [Q]          m1(x)
+    //                 bytes c01[Q]    c0 | c1 << 4
+    static constexpr int VEC = Q / 32;
+    static constexpr size_t rec_stride = VEC * sizeof(TwRec<T>) + 16;            // bytes per eta-block of records
+    static constexpr size_t off_rec = (size_t)Q * TW_DC * sizeof(T);
+    static constexpr size_t off_m1 = off_rec + 32 * rec_stride;
+    static constexpr size_t off_c01 = off_m1 + (size_t)Q * sizeof(T);
+    // slabs are aligned to one message vector (at most 1 KB) so that a gather address is  base ^ (index * sizeof(T))
+    static constexpr size_t vec_align = (size_t)Q * sizeof(T) <= 1024 ? (size_t)Q * sizeof(T) : 16;
+    static constexpr bool xor_gather = (size_t)Q * sizeof(T) <= 1024;
+    static constexpr size_t bytes_per_warp = ((off_c01 + (size_t)Q + vec_align - 1) / vec_align) * vec_align;
     static constexpr size_t bytes = bytes_per_warp * TW_WARPS;
 };
 
-// P is stored so that a lane's VEC values come out of conflict-free 16-byte loads: the vector of block k is cut
+// D_c is stored so that a lane's VEC values come out of conflict-free 16-byte loads: the vector of block k is cut
 // into 16-byte pieces and piece h of all blocks is contiguous:  index(k, j) = (j / E16) * (32 * E16) + k * E16 + j % E16
 // with E16 = elements per 16 bytes (4 floats / 2 doubles), or VEC when the whole block is <= 16 bytes.
 template <typename T, int VEC> struct PLayout {
     static constexpr int E16 = (int)(16 / sizeof(T)) < VEC ? (int)(16 / sizeof(T)) : VEC;
+    static constexpr int NP = VEC / E16;                          // pieces per block
+    static constexpr int PSTRIDE = 32 * E16 * (int)sizeof(T);     // bytes between pieces
     __device__ static int index(int k, int j) { return (j / E16) * (32 * E16) + k * E16 + (j % E16); }
 };
 
@@ -91,48 +117,154 @@ template <int VEC> __device__ __forceinline__ void st_bytes(uint8_t *p, unsigned
     else if constexpr (VEC == 2) *reinterpret_cast<unsigned short *>(p) = (unsigned short)w;
     else *p = (uint8_t)w;
 }
-__device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (int)((w >> (8 * i)) & 255ull); }
+// byte i of a little-endian table word; 32-bit halves so that a constant i costs one instruction
+__device__ __forceinline__ int byte_of(unsigned long long w, int i) {
+    const unsigned h = i < 4 ? (unsigned)w : (unsigned)(w >> 32);
+    return (int)((h >> (8 * (i & 3))) & 255u);
+}
 
-// DecideLLRVector over a vector spread VEC-per-lane across the warp (x = VEC*lane + j)
+// IEEE division kept out of line (one copy of the routine; the correction factor is 1 in every shipped profile)
+template <typename T> __device__ __noinline__ T div_call(T a, T b) { return a / b; }
+
+// shared-memory loads by 32-bit shared-window address (lets the gathers fold base and index into one LOP3)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_addr(unsigned a, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ double lds_addr(unsigned a, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+// V[(byte j of w) ^ x] for a vector V at shared address `base` (aligned to its size when XG): one shift, one LOP3, one LDS
+template <typename T, bool XG> struct Gather {
+    static constexpr int SH = sizeof(T) == 4 ? 2 : 3;
+    unsigned key;                                                    // XG: base ^ (x << SH);  else x << SH
+    unsigned base;
+    __device__ __forceinline__ Gather(unsigned base_, int x) : key(XG ? (base_ ^ ((unsigned)x << SH)) : ((unsigned)x << SH)), base(base_) {}
+    __device__ __forceinline__ T at(unsigned long long w, int j) const {
+        const unsigned h = j < 4 ? (unsigned)w : (unsigned)(w >> 32);
+        const int jj = j & 3;
+        const unsigned b = (jj == 0 ? (h << SH) : (h >> (8 * jj - SH))) & (255u << SH);
+        return lds_addr(XG ? (b ^ key) : (base + (b ^ key)), T());
+    }
+};
+
+// 3-input minimum / maximum: one FMNMX3 on sm_100a for fp32
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+}
+__device__ __forceinline__ double min3(double a, double b, double c) { return fmin(fmin(a, b), c); }
+__device__ __forceinline__ double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
+// two adjacent elements of a D_c vector + one scalar: a single FADD2 on sm_100a for fp32
+template <typename T> struct Pair2;
+template <> struct Pair2<float> {
+    unsigned long long v;
+    __device__ __forceinline__ float lo() const { return __uint_as_float((unsigned)v); }
+    __device__ __forceinline__ float hi() const { return __uint_as_float((unsigned)(v >> 32)); }
+    __device__ __forceinline__ Pair2 plus(float c) const {
+        Pair2 r; unsigned long long cc;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(v), "l"(cc));
+        return r;
+    }
+};
+template <> struct Pair2<double> {
+    double a, b;
+    __device__ __forceinline__ double lo() const { return a; }
+    __device__ __forceinline__ double hi() const { return b; }
+    __device__ __forceinline__ Pair2 plus(double c) const { Pair2 r; r.a = a + c; r.b = b + c; return r; }
+};
+// the VEC/2 pairs of block k of a D_c vector (split layout) from shared memory
+template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char *src, Pair2<float> (&p)[VEC / 2]) {
+    if constexpr (VEC >= 4) {
+#pragma unroll
+        for (int h = 0; h < VEC / 4; ++h) {
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(src + h * 512);
+            p[2 * h].v = w.x; p[2 * h + 1].v = w.y;
+        }
+    } else p[0].v = *reinterpret_cast<const unsigned long long *>(src);
+}
+template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char *src, Pair2<double> (&p)[VEC / 2]) {
+#pragma unroll
+    for (int h = 0; h < VEC / 2; ++h) {
+        const double2 w = *reinterpret_cast<const double2 *>(src + h * 512);
+        p[h].a = w.x; p[h].b = w.y;
+    }
+}
+
+template <typename T, int N> __device__ __forceinline__ T vec_max(const T (&v)[N]) {
+    if constexpr (N == 8) return max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), fmax(v[6], v[7]));
+    else if constexpr (N == 4) return fmax(max3(v[0], v[1], v[2]), v[3]);
+    else if constexpr (N == 2) return fmax(v[0], v[1]);
+    else return v[0];
+}
+
+// entry records REC[first .. first+VEC) <-> registers, with 16-byte shared-memory accesses
+template <int VEC> __device__ __forceinline__ void ld_recs(const TwRec<float> *__restrict__ src, float (&cost)[VEC], int (&off)[VEC]) {
+    if constexpr (VEC >= 2) {
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) {
+            const int4 w = reinterpret_cast<const int4 *>(src)[i];
+            cost[2 * i] = __int_as_float(w.x); off[2 * i] = w.y; cost[2 * i + 1] = __int_as_float(w.z); off[2 * i + 1] = w.w;
+        }
+    } else {
+        const int2 w = *reinterpret_cast<const int2 *>(src);
+        cost[0] = __int_as_float(w.x); off[0] = w.y;
+    }
+}
+template <int VEC> __device__ __forceinline__ void ld_recs(const TwRec<double> *__restrict__ src, double (&cost)[VEC], int (&off)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int4 w = reinterpret_cast<const int4 *>(src)[i];
+        cost[i] = __hiloint2double(w.y, w.x); off[i] = w.z;
+    }
+}
+template <int VEC> __device__ __forceinline__ void st_recs(TwRec<float> *dst, const float (&cost)[VEC], const int (&off)[VEC]) {
+    if constexpr (VEC >= 2) {
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i)
+            reinterpret_cast<int4 *>(dst)[i] = make_int4(__float_as_int(cost[2 * i]), off[2 * i], __float_as_int(cost[2 * i + 1]), off[2 * i + 1]);
+    } else *reinterpret_cast<int2 *>(dst) = make_int2(__float_as_int(cost[0]), off[0]);
+}
+template <int VEC> __device__ __forceinline__ void st_recs(TwRec<double> *dst, const double (&cost)[VEC], const int (&off)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        reinterpret_cast<int4 *>(dst)[i] = make_int4(__double2loint(cost[i]), __double2hiint(cost[i]), off[i], 0);
+}
+
+// DecideLLRVector over a vector spread VEC-per-lane across the warp (x = VEC*lane + j): the largest strictly positive
+// entry, ties to the lowest symbol, 0 when nothing is positive.
 template <typename T, int VEC> __device__ __forceinline__ int warp_decide(const T (&v)[VEC], int lane) {
     using K = typename Real<T>::key_t;
-    K bk = 0; int bj = 0;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) { const K k = pos_key<T>(v[j]); if (k > bk) { bk = k; bj = j; } }
+    const T lm = vec_max<T, VEC>(v);
     K kmax; int src;
-    warp_argmax<true>(bk, 0xffffffffu, kmax, src);
-    const int x = __shfl_sync(0xffffffffu, VEC * lane + bj, src);
+    warp_argmax<true>(pos_key<T>(lm), 0xffffffffu, kmax, src);      // lowest lane holding the maximum
+    int idx = VEC - 1;
+#pragma unroll
+    for (int j = VEC - 2; j >= 0; --j) if (Real<T>::bits(v[j]) == kmax) idx = j;   // lowest element inside that lane
+    const int x = __shfl_sync(0xffffffffu, VEC * lane + idx, src);
     return kmax == K(0) ? 0 : x;
 }
 
-// Recover the recorded two-deviation path of output s = VEC*lane + R from the winning eta-block `bh` by re-scanning its
-// VEC entries in the search order.  Returns a | b << 8 | c_a << 16 | c_b << 20 and the two deviation costs
-// dU[c_a][a] (= m0(a)) and dU[c_b][b] (= D_{c_a}[b]).
-template <typename T, int Q, int R>
-__device__ __forceinline__ unsigned tw_recover_path(const T *__restrict__ sD, const T *__restrict__ sM0,
-                                                    const uint8_t *__restrict__ c01, int lane, T best, int bh, T &ua, T &ub) {
-    constexpr int VEC = Q / 32;
-    using PL = PLayout<T, VEC>;
-    const unsigned long long cw = ld_bytes<VEC>(c01 + VEC * bh);
-    T cost[VEC];
-    ld_vec<T, VEC>(sM0 + VEC * bh, cost);
-    const int k = lane ^ bh;
-    int bl0 = 0; ua = T(0); ub = T(0);
-#pragma unroll
-    for (int bl = VEC - 1; bl >= 0; --bl) {                         // descending: the smallest matching eta remains
-        const T dv = sD[(size_t)(byte_of(cw, bl) & 15) * Q + PL::index(k, R ^ bl)];
-        if (dv + cost[bl] == best) { bl0 = bl; ua = cost[bl]; ub = dv; }
+// byte `i` (runtime) of the table row whose bytes VEC*l .. VEC*l+VEC-1 lane l holds in `w`
+template <int VEC> __device__ __forceinline__ int row_byte(unsigned long long w, int i) {
+    const int src = i / VEC, sh = 8 * (i % VEC);
+    unsigned lo = __shfl_sync(0xffffffffu, (unsigned)w, src);
+    if constexpr (VEC == 8) {
+        const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(w >> 32), src);
+        lo = (sh & 32) ? hi : lo;
     }
-    const int aa = VEC * bh + bl0, bb = (VEC * lane + R) ^ aa, ca = byte_of(cw, bl0) & 15, kb = c01[bb];
-    const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
-    return (unsigned)aa | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 20);
+    return (int)((lo >> (sh & 31)) & 255u);
 }
 
-template <typename T, int Q>
-__global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterParams<T> P) {
+// DC > 0: every check row has exactly DC edges (no degree guards in the unrolled stages); DC == 0: row degree from the
+// descriptor.  DV > 0: every variable has exactly DV <= TW_HOIST edges; DV == 0: variable degree from the descriptor.
+template <typename T, int Q, int DC, int DV>
+__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 1) k_iterate_tems_warp(const IterParams<T> P) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Rec = TwRec<T>;
+    using S = TwSmem<T, Q>;
+    using G = Gather<T, S::xor_gather>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const DevGraph &g = P.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long w = (long long)blockIdx.x * TW_WARPS + warp;
@@ -140,135 +272,159 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
     const int f = (int)(w / g.M), row = (int)(w % g.M);
     if (P.early_stop && P.done[f]) return;
 
-    T *R1 = reinterpret_cast<T *>(smem_raw + TwSmem<T, Q>::bytes_per_warp * warp);
-    T *sM0 = R1 + (size_t)TW_DC * Q;
-    uint8_t *c01 = reinterpret_cast<uint8_t *>(sM0 + Q);
-    int *meta = reinterpret_cast<int *>(c01 + Q);                   // [0..TW_DC) decide(v2c_d), [TW_DC..) beta_d
+    unsigned char *slab = smem_raw + S::bytes_per_warp * warp;
+    T *R1 = reinterpret_cast<T *>(slab);
+    unsigned char *recb = slab + S::off_rec;
+    auto rec_blk = [&](int bh) { return reinterpret_cast<Rec *>(recb + bh * (int)S::rec_stride); };   // records of eta-block bh
+    T *sM1 = reinterpret_cast<T *>(slab + S::off_m1);
+    uint8_t *c01 = slab + S::off_c01;
+    const unsigned slab32 = smem_u32(slab);
     const T INF = Real<T>::inf();
     const unsigned FULL = 0xffffffffu;
 
-    // One coalesced 128-byte load brings the whole row descriptor (per edge: variable, its degree, the edge ids of
-    // its messages in summation order), so the message loads below do not wait on a chain of index loads.
-    const int dsc = g.rowdesc[(size_t)row * 32 + lane];
-    const int e0 = __shfl_sync(FULL, dsc, TW_DSC - 1), dcn = __shfl_sync(FULL, dsc, 2 * TW_DSC - 1);
-    const size_t fE = (size_t)f * g.E, fN = (size_t)f * g.N;
+    // Row descriptor: per edge {variable, its degree, the edge ids of its messages in summation order}; every lane reads
+    // the same 16 bytes (one broadcast transaction), so the message loads do not wait on a chain of index loads.
+    const int *rd = g.rowdesc + (size_t)row * 32;
+    const int e0 = DC ? DC * row : rd[TW_DSC - 1];
+    const int dcn = DC ? DC : rd[2 * TW_DSC - 1];
+    const T *lchf = P.lch + (size_t)f * g.N * Q + VEC * lane;        // this frame, this lane's elements
+    const T *cinf = P.c2v_in + (size_t)f * g.E * Q + VEC * lane;
+    T *v2cf = P.v2c + (size_t)f * g.E * Q + VEC * lane;
+    uint8_t *vdecf = P.vdec + (size_t)f * g.E;
     const int x0 = VEC * lane;
     int syn_dec = 0, syn = 0;
-    // ---- steps A-C for the row's variables (NBLDPC.cpp:977-1052) ---------------------------------------
-#pragma unroll 1
-    for (int d = 0; d < dcn; ++d) {
-        const int e = e0 + d;
-        const int col = __shfl_sync(FULL, dsc, TW_DSC * d), nv = __shfl_sync(FULL, dsc, TW_DSC * d + 1);
-        T post[VEC], vnew[VEC];
-        ld_vec<T, VEC>(P.lch + (fN + col) * Q + x0, post);
-        if (!P.first) {
-            constexpr int HOIST = 3;                               // messages loaded before the first add
-            T m[HOIST][VEC]; int ee[HOIST];
+    unsigned sdecw = 0, sbetaw = 0;                                 // byte d: decide(v2c_d), beta_d = h_d * decide(v2c_d)
+    // ---- steps A-C for the row's variables (NBLDPC.cpp:977-1052); the loads of edge d+1 are in flight during edge d ----
+    T nl[2][VEC], nm[2][TW_HOIST][VEC]; int4 nd[2]; int nbefore[2];
+    unsigned long long ntf[2];                                      // the lane's own bytes of the edge's h * x row
+    auto fetch = [&](int d, int slot) {
+        nd[slot] = *reinterpret_cast<const int4 *>(rd + TW_DSC * d);                // {variable, degree, edge id 0, edge id 1}
+        ld_vec<T, VEC>(lchf + (size_t)nd[slot].x * Q, nl[slot]);
+        ntf[slot] = ld_bytes<VEC>(g.pfwd + (size_t)(e0 + d) * Q + x0);
+        const int nv = DV ? DV : nd[slot].y;
 #pragma unroll
-            for (int j = 0; j < HOIST; ++j) {
-                ee[j] = __shfl_sync(FULL, dsc, TW_DSC * d + 2 + j);
-                if (j < nv) ld_vec<T, VEC>(P.c2v_in + (fE + ee[j]) * Q + x0, m[j]);
+        for (int j = 0; j < TW_HOIST; ++j) {
+            if (!P.first && j < nv) ld_vec<T, VEC>(cinf + (size_t)(j == 0 ? nd[slot].z : nd[slot].w) * Q, nm[slot][j]);
+            else {                                                  // iteration 1: c2v == 0 (x + 0 and x - 0 are exact)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) nm[slot][j][i] = T(0);
             }
-            const int before = (int)P.vdec[fE + e];
-            T own[VEC];
+        }
+        nbefore[slot] = P.first ? -1 : (int)vdecf[e0 + d];
+    };
+    auto edge = [&](int d, int slot) {
+        const int e = e0 + d, col = nd[slot].x, nv = DV ? DV : nd[slot].y;
+        T post[VEC], vnew[VEC], own[VEC];
+        const bool mine0 = nd[slot].z == e;                         // warp-uniform
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) own[j] = T(0);
+        for (int i = 0; i < VEC; ++i) {
+            post[i] = nl[slot][i] + nm[slot][0][i];
+            own[i] = mine0 ? nm[slot][0][i] : (TW_HOIST > 1 ? nm[slot][1][i] : T(0));
+        }
+        if (TW_HOIST > 1 && (DV ? DV > 1 : nv > 1)) {
 #pragma unroll
-            for (int j = 0; j < HOIST; ++j) {
-                if (j < nv) {
+            for (int i = 0; i < VEC; ++i) post[i] = post[i] + nm[slot][1][i];
+        } else if (!mine0) {
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) { post[i] = post[i] + m[j][i]; if (ee[j] == e) own[i] = m[j][i]; }
-                }
-            }
+            for (int i = 0; i < VEC; ++i) own[i] = T(0);
+        }
+        if (!DV && !P.first) {
 #pragma unroll 1
-            for (int j = HOIST; j < nv; ++j) {                      // variables of degree > HOIST
-                const int ej = __shfl_sync(FULL, dsc, TW_DSC * d + 2 + j);
+            for (int j = TW_HOIST; j < nv; ++j) {                   // variables of degree > TW_HOIST
+                const int ej = rd[TW_DSC * d + 2 + j];
                 T mj[VEC];
-                ld_vec<T, VEC>(P.c2v_in + (fE + ej) * Q + x0, mj);
+                ld_vec<T, VEC>(cinf + (size_t)ej * Q, mj);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) { post[i] = post[i] + mj[i]; if (ej == e) own[i] = mj[i]; }
             }
+        }
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) vnew[j] = post[j] - own[j];
-            const int dpost = warp_decide<T, VEC>(post, lane);
-            int dfin = warp_decide<T, VEC>(vnew, lane);
-            if (P.w_old != T(0) && dfin != before) {                 // warp-uniform
-                T vold[VEC];
-                ld_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vold);
+        for (int i = 0; i < VEC; ++i) vnew[i] = post[i] - own[i];
+        const int dpost = warp_decide<T, VEC>(post, lane);
+        int dfin = warp_decide<T, VEC>(vnew, lane);
+        if (!P.first && P.w_old != T(0) && dfin != nbefore[slot]) { // warp-uniform
+            T vold[VEC];
+            ld_vec<T, VEC>(v2cf + (size_t)e * Q, vold);
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) vnew[j] = P.w_old * vold[j] + P.w_new * vnew[j];   // -fmad=false
-                dfin = warp_decide<T, VEC>(vnew, lane);
-            }
-            st_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, vnew);
-            st_vec<T, VEC>(R1 + d * Q + x0, vnew);
-            const int bt = g.pfwd[(size_t)e * Q + dfin];
-            if (lane == 0) { P.vdec[fE + e] = (uint8_t)dfin; P.dec[fN + col] = (uint8_t)dpost; meta[d] = dfin; meta[TW_DC + d] = bt; }
-            syn ^= bt;
-            syn_dec ^= g.pfwd[(size_t)e * Q + dpost];
-        } else {                                                  // iteration 1: c2v == 0, v2c == L_ch, no damping
-            const int dpost = warp_decide<T, VEC>(post, lane);
-            st_vec<T, VEC>(P.v2c + (fE + e) * Q + x0, post);
-            st_vec<T, VEC>(R1 + d * Q + x0, post);
-            const int bt = g.pfwd[(size_t)e * Q + dpost];
-            if (lane == 0) { P.vdec[fE + e] = (uint8_t)dpost; P.dec[fN + col] = (uint8_t)dpost; meta[d] = dpost; meta[TW_DC + d] = bt; }
-            syn ^= bt;
-            syn_dec ^= bt;
+            for (int i = 0; i < VEC; ++i) vnew[i] = P.w_old * vold[i] + P.w_new * vnew[i];   // -fmad=false
+            dfin = warp_decide<T, VEC>(vnew, lane);
+        }
+        st_vec<T, VEC>(v2cf + (size_t)e * Q, vnew);
+        st_vec<T, VEC>(R1 + d * Q + x0, vnew);
+        const int bt = row_byte<VEC>(ntf[slot], dfin);
+        if (lane == 0) { vdecf[e] = (uint8_t)dfin; P.dec[(size_t)f * g.N + col] = (uint8_t)dpost; }
+        sdecw |= (unsigned)dfin << (8 * d); sbetaw |= (unsigned)bt << (8 * d);
+        syn ^= bt;
+        int bp = bt;
+        if (dpost != dfin) bp = row_byte<VEC>(ntf[slot], dpost);    // warp-uniform
+        syn_dec ^= bp;
+    };
+    fetch(0, 0);
+#pragma unroll 1
+    for (int d = 0; d < dcn; d += 2) {
+        if (d + 1 < dcn) fetch(d + 1, 1);
+        edge(d, 0);
+        if (d + 1 < dcn) {
+            if (d + 2 < dcn) fetch(d + 2, 0);
+            edge(d + 1, 1);
         }
     }
     if (lane == 0 && syn_dec != 0) P.flag[f] = 1;
+    // the lane's own bytes of the rows h^-1 * x
+    unsigned long long tiv[TW_DC];
+#pragma unroll
+    for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + x0); }
     __syncwarp();
-    // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)], own etas in registers -------
+    // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)],  h^-1 (eta ^ beta_d) = h^-1 eta ^ decide ----
     T u[TW_DC][VEC];
 #pragma unroll
     for (int d = 0; d < TW_DC; ++d) {
-        if (d < dcn) {
-            const int sd = meta[d], bt = meta[TW_DC + d];
+        if (DC || d < dcn) {
+            const int sd = (sdecw >> (8 * d)) & 255;
             const T vmax = R1[d * Q + sd];
-            const int bh = bt / VEC, bl = bt % VEC;
-            const unsigned long long kk = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + VEC * (lane ^ bh));
+            const G gv(slab32 + d * Q * (int)sizeof(T), sd);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) u[d][j] = vmax - R1[d * Q + byte_of(kk, j ^ bl)];   // eta^beta = VEC*(lane^bh) + (j^bl)
+            for (int j = 0; j < VEC; ++j) u[d][j] = vmax - gv.at(tiv[d], j);
         } else {
 #pragma unroll
             for (int j = 0; j < VEC; ++j) u[d][j] = INF;
         }
     }
     __syncwarp();                                                  // all reads of v2c in R1 are done
-    // ---- column order per eta (TEMS_Get_Min): c0, c1, m0, m1;  D_c for the search ---------------------------------
-    T m0[VEC], m1[VEC]; unsigned long long c01w = 0;
+    // ---- column order per eta (TEMS_Get_Min): c0, c1, m0, m1;  D_c and the entry records for the search -------------------
     {
+        T m0[VEC], m1[VEC]; unsigned long long c01w = 0;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            int k0 = 0, k1 = 0;
-#pragma unroll
-            for (int d = 0; d < TW_DC; ++d) {
-                int rank = 0;
-#pragma unroll
-                for (int c = 0; c < TW_DC; ++c) {
-                    if (c < d) rank += (c < dcn) && (u[c][j] <= u[d][j]);           // stable: the lower column wins ties
-                    if (c > d) rank += (c < dcn) && (u[c][j] < u[d][j]);
-                }
-                if (d < dcn) { if (rank == 0) k0 = d; if (rank == 1) k1 = d; }
-            }
+            const T a = u[0][j], b = u[1][j], c = u[2][j], dd = u[3][j];
+            m0[j] = fmin(min3(a, b, c), dd);
+            const int k0 = (a == m0[j]) ? 0 : (b == m0[j]) ? 1 : (c == m0[j]) ? 2 : 3;      // stable: the lower column wins ties
+            const T a1 = k0 == 0 ? INF : a, b1 = k0 == 1 ? INF : b, c1 = k0 == 2 ? INF : c, d1 = k0 == 3 ? INF : dd;
+            m1[j] = fmin(min3(a1, b1, c1), d1);
+            int k1 = (k0 != 3) ? 3 : 2;                             // lowest column other than k0 that attains m1 (row degree >= 2)
+            if (c1 == m1[j]) k1 = 2;
+            if (b1 == m1[j]) k1 = 1;
+            if (a1 == m1[j]) k1 = 0;
             c01w |= (unsigned long long)(k0 | (k1 << 4)) << (8 * j);
-            m0[j] = INF; m1[j] = INF;
-#pragma unroll
-            for (int d = 0; d < TW_DC; ++d) { if (k0 == d) m0[j] = u[d][j]; if (k1 == d) m1[j] = u[d][j]; }
         }
         st_bytes<VEC>(c01 + x0, c01w);
+        st_vec<T, VEC>(sM1 + x0, m1);
         {
-            T mm[VEC];
+            T rcost[VEC]; int roff[VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) mm[j] = (x0 + j == 0) ? INF : m0[j];
-            st_vec<T, VEC>(sM0 + x0, mm);
+            for (int j = 0; j < VEC; ++j) {
+                rcost[j] = (x0 + j == 0) ? INF : m0[j];
+                roff[j] = byte_of(c01w, j) & 15;                       // c0(x)
+            }
+            st_recs<VEC>(rec_blk(lane), rcost, roff);
         }
         const T second_ok = P.p0 >= 2 ? T(0) : INF;                 // n_r = 1: only the cheapest column may deviate
 #pragma unroll
         for (int c = 0; c < TW_DC; ++c) {
-            if (c < dcn) {                                          // D_c[x]: cheapest allowed column of x other than c
+            if (DC || c < dcn) {                                    // D_c[x]: cheapest allowed column of x other than c
                 constexpr int E16 = PL::E16;
 #pragma unroll
-                for (int h = 0; h < VEC / E16; ++h) {
+                for (int h = 0; h < PL::NP; ++h) {
                     T tmp[E16];
 #pragma unroll
                     for (int i = 0; i < E16; ++i) {
@@ -287,26 +443,56 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
 #pragma unroll
     for (int r = 0; r < VEC; ++r) { best[r] = INF; alt[r] = INF; tag[r] = 0; }
     if (P.p1 >= 2) {
-        // one eta-block: `to` = min(`from`, candidates of the block); tag the block where it got smaller
+        // one eta-block: `to` = min(`from`, candidates of the block); tag the block where it got smaller.
+        // The block's entries need block k = lane ^ bh of D_c for their own column c only, and entries of one column share
+        // it: the TW_DC vectors are loaded once (shared-memory traffic is what bounds this loop) and each entry picks
+        // its column with a warp-uniform branch.
         auto block = [&](int bh, const T (&from)[VEC], T (&to)[VEC]) {
-            const unsigned long long cw = ld_bytes<VEC>(c01 + VEC * bh);           // columns of the block's entries (uniform)
-            T cost[VEC];
-            ld_vec<T, VEC>(sM0 + VEC * bh, cost);                                  // their costs (uniform)
-            const int k = lane ^ bh;
+            T cost[VEC]; int off[VEC];
+            ld_recs<VEC>(rec_blk(bh), cost, off);                   // warp-uniform operands of the block's entries
+            const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
+            if constexpr (VEC >= 2) {
+                constexpr int NP2 = VEC / 2;
+                Pair2<T> pc[TW_DC][NP2];
 #pragma unroll
-            for (int bl = 0; bl < VEC; ++bl) {
-                const T *Dc = R1 + (size_t)(byte_of(cw, bl) & 15) * Q;
-                T p[VEC];
-                constexpr int E16 = PL::E16;
+                for (int c = 0; c < TW_DC; ++c) ld_pairs<VEC>(Dk + c * (int)(Q * sizeof(T)), pc[c]);
+                // sums of entry bl for all VEC outputs: output r takes element r ^ bl = half (r ^ bl) & 1 of pair (r ^ bl) >> 1
+                auto sums = [&](int bl, T (&t)[VEC]) {
+                    Pair2<T> q[NP2];
+                    const int c = off[bl];
+                    if (c & 2) {
+                        if (c & 1) {
 #pragma unroll
-                for (int h = 0; h < VEC / E16; ++h) {
-                    T tmp[E16];
-                    ld_vec<T, E16>(Dc + h * (32 * E16) + k * E16, tmp);
+                            for (int i = 0; i < NP2; ++i) q[i] = pc[3][i].plus(cost[bl]);
+                        } else {
 #pragma unroll
-                    for (int i = 0; i < E16; ++i) p[h * E16 + i] = tmp[i];
+                            for (int i = 0; i < NP2; ++i) q[i] = pc[2][i].plus(cost[bl]);
+                        }
+                    } else {
+                        if (c & 1) {
+#pragma unroll
+                            for (int i = 0; i < NP2; ++i) q[i] = pc[1][i].plus(cost[bl]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < NP2; ++i) q[i] = pc[0][i].plus(cost[bl]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < VEC; ++r) {
+                        const int j = r ^ bl;
+                        t[r] = (j & 1) ? q[j >> 1].hi() : q[j >> 1].lo();
+                    }
+                };
+#pragma unroll
+                for (int bl = 0; bl < VEC; bl += 2) {
+                    T t0[VEC], t1[VEC];
+                    sums(bl, t0); sums(bl + 1, t1);
+#pragma unroll
+                    for (int r = 0; r < VEC; ++r) to[r] = min3(bl == 0 ? from[r] : to[r], t0[r], t1[r]);
                 }
-#pragma unroll
-                for (int r = 0; r < VEC; ++r) to[r] = fmin(bl == 0 ? from[r] : to[r], p[r ^ bl] + cost[bl]);
+            } else {
+                const T p = *reinterpret_cast<const T *>(Dk + off[0] * (int)(Q * sizeof(T)));
+                to[0] = fmin(from[0], p + cost[0]);
             }
 #pragma unroll
             for (int r = 0; r < VEC; ++r) if (to[r] < from[r]) tag[r] = bh;
@@ -314,93 +500,115 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_tems_warp(const IterP
 #pragma unroll 1
         for (int bh = 0; bh < 32; bh += 2) { block(bh, best, alt); block(bh + 1, alt, best); }
     }
-    // ---- deltaW and the recorded path of each owned s: path = a | b << 8 | c_a << 16 | c_b << 20 | ndev << 24 ------
-    T dw[VEC], ua[VEC], ub[VEC]; unsigned path[VEC];
-    auto finish = [&](auto RC) {
-        constexpr int r = decltype(RC)::value;
-        const int s = x0 + r;
-        dw[r] = m0[r]; ua[r] = T(0); ub[r] = T(0);
-        path[r] = (unsigned)s | ((unsigned)byte_of(c01w, r) & 15u) << 16 | (1u << 24);
-        if (s == 0) { dw[r] = T(0); path[r] = 0; }
-        else if (best[r] < m0[r]) {
-            dw[r] = best[r];
-            path[r] = tw_recover_path<T, Q, r>(R1, sM0, c01, lane, best[r], tag[r], ua[r], ub[r]) | (2u << 24);
+    // ---- deltaW and the recorded path of each owned s --------------------------------------------------------------------
+    // single deviation: (s, c0(s));  pair: a in column ca, b = s ^ a in column cb, costs ua = m0(a), ub = D_ca[b]
+    unsigned path[VEC];             // a | b << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
+    T va[VEC], vb[VEC];                                             // dw - ua, dw - ub of pair paths
+    const unsigned long long c01w = ld_bytes<VEC>(c01 + x0);
+    {
+        T m0[VEC];
+        {
+            int unused[VEC];
+            ld_recs<VEC>(rec_blk(lane), m0, unused);
         }
-    };
-    finish(std::integral_constant<int, 0>{});
-    if constexpr (VEC > 1) finish(std::integral_constant<int, 1>{});
-    if constexpr (VEC > 2) { finish(std::integral_constant<int, 2>{}); finish(std::integral_constant<int, 3>{}); }
-    if constexpr (VEC > 4) {
-        finish(std::integral_constant<int, 4>{}); finish(std::integral_constant<int, 5>{});
-        finish(std::integral_constant<int, 6>{}); finish(std::integral_constant<int, 7>{});
+        if (lane == 0) m0[0] = T(0);
+#pragma unroll
+        for (int r = 0; r < VEC; ++r) {
+            const int s = x0 + r;
+            va[r] = T(0); vb[r] = T(0);
+            path[r] = s == 0 ? 0u : (0x100000u << (byte_of(c01w, r) & 15));
+            const bool pair = best[r] < m0[r];                      // never for s == 0 (m0 = 0)
+            if (!pair) best[r] = m0[r];                             // from here on best = deltaW
+            else {
+                // recover the pair from the winning block: the first entry in search order that attains the minimum
+                const int bh = tag[r], k = lane ^ bh;
+                T cost[VEC]; int off[VEC];
+                ld_recs<VEC>(rec_blk(bh), cost, off);
+                const unsigned char *Dk = slab + k * (PL::E16 * (int)sizeof(T));
+                int bl0 = 0; T ub = T(0);
+#pragma unroll
+                for (int bl = VEC - 1; bl >= 0; --bl) {             // descending: the smallest matching eta remains
+                    constexpr int E16 = PL::E16;
+                    const int j = r ^ bl;
+                    const T dv = *reinterpret_cast<const T *>(Dk + off[bl] * (int)(Q * sizeof(T)) + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
+                    if (dv + cost[bl] == best[r]) { bl0 = bl; ub = dv; }
+                }
+                const int aa = VEC * bh + bl0, bb = s ^ aa;
+                T ua[1]; int oa[1];
+                ld_recs<1>(rec_blk(bh) + bl0, ua, oa);
+                const int ca = oa[0], kb = c01[bb];
+                const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
+                va[r] = best[r] - ua[0]; vb[r] = best[r] - ub;
+                path[r] = (unsigned)aa | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) |
+                          (0x100000u << cb) | (1u << 24);
+            }
+        }
     }
     __syncwarp();                                                  // everyone is done with D
     // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
     T *Tout = R1;
-#pragma unroll 1
-    for (int d = 0; d < dcn; ++d) {
-        T tv[VEC];
 #pragma unroll
-        for (int r = 0; r < VEC; ++r) {
-            const int nd = path[r] >> 24, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
-            const bool uses = (nd == 1 && ca == d) || (nd == 2 && (ca == d || cb == d));
-            tv[r] = (nd == 0) ? T(0) : (uses ? INF : dw[r]);
+    for (int d = 0; d < TW_DC; ++d) {
+        if (DC || d < dcn) {
+            T tv[VEC];
+#pragma unroll
+            for (int r = 0; r < VEC; ++r) tv[r] = (path[r] & (0x100000u << d)) ? INF : best[r];
+            st_vec<T, VEC>(Tout + d * Q + x0, tv);
         }
-        st_vec<T, VEC>(Tout + d * Q + x0, tv);
     }
     __syncwarp();
-    {   // ... then the entries of two-deviation paths, which land on another index: conflict-safe min-store
-        unsigned pending = 0;                                       // bits 2r, 2r+1: the two entries of output r
+    // ... then the entries of two-deviation paths, which land on another index (values are >= 0: ordered like their bits)
 #pragma unroll
-        for (int r = 0; r < VEC; ++r) if ((path[r] >> 24) == 2) pending |= 3u << (2 * r);
-        while (__any_sync(FULL, pending != 0)) {
-#pragma unroll
-            for (int r = 0; r < VEC; ++r) {
-                if (pending & (3u << (2 * r))) {
-                    const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
-                    const T va = dw[r] - ua[r], vb = dw[r] - ub[r];
-                    if (pending & (1u << (2 * r))) { if (va < Tout[ca * Q + b]) Tout[ca * Q + b] = va; }
-                    if (pending & (2u << (2 * r))) { if (vb < Tout[cb * Q + a]) Tout[cb * Q + a] = vb; }
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < VEC; ++r) {
-                if (pending & (3u << (2 * r))) {
-                    const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 15, cb = (path[r] >> 20) & 15;
-                    const T va = dw[r] - ua[r], vb = dw[r] - ub[r];
-                    if (!(va < Tout[ca * Q + b])) pending &= ~(1u << (2 * r));
-                    if (!(vb < Tout[cb * Q + a])) pending &= ~(2u << (2 * r));
-                }
-            }
-            __syncwarp();
+    for (int r = 0; r < VEC; ++r) {
+        if (path[r] >> 24) {
+            const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 3, cb = (path[r] >> 18) & 3;
+            atomic_min_nonneg(Tout + ca * Q + b, va[r]);
+            atomic_min_nonneg(Tout + cb * Q + a, vb[r]);
         }
     }
-    // ---- fill-in (NBLDPC.cpp:1095-1102), normal domain, un-permute, correct (1105-1128) ---------------------------------
-    T *cout = P.c2v_out + fE * Q;
+    __syncwarp();
+    // ---- fill-in (NBLDPC.cpp:1095-1102): indices no path landed on take the smallest dU of the other columns -------------
+    {
+        T m0[VEC], m1[VEC];
+        {
+            int unused[VEC];
+            ld_recs<VEC>(rec_blk(lane), m0, unused);
+        }
+        ld_vec<T, VEC>(sM1 + x0, m1);
 #pragma unroll 1
-    for (int d = 0; d < dcn; ++d) {
-        {   // indices no path landed on take the smallest dU of the other columns; the owner of t knows it
+        for (int d = 0; d < dcn; ++d) {
             T tv[VEC];
             ld_vec<T, VEC>(Tout + d * Q + x0, tv);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
-                if (tv[j] == INF) tv[j] = ((byte_of(c01w, j) & 15) == d) ? m1[j] : m0[j];
+                if (tv[j] == INF) tv[j] = ((byte_of(c01w, j) & 15) == d) ? m1[j] : m0[j];   // (t = 0 is never +inf)
             st_vec<T, VEC>(Tout + d * Q + x0, tv);
         }
-        __syncwarp();
-        const int e = e0 + d;
-        const int bs = syn ^ meta[TW_DC + d];
+    }
+    __syncwarp();
+    // ---- normal domain, un-permute, correct (NBLDPC.cpp:1105-1128) ------------------------------------------------------
+    T *coutf = P.c2v_out + (size_t)f * g.E * Q + VEC * lane;
+    unsigned long long tnext = ld_bytes<VEC>(g.pfwd + (size_t)e0 * Q + x0);
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        const unsigned long long tt = tnext;
+        if (d + 1 < dcn) tnext = ld_bytes<VEC>(g.pfwd + (size_t)(e0 + d + 1) * Q + x0);
+        const int bs = syn ^ (int)((sbetaw >> (8 * d)) & 255u);
         const T Tb = Tout[d * Q + bs];
-        const unsigned long long tt = ld_bytes<VEC>(g.pfwd + (size_t)e * Q + x0);
+        const G gt(slab32 + d * Q * (int)sizeof(T), bs);
         T out[VEC];
 #pragma unroll
+        for (int j = 0; j < VEC; ++j) out[j] = Tb - gt.at(tt, j);
+        if (P.factor != T(1)) {                                     // x / 1 == x exactly; skips the IEEE division routine
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) out[j] = div_call(out[j], P.factor);
+        }
+#pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            T v = Tb - Tout[d * Q + (byte_of(tt, j) ^ bs)];
-            if (P.factor != T(1)) v = v / P.factor;                 // x / 1 == x exactly; skips the IEEE division routine
+            const T v = out[j];
             out[j] = (x0 + j == 0) ? T(0) : (v < -P.offset ? v + P.offset : (v > P.offset ? v - P.offset : T(0)));
         }
-        st_vec<T, VEC>(cout + (size_t)e * Q + x0, out);
+        st_vec<T, VEC>(coutf + (size_t)(e0 + d) * Q, out);
     }
 }
 
