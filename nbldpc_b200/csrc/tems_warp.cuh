@@ -190,6 +190,105 @@ template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char 
     }
 }
 
+// q[i] = pc[c][i] + cost for the warp-uniform column c: one indirect (or two direct) UNIFORM branches in PTX, so that no
+// divergence bookkeeping (BSSY/BSYNC) and no select chain is generated around the four 4-instruction bodies.
+#ifndef TW_BLOCKS_PER_ITER
+#define TW_BLOCKS_PER_ITER 1    // eta-blocks per trip of the search loop
+#endif
+#ifndef TW_DISPATCH
+#define TW_DISPATCH 1          // 0: C++ if-tree, 1: PTX bra.uni tree, 2: PTX brx.idx.uni jump table, 3: 16-way table per entry pair
+#endif
+#define TW_ADD4(a, b, c, d) "add.rn.f32x2 %0, " #a ", cc; add.rn.f32x2 %1, " #b ", cc; add.rn.f32x2 %2, " #c ", cc; add.rn.f32x2 %3, " #d ", cc;"
+__device__ __forceinline__ void pick_add(int c, float cost, const Pair2<float> (&p)[TW_DC][4], Pair2<float> (&q)[4]) {
+#if TW_DISPATCH == 2
+    asm("{\n\t"
+        ".reg .b64 cc;\n\t"
+        "mov.b64 cc, {%5, %5};\n\t"
+        "ts: .branchtargets L0, L1, L2, L3;\n\t"
+        "brx.idx.uni %4, ts;\n\t"
+        "L0: " TW_ADD4(%6, %7, %8, %9) " bra.uni LD;\n\t"
+        "L1: " TW_ADD4(%10, %11, %12, %13) " bra.uni LD;\n\t"
+        "L2: " TW_ADD4(%14, %15, %16, %17) " bra.uni LD;\n\t"
+        "L3: " TW_ADD4(%18, %19, %20, %21) "\n\t"
+        "LD:\n\t"
+        "}"
+#else
+    asm("{\n\t"
+        ".reg .b64 cc;\n\t"
+        ".reg .pred ph, pl;\n\t"
+        ".reg .b32 lowbit;\n\t"
+        "mov.b64 cc, {%5, %5};\n\t"
+        "setp.ge.s32 ph, %4, 2;\n\t"
+        "and.b32 lowbit, %4, 1;\n\t"
+        "setp.eq.s32 pl, lowbit, 0;\n\t"
+        "@ph bra.uni LH;\n\t"
+        "@pl bra.uni L0;\n\t"
+        "L1: " TW_ADD4(%10, %11, %12, %13) " bra.uni LD;\n\t"
+        "L0: " TW_ADD4(%6, %7, %8, %9) " bra.uni LD;\n\t"
+        "LH: @pl bra.uni L2;\n\t"
+        "L3: " TW_ADD4(%18, %19, %20, %21) " bra.uni LD;\n\t"
+        "L2: " TW_ADD4(%14, %15, %16, %17) "\n\t"
+        "LD:\n\t"
+        "}"
+#endif
+        : "=l"(q[0].v), "=l"(q[1].v), "=l"(q[2].v), "=l"(q[3].v)
+        : "r"(c), "f"(cost),
+          "l"(p[0][0].v), "l"(p[0][1].v), "l"(p[0][2].v), "l"(p[0][3].v), "l"(p[1][0].v), "l"(p[1][1].v), "l"(p[1][2].v), "l"(p[1][3].v),
+          "l"(p[2][0].v), "l"(p[2][1].v), "l"(p[2][2].v), "l"(p[2][3].v), "l"(p[3][0].v), "l"(p[3][1].v), "l"(p[3][2].v), "l"(p[3][3].v));
+}
+#undef TW_ADD4
+// two entries at once: q0[i] = pc[c_even][i] + cost0, q1[i] = pc[c_odd][i] + cost1, idx = c_even | c_odd << 2 (16-way jump table)
+__device__ __forceinline__ void pick_add2(int idx, float cost0, float cost1, const Pair2<float> (&p)[TW_DC][4], Pair2<float> (&q0)[4], Pair2<float> (&q1)[4]) {
+    asm("{\n\t"
+        ".reg .b64 ce, co;\n\t"
+        "mov.b64 ce, {%9, %9};\n\t"
+        "mov.b64 co, {%10, %10};\n\t"
+        "tp: .branchtargets P00, P01, P02, P03, P10, P11, P12, P13, P20, P21, P22, P23, P30, P31, P32, P33;\n\t"
+        "brx.idx.uni %8, tp;\n\t"
+        "P00: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
+        "P01: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
+        "P02: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
+        "P03: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
+        "P10: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
+        "P11: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
+        "P12: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
+        "P13: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
+        "P20: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
+        "P21: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
+        "P22: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
+        "P23: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
+        "P30: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co; bra.uni PD;\n\t"
+        "P31: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co; bra.uni PD;\n\t"
+        "P32: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co; bra.uni PD;\n\t"
+        "P33: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co;\n\t"
+        "PD:\n\t"
+        "}"
+        : "=l"(q0[0].v), "=l"(q0[1].v), "=l"(q0[2].v), "=l"(q0[3].v), "=l"(q1[0].v), "=l"(q1[1].v), "=l"(q1[2].v), "=l"(q1[3].v)
+        : "r"(idx), "f"(cost0), "f"(cost1),
+          "l"(p[0][0].v), "l"(p[0][1].v), "l"(p[0][2].v), "l"(p[0][3].v), "l"(p[1][0].v), "l"(p[1][1].v), "l"(p[1][2].v), "l"(p[1][3].v),
+          "l"(p[2][0].v), "l"(p[2][1].v), "l"(p[2][2].v), "l"(p[2][3].v), "l"(p[3][0].v), "l"(p[3][1].v), "l"(p[3][2].v), "l"(p[3][3].v));
+}
+// generic form (other vector widths, fp64 parity mode)
+template <typename T, int NP2> __device__ __forceinline__ void pick_add(int c, T cost, const Pair2<T> (&p)[TW_DC][NP2], Pair2<T> (&q)[NP2]) {
+    if (c & 2) {
+        if (c & 1) {
+#pragma unroll
+            for (int i = 0; i < NP2; ++i) q[i] = p[3][i].plus(cost);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP2; ++i) q[i] = p[2][i].plus(cost);
+        }
+    } else {
+        if (c & 1) {
+#pragma unroll
+            for (int i = 0; i < NP2; ++i) q[i] = p[1][i].plus(cost);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP2; ++i) q[i] = p[0][i].plus(cost);
+        }
+    }
+}
+
 template <typename T, int N> __device__ __forceinline__ T vec_max(const T (&v)[N]) {
     if constexpr (N == 8) return max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), fmax(v[6], v[7]));
     else if constexpr (N == 4) return fmax(max3(v[0], v[1], v[2]), v[3]);
@@ -414,7 +513,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 rcost[j] = (x0 + j == 0) ? INF : m0[j];
-                roff[j] = byte_of(c01w, j) & 15;                       // c0(x)
+                roff[j] = (byte_of(c01w, j) & 3) | ((j & 1) || j + 1 >= VEC ? 0 : (byte_of(c01w, j + 1) & 3) << 2);   // c0(x) | c0(x+1) << 2
             }
             st_recs<VEC>(rec_blk(lane), rcost, roff);
         }
@@ -459,24 +558,8 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
                 // sums of entry bl for all VEC outputs: output r takes element r ^ bl = half (r ^ bl) & 1 of pair (r ^ bl) >> 1
                 auto sums = [&](int bl, T (&t)[VEC]) {
                     Pair2<T> q[NP2];
-                    const int c = off[bl];
-                    if (c & 2) {
-                        if (c & 1) {
-#pragma unroll
-                            for (int i = 0; i < NP2; ++i) q[i] = pc[3][i].plus(cost[bl]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < NP2; ++i) q[i] = pc[2][i].plus(cost[bl]);
-                        }
-                    } else {
-                        if (c & 1) {
-#pragma unroll
-                            for (int i = 0; i < NP2; ++i) q[i] = pc[1][i].plus(cost[bl]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < NP2; ++i) q[i] = pc[0][i].plus(cost[bl]);
-                        }
-                    }
+                    if constexpr (std::is_same<T, float>::value && NP2 == 4 && TW_DISPATCH != 0) pick_add(off[bl] & 3, cost[bl], pc, q);
+                    else pick_add<T, NP2>(off[bl] & 3, cost[bl], pc, q);
 #pragma unroll
                     for (int r = 0; r < VEC; ++r) {
                         const int j = r ^ bl;
@@ -486,19 +569,38 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
 #pragma unroll
                 for (int bl = 0; bl < VEC; bl += 2) {
                     T t0[VEC], t1[VEC];
-                    sums(bl, t0); sums(bl + 1, t1);
+                    if constexpr (std::is_same<T, float>::value && NP2 == 4 && TW_DISPATCH == 3) {
+                        Pair2<T> q0[NP2], q1[NP2];
+                        pick_add2(off[bl], cost[bl], cost[bl + 1], pc, q0, q1);
+#pragma unroll
+                        for (int r = 0; r < VEC; ++r) {
+                            const int j0 = r ^ bl, j1 = r ^ (bl + 1);
+                            t0[r] = (j0 & 1) ? q0[j0 >> 1].hi() : q0[j0 >> 1].lo();
+                            t1[r] = (j1 & 1) ? q1[j1 >> 1].hi() : q1[j1 >> 1].lo();
+                        }
+                    } else { sums(bl, t0); sums(bl + 1, t1); }
 #pragma unroll
                     for (int r = 0; r < VEC; ++r) to[r] = min3(bl == 0 ? from[r] : to[r], t0[r], t1[r]);
                 }
             } else {
-                const T p = *reinterpret_cast<const T *>(Dk + off[0] * (int)(Q * sizeof(T)));
+                const T p = *reinterpret_cast<const T *>(Dk + (off[0] & 3) * (int)(Q * sizeof(T)));
                 to[0] = fmin(from[0], p + cost[0]);
             }
 #pragma unroll
             for (int r = 0; r < VEC; ++r) if (to[r] < from[r]) tag[r] = bh;
         };
+#if TW_BLOCKS_PER_ITER == 2
 #pragma unroll 1
         for (int bh = 0; bh < 32; bh += 2) { block(bh, best, alt); block(bh + 1, alt, best); }
+#else
+        // one block per trip keeps the loop body inside the instruction cache; the price is VEC register moves
+#pragma unroll 1
+        for (int bh = 0; bh < 32; ++bh) {
+            block(bh, best, alt);
+#pragma unroll
+            for (int r = 0; r < VEC; ++r) best[r] = alt[r];
+        }
+#endif
     }
     // ---- deltaW and the recorded path of each owned s --------------------------------------------------------------------
     // single deviation: (s, c0(s));  pair: a in column ca, b = s ^ a in column cb, costs ua = m0(a), ub = D_ca[b]
@@ -530,13 +632,13 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
                 for (int bl = VEC - 1; bl >= 0; --bl) {             // descending: the smallest matching eta remains
                     constexpr int E16 = PL::E16;
                     const int j = r ^ bl;
-                    const T dv = *reinterpret_cast<const T *>(Dk + off[bl] * (int)(Q * sizeof(T)) + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
+                    const T dv = *reinterpret_cast<const T *>(Dk + (off[bl] & 3) * (int)(Q * sizeof(T)) + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
                     if (dv + cost[bl] == best[r]) { bl0 = bl; ub = dv; }
                 }
                 const int aa = VEC * bh + bl0, bb = s ^ aa;
                 T ua[1]; int oa[1];
                 ld_recs<1>(rec_blk(bh) + bl0, ua, oa);
-                const int ca = oa[0], kb = c01[bb];
+                const int ca = oa[0] & 3, kb = c01[bb];
                 const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
                 va[r] = best[r] - ua[0]; vb[r] = best[r] - ub;
                 path[r] = (unsigned)aa | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) |
