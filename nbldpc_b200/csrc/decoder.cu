@@ -47,6 +47,7 @@ template <typename T> struct IterParams {
     uint8_t *vdec, *dec;
     int *flag;
     const uint8_t *done;
+    const uint8_t *pfwd_sw, *pinv_sw;   // warp fast path: the permutation tables with values as split-layout indices
 };
 
 #include "tems_warp.cuh"
@@ -227,7 +228,7 @@ struct nbl_decoder {
     size_t tsz = 4;
     // device buffers
     int *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr, *d_ysym = nullptr, *d_rowdesc = nullptr;
-    uint8_t *d_pfwd = nullptr, *d_pinv = nullptr;
+    uint8_t *d_pfwd = nullptr, *d_pinv = nullptr, *d_pfwd_sw = nullptr, *d_pinv_sw = nullptr;
     void *d_lch = nullptr, *d_v2c = nullptr, *d_c2v[2] = {nullptr, nullptr};
     uint8_t *d_vdec = nullptr, *d_dec = nullptr, *d_done = nullptr, *d_newly = nullptr;
     int *d_flag = nullptr, *d_iters = nullptr, *d_conv = nullptr, *d_out = nullptr;
@@ -286,7 +287,7 @@ static size_t smem_for(const nbl_decoder *d, int Q) {
 extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
     if (!d) return;
     cudaSetDevice(d->cfg.device);
-    void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_rowdesc, d->d_pfwd, d->d_pinv, d->d_lch, d->d_v2c,
+    void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_rowdesc, d->d_pfwd, d->d_pinv, d->d_pfwd_sw, d->d_pinv_sw, d->d_lch, d->d_v2c,
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
                     d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -351,6 +352,14 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
             }
         }
         if ((rc = upload(&d->d_rowdesc, rd))) return fail(rc);
+        if (q >= 32) {
+            // table VALUES re-indexed to the split layout of the warp kernel's shared-memory vectors (PLayout in tems_warp.cuh)
+            const int vec = q / 32, e16 = std::min<int>(16 / (int)d->tsz, vec);
+            auto swz = [&](int x) { const int k = x / vec, j = x % vec; return (j / e16) * (32 * e16) + k * e16 + j % e16; };
+            std::vector<uint8_t> pfs(pf.size()), pis(pi.size());
+            for (size_t i = 0; i < pf.size(); ++i) { pfs[i] = (uint8_t)swz(pf[i]); pis[i] = (uint8_t)swz(pi[i]); }
+            if ((rc = upload(&d->d_pfwd_sw, pfs)) || (rc = upload(&d->d_pinv_sw, pis))) return fail(rc);
+        }
     }
     d->g = DevGraph{q, code->p, N, code->M, E, code->max_dv, code->max_dc, d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_pfwd, d->d_pinv, d->d_rowdesc};
     const size_t B = cfg->max_batch;
@@ -492,6 +501,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
             P.p0 = c.p0; P.p1 = c.p1; P.factor = (T)c.factor; P.offset = (T)c.offset; P.w_old = w_old; P.w_new = w_new;
             P.lch = (const T *)d->d_lch; P.v2c = (T *)d->d_v2c; P.c2v_in = cin; P.c2v_out = cout;
             P.vdec = d->d_vdec; P.dec = d->d_dec; P.flag = d->d_flag; P.done = d->d_done;
+            P.pfwd_sw = d->d_pfwd_sw; P.pinv_sw = d->d_pinv_sw;
             CK(cudaEventRecord(d->it_ev[2 * (it - 1)], d->stream));
             DISPATCH_Q(q, rc = (launch_iterate_tq<T, QQ>(d, P)));
             if (rc) return rc;

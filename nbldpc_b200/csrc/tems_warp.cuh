@@ -1,7 +1,9 @@
 // Fast path of the fused iteration kernel for T-EMS with n_c <= 2 (the headline configuration):
 // ONE WARP per (frame, check row), VEC = Q/32 consecutive field elements per lane.
 //
-// Same results as the generic group kernel (decoder.cu / cn_tems.cuh), organised for the issue-bound search:
+// Same results as the generic group kernel (decoder.cu / cn_tems.cuh).  Two resources bound it, in this order on B200:
+// the shared-memory pipe (128 B/clk per SM, shared by four schedulers: one wavefront costs as much as four issue slots)
+// and instruction issue.  The organisation follows from that:
 //   * no block-level barriers: every exchange between lanes is a __syncwarp on the warp's private smem slab;
 //   * the pair search uses the structure of the allowed sets.  Let c0(x), c1(x) be the cheapest / second cheapest
 //     column of eta = x and m0(x) <= m1(x) their costs (TEMS_Min).  For a pair (a, b) with a ^ b = s the cheapest
@@ -11,19 +13,20 @@
 //         deltaW2[s] = min over a != 0 of  m0(a) + D_{c0(a)}[s ^ a] ,
 //     255 x q leaves instead of the ~94 k configurations the reference enumerates (or the 98 k of a per-column
 //     scan), every leaf useful.  (n_r = 1: D_c[x] = +inf where c0(x) == c.  n_r >= 2 all give this minimum.)
-//   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; entry a = VEC*bh + bl loads the VEC values
-//     D_c[VEC*(t^bh) ..] with conflict-free 128-bit loads and serves all VEC outputs from registers.  Two entries
-//     share one 3-input minimum:   best[r] = min3(best[r], d[r ^ bl] + m0(a), d'[r ^ bl'] + m0(a'))
-//     -> 2 FADD + 1 FMNMX3 per two leaves, no branches.  The per-entry operands (cost, byte offset of its D_c)
-//     come from one 8/16-byte record, so an entry costs one integer add of address arithmetic;
-//   * arg-min bookkeeping is done per eta-block (2 instructions per output per block: the running minima alternate
-//     between two register sets, so "did this block improve it" is one compare); the winning block is re-scanned
-//     once at the end to recover the exact pair of the recorded path;
-//   * table bytes (h x, h^-1 x of the row's edges) are fetched once at the top, for the lane's own elements only:
-//     h^-1 (eta ^ beta) = h^-1 eta ^ decide(v2c)  and  h (x) ^ (syn ^ beta)  need no data-dependent table row, and the
-//     scalar look-ups beta = h * decide(.) are two shuffles out of the same registers;
-//   * everything outside the search is written for instruction count (3-input min/max, select chains instead of
-//     rank counting, shared-memory atomics for the trellis scatter) and 128-bit shared-memory accesses.
+//   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; the VEC entries a = VEC*bh + bl of eta-block bh all
+//     read block k = t ^ bh of some D_c, permuted by bl.  The TW_DC candidate vectors are loaded ONCE per block with
+//     conflict-free 128-bit loads (2 bytes of shared-memory traffic per leaf instead of 4) and every entry picks its
+//     column with a warp-uniform branch; a leaf pair is one FADD2 (two sums) and half an FMNMX3:
+//         best[r] = min3(best[r], d[r ^ bl] + m0(a), d'[r ^ bl'] + m0(a'));
+//   * arg-min bookkeeping is done per eta-block (2 instructions per output per block: "did this block improve it" is
+//     one compare of the running minimum before and after); the winning block is re-scanned once at the end to recover
+//     the exact pair of the recorded path;
+//   * all message-sized vectors in shared memory (v2c, D_c, the output trellis) use the same split layout, so that the
+//     128-bit accesses of a lane to its own elements are conflict free; gathers go through table bytes that are stored
+//     pre-swizzled to that layout, for the lane's own elements only:  h^-1 (eta ^ beta) = h^-1 eta ^ decide(v2c)  and
+//     h x ^ (syn ^ beta)  need no data-dependent table row, an address is  base ^ (byte ^ key) << 2  (one shift, one LOP3),
+//     and the scalar look-ups beta = h * decide(.) are two shuffles out of registers;
+//   * the search loop does one eta-block per trip so that its body stays inside the instruction cache.
 #pragma once
 #include "dev_common.cuh"
 #include <type_traits>
@@ -38,39 +41,38 @@ constexpr int TW_HOIST = 2;   // messages of a variable fetched ahead (its degre
 #ifndef TW_MIN_CTAS_VALUE
 #define TW_MIN_CTAS_VALUE 5
 #endif
-constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident CTAs per SM the register allocation aims for (6 x 4 warps)
+constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident CTAs per SM the register allocation aims for (5 x 4 warps)
 
-template <typename T> struct TwRec;                                // search operand of one entry a
-template <> struct __align__(8) TwRec<float> { float cost; int off; };
-template <> struct __align__(16) TwRec<double> { double cost; int off; int pad; };
+// A message-sized vector in shared memory is cut into 16-byte pieces; piece h of all 32 lane-blocks is contiguous:
+//   index(k, j) = (j / E16) * (32 * E16) + k * E16 + j % E16     (element VEC*k + j; E16 = elements per 16 bytes, or VEC
+// when a whole block is <= 16 bytes).  A bit permutation of the element index, hence linear over XOR.
+template <typename T, int VEC> struct PLayout {
+    static constexpr int E16 = (int)(16 / sizeof(T)) < VEC ? (int)(16 / sizeof(T)) : VEC;
+    static constexpr int NP = VEC / E16;                          // pieces per block
+    static constexpr int PSTRIDE = 32 * E16 * (int)sizeof(T);     // bytes between pieces
+    __host__ __device__ static constexpr int index(int k, int j) { return (j / E16) * (32 * E16) + k * E16 + (j % E16); }
+    __host__ __device__ static constexpr int swz(int x) { return index(x / VEC, x % VEC); }
+};
 
 template <typename T, int Q> struct TwSmem {
-    // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> D_c, split layout (search) -> output trellis Tout
-    //                 REC [Q]         {m0(x) (+inf at x = 0), c0(x)}: uniform operands of the search;
-    //                                 the VEC records of an eta-block are followed by 16 bytes of padding so that the
-    //                                 per-lane reads of the path recovery (every lane another block) spread over the banks
-    //                 M1 [Q]          m1(x)
+    // per-warp slab:  R1 [TW_DC][Q]   v2c (VN stage) -> D_c (search) -> output trellis Tout, split layout
+    //                 BLK [32]        per eta-block: m0 of its VEC entries (+inf at x = 0), their columns c0 (2 bits each);
+    //                                 warp-uniform operands of the search.  The stride is an odd number of 16-byte units so
+    //                                 that the per-lane reads of the path recovery (every lane another block) spread out
+    //                 M1 [Q]          m1(x), split layout
     //                 bytes c01[Q]    c0 | c1 << 4
     static constexpr int VEC = Q / 32;
-    static constexpr size_t rec_stride = VEC * sizeof(TwRec<T>) + 16;            // bytes per eta-block of records
-    static constexpr size_t off_rec = (size_t)Q * TW_DC * sizeof(T);
-    static constexpr size_t off_m1 = off_rec + 32 * rec_stride;
+    static constexpr size_t blk_raw = ((VEC * sizeof(T) + 4 + 15) / 16) * 16;
+    static constexpr size_t blk_stride = (blk_raw / 16) % 2 ? blk_raw : blk_raw + 16;
+    static constexpr size_t blk_cls = VEC * sizeof(T);                           // offset of the column word inside a record
+    static constexpr size_t off_blk = (size_t)Q * TW_DC * sizeof(T);
+    static constexpr size_t off_m1 = off_blk + 32 * blk_stride;
     static constexpr size_t off_c01 = off_m1 + (size_t)Q * sizeof(T);
     // slabs are aligned to one message vector (at most 1 KB) so that a gather address is  base ^ (index * sizeof(T))
     static constexpr size_t vec_align = (size_t)Q * sizeof(T) <= 1024 ? (size_t)Q * sizeof(T) : 16;
     static constexpr bool xor_gather = (size_t)Q * sizeof(T) <= 1024;
     static constexpr size_t bytes_per_warp = ((off_c01 + (size_t)Q + vec_align - 1) / vec_align) * vec_align;
     static constexpr size_t bytes = bytes_per_warp * TW_WARPS;
-};
-
-// D_c is stored so that a lane's VEC values come out of conflict-free 16-byte loads: the vector of block k is cut
-// into 16-byte pieces and piece h of all blocks is contiguous:  index(k, j) = (j / E16) * (32 * E16) + k * E16 + j % E16
-// with E16 = elements per 16 bytes (4 floats / 2 doubles), or VEC when the whole block is <= 16 bytes.
-template <typename T, int VEC> struct PLayout {
-    static constexpr int E16 = (int)(16 / sizeof(T)) < VEC ? (int)(16 / sizeof(T)) : VEC;
-    static constexpr int NP = VEC / E16;                          // pieces per block
-    static constexpr int PSTRIDE = 32 * E16 * (int)sizeof(T);     // bytes between pieces
-    __device__ static int index(int k, int j) { return (j / E16) * (32 * E16) + k * E16 + (j % E16); }
 };
 
 template <typename T, int N> __device__ __forceinline__ void ld_vec(const T *__restrict__ p, T (&v)[N]) {
@@ -104,6 +106,27 @@ template <typename T, int N> __device__ __forceinline__ void st_vec(T *__restric
         for (int i = 0; i < N; ++i) p[i] = v[i];
     }
 }
+// a lane's VEC elements of a split-layout vector (block k): NP pieces of 16 bytes, PSTRIDE apart
+template <typename T, int VEC> __device__ __forceinline__ void ld_split(const T *__restrict__ vec, int k, T (&v)[VEC]) {
+    using PL = PLayout<T, VEC>;
+#pragma unroll
+    for (int h = 0; h < PL::NP; ++h) {
+        T tmp[PL::E16];
+        ld_vec<T, PL::E16>(vec + h * (32 * PL::E16) + k * PL::E16, tmp);
+#pragma unroll
+        for (int i = 0; i < PL::E16; ++i) v[h * PL::E16 + i] = tmp[i];
+    }
+}
+template <typename T, int VEC> __device__ __forceinline__ void st_split(T *__restrict__ vec, int k, const T (&v)[VEC]) {
+    using PL = PLayout<T, VEC>;
+#pragma unroll
+    for (int h = 0; h < PL::NP; ++h) {
+        T tmp[PL::E16];
+#pragma unroll
+        for (int i = 0; i < PL::E16; ++i) tmp[i] = v[h * PL::E16 + i];
+        st_vec<T, PL::E16>(vec + h * (32 * PL::E16) + k * PL::E16, tmp);
+    }
+}
 // VEC consecutive table bytes starting at a VEC-aligned offset, as one little-endian word
 template <int VEC> __device__ __forceinline__ unsigned long long ld_bytes(const uint8_t *__restrict__ p) {
     if constexpr (VEC == 8) return *reinterpret_cast<const unsigned long long *>(p);
@@ -130,7 +153,8 @@ template <typename T> __device__ __noinline__ T div_call(T a, T b) { return a / 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float lds_addr(unsigned a, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ double lds_addr(unsigned a, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
-// V[(byte j of w) ^ x] for a vector V at shared address `base` (aligned to its size when XG): one shift, one LOP3, one LDS
+// V[(byte j of w) ^ x] for a vector V at shared address `base` (aligned to its size when XG): one shift, one LOP3, one LDS.
+// Bytes and x are split-layout indices (the layout is linear over XOR).
 template <typename T, bool XG> struct Gather {
     static constexpr int SH = sizeof(T) == 4 ? 2 : 3;
     unsigned key;                                                    // XG: base ^ (x << SH);  else x << SH
@@ -153,6 +177,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 __device__ __forceinline__ double min3(double a, double b, double c) { return fmin(fmin(a, b), c); }
 __device__ __forceinline__ double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
+
 // two adjacent elements of a D_c vector + one scalar: a single FADD2 on sm_100a for fp32
 template <typename T> struct Pair2;
 template <> struct Pair2<float> {
@@ -172,7 +197,7 @@ template <> struct Pair2<double> {
     __device__ __forceinline__ double hi() const { return b; }
     __device__ __forceinline__ Pair2 plus(double c) const { Pair2 r; r.a = a + c; r.b = b + c; return r; }
 };
-// the VEC/2 pairs of block k of a D_c vector (split layout) from shared memory
+// the VEC/2 pairs of block k of a split-layout vector from shared memory (src = first piece of the block)
 template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char *src, Pair2<float> (&p)[VEC / 2]) {
     if constexpr (VEC >= 4) {
 #pragma unroll
@@ -190,37 +215,23 @@ template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char 
     }
 }
 
-// q[i] = pc[c][i] + cost for the warp-uniform column c: one indirect (or two direct) UNIFORM branches in PTX, so that no
-// divergence bookkeeping (BSSY/BSYNC) and no select chain is generated around the four 4-instruction bodies.
-#ifndef TW_BLOCKS_PER_ITER
-#define TW_BLOCKS_PER_ITER 1    // eta-blocks per trip of the search loop
-#endif
+// q[i] = pc[c][i] + cost for the warp-uniform column c = bits 2*BL, 2*BL+1 of the block's column word: two UNIFORM branches
+// written in PTX, so that the four 4-instruction bodies are reached without a select chain.
 #ifndef TW_DISPATCH
-#define TW_DISPATCH 1          // 0: C++ if-tree, 1: PTX bra.uni tree, 2: PTX brx.idx.uni jump table, 3: 16-way table per entry pair
+#define TW_DISPATCH 1          // 0: C++ if-tree, 1: PTX bra.uni tree
 #endif
 #define TW_ADD4(a, b, c, d) "add.rn.f32x2 %0, " #a ", cc; add.rn.f32x2 %1, " #b ", cc; add.rn.f32x2 %2, " #c ", cc; add.rn.f32x2 %3, " #d ", cc;"
-__device__ __forceinline__ void pick_add(int c, float cost, const Pair2<float> (&p)[TW_DC][4], Pair2<float> (&q)[4]) {
-#if TW_DISPATCH == 2
-    asm("{\n\t"
-        ".reg .b64 cc;\n\t"
-        "mov.b64 cc, {%5, %5};\n\t"
-        "ts: .branchtargets L0, L1, L2, L3;\n\t"
-        "brx.idx.uni %4, ts;\n\t"
-        "L0: " TW_ADD4(%6, %7, %8, %9) " bra.uni LD;\n\t"
-        "L1: " TW_ADD4(%10, %11, %12, %13) " bra.uni LD;\n\t"
-        "L2: " TW_ADD4(%14, %15, %16, %17) " bra.uni LD;\n\t"
-        "L3: " TW_ADD4(%18, %19, %20, %21) "\n\t"
-        "LD:\n\t"
-        "}"
-#else
+template <int BL>
+__device__ __forceinline__ void pick_add_ptx(unsigned cls, float cost, const Pair2<float> (&p)[TW_DC][4], Pair2<float> (&q)[4]) {
     asm("{\n\t"
         ".reg .b64 cc;\n\t"
         ".reg .pred ph, pl;\n\t"
-        ".reg .b32 lowbit;\n\t"
+        ".reg .b32 bh, bl;\n\t"
         "mov.b64 cc, {%5, %5};\n\t"
-        "setp.ge.s32 ph, %4, 2;\n\t"
-        "and.b32 lowbit, %4, 1;\n\t"
-        "setp.eq.s32 pl, lowbit, 0;\n\t"
+        "and.b32 bh, %4, %22;\n\t"
+        "and.b32 bl, %4, %23;\n\t"
+        "setp.ne.b32 ph, bh, 0;\n\t"
+        "setp.eq.b32 pl, bl, 0;\n\t"
         "@ph bra.uni LH;\n\t"
         "@pl bra.uni L0;\n\t"
         "L1: " TW_ADD4(%10, %11, %12, %13) " bra.uni LD;\n\t"
@@ -230,63 +241,55 @@ __device__ __forceinline__ void pick_add(int c, float cost, const Pair2<float> (
         "L2: " TW_ADD4(%14, %15, %16, %17) "\n\t"
         "LD:\n\t"
         "}"
-#endif
         : "=l"(q[0].v), "=l"(q[1].v), "=l"(q[2].v), "=l"(q[3].v)
-        : "r"(c), "f"(cost),
+        : "r"(cls), "f"(cost),
           "l"(p[0][0].v), "l"(p[0][1].v), "l"(p[0][2].v), "l"(p[0][3].v), "l"(p[1][0].v), "l"(p[1][1].v), "l"(p[1][2].v), "l"(p[1][3].v),
-          "l"(p[2][0].v), "l"(p[2][1].v), "l"(p[2][2].v), "l"(p[2][3].v), "l"(p[3][0].v), "l"(p[3][1].v), "l"(p[3][2].v), "l"(p[3][3].v));
+          "l"(p[2][0].v), "l"(p[2][1].v), "l"(p[2][2].v), "l"(p[2][3].v), "l"(p[3][0].v), "l"(p[3][1].v), "l"(p[3][2].v), "l"(p[3][3].v),
+          "n"(2u << (2 * BL)), "n"(1u << (2 * BL)));
 }
 #undef TW_ADD4
-// two entries at once: q0[i] = pc[c_even][i] + cost0, q1[i] = pc[c_odd][i] + cost1, idx = c_even | c_odd << 2 (16-way jump table)
-__device__ __forceinline__ void pick_add2(int idx, float cost0, float cost1, const Pair2<float> (&p)[TW_DC][4], Pair2<float> (&q0)[4], Pair2<float> (&q1)[4]) {
-    asm("{\n\t"
-        ".reg .b64 ce, co;\n\t"
-        "mov.b64 ce, {%9, %9};\n\t"
-        "mov.b64 co, {%10, %10};\n\t"
-        "tp: .branchtargets P00, P01, P02, P03, P10, P11, P12, P13, P20, P21, P22, P23, P30, P31, P32, P33;\n\t"
-        "brx.idx.uni %8, tp;\n\t"
-        "P00: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
-        "P01: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
-        "P02: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
-        "P03: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %11, co; add.rn.f32x2 %5, %12, co; add.rn.f32x2 %6, %13, co; add.rn.f32x2 %7, %14, co; bra.uni PD;\n\t"
-        "P10: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
-        "P11: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
-        "P12: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
-        "P13: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %15, co; add.rn.f32x2 %5, %16, co; add.rn.f32x2 %6, %17, co; add.rn.f32x2 %7, %18, co; bra.uni PD;\n\t"
-        "P20: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
-        "P21: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
-        "P22: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
-        "P23: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %19, co; add.rn.f32x2 %5, %20, co; add.rn.f32x2 %6, %21, co; add.rn.f32x2 %7, %22, co; bra.uni PD;\n\t"
-        "P30: add.rn.f32x2 %0, %11, ce; add.rn.f32x2 %1, %12, ce; add.rn.f32x2 %2, %13, ce; add.rn.f32x2 %3, %14, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co; bra.uni PD;\n\t"
-        "P31: add.rn.f32x2 %0, %15, ce; add.rn.f32x2 %1, %16, ce; add.rn.f32x2 %2, %17, ce; add.rn.f32x2 %3, %18, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co; bra.uni PD;\n\t"
-        "P32: add.rn.f32x2 %0, %19, ce; add.rn.f32x2 %1, %20, ce; add.rn.f32x2 %2, %21, ce; add.rn.f32x2 %3, %22, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co; bra.uni PD;\n\t"
-        "P33: add.rn.f32x2 %0, %23, ce; add.rn.f32x2 %1, %24, ce; add.rn.f32x2 %2, %25, ce; add.rn.f32x2 %3, %26, ce; add.rn.f32x2 %4, %23, co; add.rn.f32x2 %5, %24, co; add.rn.f32x2 %6, %25, co; add.rn.f32x2 %7, %26, co;\n\t"
-        "PD:\n\t"
-        "}"
-        : "=l"(q0[0].v), "=l"(q0[1].v), "=l"(q0[2].v), "=l"(q0[3].v), "=l"(q1[0].v), "=l"(q1[1].v), "=l"(q1[2].v), "=l"(q1[3].v)
-        : "r"(idx), "f"(cost0), "f"(cost1),
-          "l"(p[0][0].v), "l"(p[0][1].v), "l"(p[0][2].v), "l"(p[0][3].v), "l"(p[1][0].v), "l"(p[1][1].v), "l"(p[1][2].v), "l"(p[1][3].v),
-          "l"(p[2][0].v), "l"(p[2][1].v), "l"(p[2][2].v), "l"(p[2][3].v), "l"(p[3][0].v), "l"(p[3][1].v), "l"(p[3][2].v), "l"(p[3][3].v));
-}
 // generic form (other vector widths, fp64 parity mode)
-template <typename T, int NP2> __device__ __forceinline__ void pick_add(int c, T cost, const Pair2<T> (&p)[TW_DC][NP2], Pair2<T> (&q)[NP2]) {
-    if (c & 2) {
-        if (c & 1) {
+template <typename T, int NP2, int BL> __device__ __forceinline__ void pick_add(unsigned cls, T cost, const Pair2<T> (&p)[TW_DC][NP2], Pair2<T> (&q)[NP2]) {
+    if constexpr (std::is_same<T, float>::value && NP2 == 4 && TW_DISPATCH != 0) pick_add_ptx<BL>(cls, cost, p, q);
+    else {
+        if (cls & (2u << (2 * BL))) {
+            if (cls & (1u << (2 * BL))) {
 #pragma unroll
-            for (int i = 0; i < NP2; ++i) q[i] = p[3][i].plus(cost);
+                for (int i = 0; i < NP2; ++i) q[i] = p[3][i].plus(cost);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NP2; ++i) q[i] = p[2][i].plus(cost);
+            }
         } else {
+            if (cls & (1u << (2 * BL))) {
 #pragma unroll
-            for (int i = 0; i < NP2; ++i) q[i] = p[2][i].plus(cost);
-        }
-    } else {
-        if (c & 1) {
+                for (int i = 0; i < NP2; ++i) q[i] = p[1][i].plus(cost);
+            } else {
 #pragma unroll
-            for (int i = 0; i < NP2; ++i) q[i] = p[1][i].plus(cost);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NP2; ++i) q[i] = p[0][i].plus(cost);
+                for (int i = 0; i < NP2; ++i) q[i] = p[0][i].plus(cost);
+            }
         }
     }
+}
+
+// entries BL and BL+1 of an eta-block for all VEC outputs: output r takes element r ^ bl = half (r ^ bl) & 1 of pair (r ^ bl) >> 1
+template <typename T, int VEC, int BL>
+__device__ __forceinline__ void entry_sums(unsigned cls, const T (&cost)[VEC], const Pair2<T> (&pc)[TW_DC][VEC / 2], T (&t)[VEC]) {
+    Pair2<T> q[VEC / 2];
+    pick_add<T, VEC / 2, BL>(cls, cost[BL], pc, q);
+#pragma unroll
+    for (int r = 0; r < VEC; ++r) {
+        const int j = r ^ BL;
+        t[r] = (j & 1) ? q[j >> 1].hi() : q[j >> 1].lo();
+    }
+}
+template <typename T, int VEC, int BL>
+__device__ __forceinline__ void entry_pair(unsigned cls, const T (&cost)[VEC], const Pair2<T> (&pc)[TW_DC][VEC / 2], const T (&best)[VEC], T (&nb)[VEC]) {
+    T t0[VEC], t1[VEC];
+    entry_sums<T, VEC, BL>(cls, cost, pc, t0);
+    entry_sums<T, VEC, BL + 1>(cls, cost, pc, t1);
+#pragma unroll
+    for (int r = 0; r < VEC; ++r) nb[r] = min3(BL == 0 ? best[r] : nb[r], t0[r], t1[r]);
 }
 
 template <typename T, int N> __device__ __forceinline__ T vec_max(const T (&v)[N]) {
@@ -294,39 +297,6 @@ template <typename T, int N> __device__ __forceinline__ T vec_max(const T (&v)[N
     else if constexpr (N == 4) return fmax(max3(v[0], v[1], v[2]), v[3]);
     else if constexpr (N == 2) return fmax(v[0], v[1]);
     else return v[0];
-}
-
-// entry records REC[first .. first+VEC) <-> registers, with 16-byte shared-memory accesses
-template <int VEC> __device__ __forceinline__ void ld_recs(const TwRec<float> *__restrict__ src, float (&cost)[VEC], int (&off)[VEC]) {
-    if constexpr (VEC >= 2) {
-#pragma unroll
-        for (int i = 0; i < VEC / 2; ++i) {
-            const int4 w = reinterpret_cast<const int4 *>(src)[i];
-            cost[2 * i] = __int_as_float(w.x); off[2 * i] = w.y; cost[2 * i + 1] = __int_as_float(w.z); off[2 * i + 1] = w.w;
-        }
-    } else {
-        const int2 w = *reinterpret_cast<const int2 *>(src);
-        cost[0] = __int_as_float(w.x); off[0] = w.y;
-    }
-}
-template <int VEC> __device__ __forceinline__ void ld_recs(const TwRec<double> *__restrict__ src, double (&cost)[VEC], int (&off)[VEC]) {
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        const int4 w = reinterpret_cast<const int4 *>(src)[i];
-        cost[i] = __hiloint2double(w.y, w.x); off[i] = w.z;
-    }
-}
-template <int VEC> __device__ __forceinline__ void st_recs(TwRec<float> *dst, const float (&cost)[VEC], const int (&off)[VEC]) {
-    if constexpr (VEC >= 2) {
-#pragma unroll
-        for (int i = 0; i < VEC / 2; ++i)
-            reinterpret_cast<int4 *>(dst)[i] = make_int4(__float_as_int(cost[2 * i]), off[2 * i], __float_as_int(cost[2 * i + 1]), off[2 * i + 1]);
-    } else *reinterpret_cast<int2 *>(dst) = make_int2(__float_as_int(cost[0]), off[0]);
-}
-template <int VEC> __device__ __forceinline__ void st_recs(TwRec<double> *dst, const double (&cost)[VEC], const int (&off)[VEC]) {
-#pragma unroll
-    for (int i = 0; i < VEC; ++i)
-        reinterpret_cast<int4 *>(dst)[i] = make_int4(__double2loint(cost[i]), __double2hiint(cost[i]), off[i], 0);
 }
 
 // DecideLLRVector over a vector spread VEC-per-lane across the warp (x = VEC*lane + j): the largest strictly positive
@@ -354,15 +324,21 @@ template <int VEC> __device__ __forceinline__ int row_byte(unsigned long long w,
     return (int)((lo >> (sh & 31)) & 255u);
 }
 
+// per eta-block record: VEC costs + column word
+template <typename T, int VEC> __device__ __forceinline__ void ld_blk(const unsigned char *rec, T (&cost)[VEC], unsigned &cls) {
+    ld_vec<T, VEC>(reinterpret_cast<const T *>(rec), cost);
+    cls = *reinterpret_cast<const unsigned *>(rec + VEC * sizeof(T));
+}
+
 // DC > 0: every check row has exactly DC edges (no degree guards in the unrolled stages); DC == 0: row degree from the
 // descriptor.  DV > 0: every variable has exactly DV <= TW_HOIST edges; DV == 0: variable degree from the descriptor.
 template <typename T, int Q, int DC, int DV>
 __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 1) k_iterate_tems_warp(const IterParams<T> P) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
-    using Rec = TwRec<T>;
     using S = TwSmem<T, Q>;
     using G = Gather<T, S::xor_gather>;
+    constexpr int VB = (int)(Q * sizeof(T));                        // bytes of one message vector
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const DevGraph &g = P.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,13 +349,11 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
 
     unsigned char *slab = smem_raw + S::bytes_per_warp * warp;
     T *R1 = reinterpret_cast<T *>(slab);
-    unsigned char *recb = slab + S::off_rec;
-    auto rec_blk = [&](int bh) { return reinterpret_cast<Rec *>(recb + bh * (int)S::rec_stride); };   // records of eta-block bh
+    unsigned char *blk = slab + S::off_blk;
     T *sM1 = reinterpret_cast<T *>(slab + S::off_m1);
     uint8_t *c01 = slab + S::off_c01;
     const unsigned slab32 = smem_u32(slab);
     const T INF = Real<T>::inf();
-    const unsigned FULL = 0xffffffffu;
 
     // Row descriptor: per edge {variable, its degree, the edge ids of its messages in summation order}; every lane reads
     // the same 16 bytes (one broadcast transaction), so the message loads do not wait on a chain of index loads.
@@ -449,7 +423,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
             dfin = warp_decide<T, VEC>(vnew, lane);
         }
         st_vec<T, VEC>(v2cf + (size_t)e * Q, vnew);
-        st_vec<T, VEC>(R1 + d * Q + x0, vnew);
+        st_split<T, VEC>(R1 + d * Q, lane, vnew);
         const int bt = row_byte<VEC>(ntf[slot], dfin);
         if (lane == 0) { vdecf[e] = (uint8_t)dfin; P.dec[(size_t)f * g.N + col] = (uint8_t)dpost; }
         sdecw |= (unsigned)dfin << (8 * d); sbetaw |= (unsigned)bt << (8 * d);
@@ -469,19 +443,19 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
         }
     }
     if (lane == 0 && syn_dec != 0) P.flag[f] = 1;
-    // the lane's own bytes of the rows h^-1 * x
+    // the lane's own bytes of the rows h^-1 * x, as split-layout indices
     unsigned long long tiv[TW_DC];
 #pragma unroll
-    for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + x0); }
+    for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(P.pinv_sw + (size_t)(e0 + d) * Q + x0); }
     __syncwarp();
     // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)],  h^-1 (eta ^ beta_d) = h^-1 eta ^ decide ----
     T u[TW_DC][VEC];
 #pragma unroll
     for (int d = 0; d < TW_DC; ++d) {
         if (DC || d < dcn) {
-            const int sd = (sdecw >> (8 * d)) & 255;
+            const int sd = PL::swz((sdecw >> (8 * d)) & 255);
             const T vmax = R1[d * Q + sd];
-            const G gv(slab32 + d * Q * (int)sizeof(T), sd);
+            const G gv(slab32 + d * VB, sd);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) u[d][j] = vmax - gv.at(tiv[d], j);
         } else {
@@ -490,9 +464,9 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
         }
     }
     __syncwarp();                                                  // all reads of v2c in R1 are done
-    // ---- column order per eta (TEMS_Get_Min): c0, c1, m0, m1;  D_c and the entry records for the search -------------------
+    // ---- column order per eta (TEMS_Get_Min): c0, c1, m0, m1;  D_c and the block records for the search -------------------
     {
-        T m0[VEC], m1[VEC]; unsigned long long c01w = 0;
+        T m0[VEC], m1[VEC]; unsigned long long c01w = 0; unsigned cls = 0;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             const T a = u[0][j], b = u[1][j], c = u[2][j], dd = u[3][j];
@@ -505,114 +479,69 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
             if (b1 == m1[j]) k1 = 1;
             if (a1 == m1[j]) k1 = 0;
             c01w |= (unsigned long long)(k0 | (k1 << 4)) << (8 * j);
+            cls |= (unsigned)k0 << (2 * j);
         }
         st_bytes<VEC>(c01 + x0, c01w);
-        st_vec<T, VEC>(sM1 + x0, m1);
+        st_split<T, VEC>(sM1, lane, m1);
         {
-            T rcost[VEC]; int roff[VEC];
+            T rcost[VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                rcost[j] = (x0 + j == 0) ? INF : m0[j];
-                roff[j] = (byte_of(c01w, j) & 3) | ((j & 1) || j + 1 >= VEC ? 0 : (byte_of(c01w, j + 1) & 3) << 2);   // c0(x) | c0(x+1) << 2
-            }
-            st_recs<VEC>(rec_blk(lane), rcost, roff);
+            for (int j = 0; j < VEC; ++j) rcost[j] = (x0 + j == 0) ? INF : m0[j];
+            unsigned char *mine = blk + lane * (int)S::blk_stride;
+            st_vec<T, VEC>(reinterpret_cast<T *>(mine), rcost);
+            *reinterpret_cast<unsigned *>(mine + S::blk_cls) = cls;
         }
         const T second_ok = P.p0 >= 2 ? T(0) : INF;                 // n_r = 1: only the cheapest column may deviate
 #pragma unroll
         for (int c = 0; c < TW_DC; ++c) {
             if (DC || c < dcn) {                                    // D_c[x]: cheapest allowed column of x other than c
-                constexpr int E16 = PL::E16;
+                T dcv[VEC];
 #pragma unroll
-                for (int h = 0; h < PL::NP; ++h) {
-                    T tmp[E16];
-#pragma unroll
-                    for (int i = 0; i < E16; ++i) {
-                        const int j = h * E16 + i;
-                        const T v = ((byte_of(c01w, j) & 15) == c) ? (m1[j] + second_ok) : m0[j];
-                        tmp[i] = (x0 + j == 0) ? INF : v;
-                    }
-                    st_vec<T, E16>(R1 + (size_t)c * Q + h * (32 * E16) + lane * E16, tmp);
+                for (int j = 0; j < VEC; ++j) {
+                    const T v = ((byte_of(c01w, j) & 15) == c) ? (m1[j] + second_ok) : m0[j];
+                    dcv[j] = (x0 + j == 0) ? INF : v;
                 }
+                st_split<T, VEC>(R1 + c * Q, lane, dcv);
             }
         }
     }
     __syncwarp();
     // ---- pair search: best[s] = min_a m0(a) + D_{c0(a)}[s ^ a] ----------------------------------------------------------
-    T best[VEC], alt[VEC]; int tag[VEC];
+    T best[VEC]; int tag[VEC];
 #pragma unroll
-    for (int r = 0; r < VEC; ++r) { best[r] = INF; alt[r] = INF; tag[r] = 0; }
+    for (int r = 0; r < VEC; ++r) { best[r] = INF; tag[r] = 0; }
     if (P.p1 >= 2) {
-        // one eta-block: `to` = min(`from`, candidates of the block); tag the block where it got smaller.
-        // The block's entries need block k = lane ^ bh of D_c for their own column c only, and entries of one column share
-        // it: the TW_DC vectors are loaded once (shared-memory traffic is what bounds this loop) and each entry picks
-        // its column with a warp-uniform branch.
-        auto block = [&](int bh, const T (&from)[VEC], T (&to)[VEC]) {
-            T cost[VEC]; int off[VEC];
-            ld_recs<VEC>(rec_blk(bh), cost, off);                   // warp-uniform operands of the block's entries
+#pragma unroll 1
+        for (int bh = 0; bh < 32; ++bh) {
+            // one eta-block: best = min(best, candidates of the block); tag the block where it got smaller
+            T cost[VEC]; unsigned cls;
+            ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);   // warp-uniform operands of the block's entries
             const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
+            T nb[VEC];
             if constexpr (VEC >= 2) {
                 constexpr int NP2 = VEC / 2;
                 Pair2<T> pc[TW_DC][NP2];
 #pragma unroll
-                for (int c = 0; c < TW_DC; ++c) ld_pairs<VEC>(Dk + c * (int)(Q * sizeof(T)), pc[c]);
-                // sums of entry bl for all VEC outputs: output r takes element r ^ bl = half (r ^ bl) & 1 of pair (r ^ bl) >> 1
-                auto sums = [&](int bl, T (&t)[VEC]) {
-                    Pair2<T> q[NP2];
-                    if constexpr (std::is_same<T, float>::value && NP2 == 4 && TW_DISPATCH != 0) pick_add(off[bl] & 3, cost[bl], pc, q);
-                    else pick_add<T, NP2>(off[bl] & 3, cost[bl], pc, q);
-#pragma unroll
-                    for (int r = 0; r < VEC; ++r) {
-                        const int j = r ^ bl;
-                        t[r] = (j & 1) ? q[j >> 1].hi() : q[j >> 1].lo();
-                    }
-                };
-#pragma unroll
-                for (int bl = 0; bl < VEC; bl += 2) {
-                    T t0[VEC], t1[VEC];
-                    if constexpr (std::is_same<T, float>::value && NP2 == 4 && TW_DISPATCH == 3) {
-                        Pair2<T> q0[NP2], q1[NP2];
-                        pick_add2(off[bl], cost[bl], cost[bl + 1], pc, q0, q1);
-#pragma unroll
-                        for (int r = 0; r < VEC; ++r) {
-                            const int j0 = r ^ bl, j1 = r ^ (bl + 1);
-                            t0[r] = (j0 & 1) ? q0[j0 >> 1].hi() : q0[j0 >> 1].lo();
-                            t1[r] = (j1 & 1) ? q1[j1 >> 1].hi() : q1[j1 >> 1].lo();
-                        }
-                    } else { sums(bl, t0); sums(bl + 1, t1); }
-#pragma unroll
-                    for (int r = 0; r < VEC; ++r) to[r] = min3(bl == 0 ? from[r] : to[r], t0[r], t1[r]);
-                }
+                for (int c = 0; c < TW_DC; ++c) ld_pairs<VEC>(Dk + c * VB, pc[c]);
+                entry_pair<T, VEC, 0>(cls, cost, pc, best, nb);
+                if constexpr (VEC > 2) entry_pair<T, VEC, 2>(cls, cost, pc, best, nb);
+                if constexpr (VEC > 4) { entry_pair<T, VEC, 4>(cls, cost, pc, best, nb); entry_pair<T, VEC, 6>(cls, cost, pc, best, nb); }
             } else {
-                const T p = *reinterpret_cast<const T *>(Dk + (off[0] & 3) * (int)(Q * sizeof(T)));
-                to[0] = fmin(from[0], p + cost[0]);
+                const T p = *reinterpret_cast<const T *>(Dk + (cls & 3) * VB);
+                nb[0] = fmin(best[0], p + cost[0]);
             }
 #pragma unroll
-            for (int r = 0; r < VEC; ++r) if (to[r] < from[r]) tag[r] = bh;
-        };
-#if TW_BLOCKS_PER_ITER == 2
-#pragma unroll 1
-        for (int bh = 0; bh < 32; bh += 2) { block(bh, best, alt); block(bh + 1, alt, best); }
-#else
-        // one block per trip keeps the loop body inside the instruction cache; the price is VEC register moves
-#pragma unroll 1
-        for (int bh = 0; bh < 32; ++bh) {
-            block(bh, best, alt);
-#pragma unroll
-            for (int r = 0; r < VEC; ++r) best[r] = alt[r];
+            for (int r = 0; r < VEC; ++r) { if (nb[r] < best[r]) tag[r] = bh; best[r] = nb[r]; }
         }
-#endif
     }
     // ---- deltaW and the recorded path of each owned s --------------------------------------------------------------------
     // single deviation: (s, c0(s));  pair: a in column ca, b = s ^ a in column cb, costs ua = m0(a), ub = D_ca[b]
-    unsigned path[VEC];             // a | b << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
+    unsigned path[VEC];   // swz(a) | swz(b) << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
     T va[VEC], vb[VEC];                                             // dw - ua, dw - ub of pair paths
     const unsigned long long c01w = ld_bytes<VEC>(c01 + x0);
     {
         T m0[VEC];
-        {
-            int unused[VEC];
-            ld_recs<VEC>(rec_blk(lane), m0, unused);
-        }
+        ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0);
         if (lane == 0) m0[0] = T(0);
 #pragma unroll
         for (int r = 0; r < VEC; ++r) {
@@ -624,25 +553,24 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
             else {
                 // recover the pair from the winning block: the first entry in search order that attains the minimum
                 const int bh = tag[r], k = lane ^ bh;
-                T cost[VEC]; int off[VEC];
-                ld_recs<VEC>(rec_blk(bh), cost, off);
+                T cost[VEC]; unsigned cls;
+                ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);
                 const unsigned char *Dk = slab + k * (PL::E16 * (int)sizeof(T));
-                int bl0 = 0; T ub = T(0);
+                int bl0 = 0; T ub = T(0), ua = T(0);
 #pragma unroll
                 for (int bl = VEC - 1; bl >= 0; --bl) {             // descending: the smallest matching eta remains
                     constexpr int E16 = PL::E16;
                     const int j = r ^ bl;
-                    const T dv = *reinterpret_cast<const T *>(Dk + (off[bl] & 3) * (int)(Q * sizeof(T)) + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
-                    if (dv + cost[bl] == best[r]) { bl0 = bl; ub = dv; }
+                    const int cofs = (int)((cls >> (2 * bl)) & 3u) * VB;
+                    const T dv = *reinterpret_cast<const T *>(Dk + cofs + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
+                    if (dv + cost[bl] == best[r]) { bl0 = bl; ub = dv; ua = cost[bl]; }
                 }
                 const int aa = VEC * bh + bl0, bb = s ^ aa;
-                T ua[1]; int oa[1];
-                ld_recs<1>(rec_blk(bh) + bl0, ua, oa);
-                const int ca = oa[0] & 3, kb = c01[bb];
+                const int ca = (cls >> (2 * bl0)) & 3, kb = c01[bb];
                 const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
-                va[r] = best[r] - ua[0]; vb[r] = best[r] - ub;
-                path[r] = (unsigned)aa | ((unsigned)bb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) |
-                          (0x100000u << cb) | (1u << 24);
+                va[r] = best[r] - ua; vb[r] = best[r] - ub;
+                const unsigned sa = (unsigned)PL::index(bh, bl0), sb = (unsigned)PL::index(lane, r) ^ sa;   // the layout is linear
+                path[r] = sa | (sb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
             }
         }
     }
@@ -655,7 +583,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
             T tv[VEC];
 #pragma unroll
             for (int r = 0; r < VEC; ++r) tv[r] = (path[r] & (0x100000u << d)) ? INF : best[r];
-            st_vec<T, VEC>(Tout + d * Q + x0, tv);
+            st_split<T, VEC>(Tout + d * Q, lane, tv);
         }
     }
     __syncwarp();
@@ -672,32 +600,29 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
     // ---- fill-in (NBLDPC.cpp:1095-1102): indices no path landed on take the smallest dU of the other columns -------------
     {
         T m0[VEC], m1[VEC];
-        {
-            int unused[VEC];
-            ld_recs<VEC>(rec_blk(lane), m0, unused);
-        }
-        ld_vec<T, VEC>(sM1 + x0, m1);
+        ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0);
+        ld_split<T, VEC>(sM1, lane, m1);
 #pragma unroll 1
         for (int d = 0; d < dcn; ++d) {
             T tv[VEC];
-            ld_vec<T, VEC>(Tout + d * Q + x0, tv);
+            ld_split<T, VEC>(Tout + d * Q, lane, tv);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
                 if (tv[j] == INF) tv[j] = ((byte_of(c01w, j) & 15) == d) ? m1[j] : m0[j];   // (t = 0 is never +inf)
-            st_vec<T, VEC>(Tout + d * Q + x0, tv);
+            st_split<T, VEC>(Tout + d * Q, lane, tv);
         }
     }
     __syncwarp();
     // ---- normal domain, un-permute, correct (NBLDPC.cpp:1105-1128) ------------------------------------------------------
     T *coutf = P.c2v_out + (size_t)f * g.E * Q + VEC * lane;
-    unsigned long long tnext = ld_bytes<VEC>(g.pfwd + (size_t)e0 * Q + x0);
+    unsigned long long tnext = ld_bytes<VEC>(P.pfwd_sw + (size_t)e0 * Q + x0);
 #pragma unroll 1
     for (int d = 0; d < dcn; ++d) {
-        const unsigned long long tt = tnext;
-        if (d + 1 < dcn) tnext = ld_bytes<VEC>(g.pfwd + (size_t)(e0 + d + 1) * Q + x0);
-        const int bs = syn ^ (int)((sbetaw >> (8 * d)) & 255u);
+        const unsigned long long tt = tnext;                        // the lane's bytes of h * x, as split-layout indices
+        if (d + 1 < dcn) tnext = ld_bytes<VEC>(P.pfwd_sw + (size_t)(e0 + d + 1) * Q + x0);
+        const int bs = PL::swz(syn ^ (int)((sbetaw >> (8 * d)) & 255u));
         const T Tb = Tout[d * Q + bs];
-        const G gt(slab32 + d * Q * (int)sizeof(T), bs);
+        const G gt(slab32 + d * VB, bs);
         T out[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) out[j] = Tb - gt.at(tt, j);
