@@ -217,6 +217,9 @@ template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char 
 
 // q[i] = pc[c][i] + cost for the warp-uniform column c = bits 2*BL, 2*BL+1 of the block's column word: two UNIFORM branches
 // written in PTX, so that the four 4-instruction bodies are reached without a select chain.
+#ifndef TW_UNIFORM_CLS
+#define TW_UNIFORM_CLS 1
+#endif
 #ifndef TW_DISPATCH
 #define TW_DISPATCH 1          // 0: C++ if-tree, 1: PTX bra.uni tree
 #endif
@@ -516,6 +519,9 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
             // one eta-block: best = min(best, candidates of the block); tag the block where it got smaller
             T cost[VEC]; unsigned cls;
             ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);   // warp-uniform operands of the block's entries
+#if TW_UNIFORM_CLS
+            cls = __reduce_or_sync(0xffffffffu, cls);               // same value, but now provably uniform: uniform branches below
+#endif
             const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
             T nb[VEC];
             if constexpr (VEC >= 2) {
