@@ -185,18 +185,38 @@ __global__ void k_finalize(int B, int N, int iter, int max_iter, int *flag, uint
 
 // ---- soft demapper (CComm::Demodulate, Comm.cpp:340-407); fp64 in the reference's operation order -----
 // ysym[s] = offset of symbol s's first sample in the frame's y array, or -1 when punctured
+// One CTA handles SYMS = blockDim / q symbols (thread <-> (symbol, x)).  The p bit LLRs of a symbol, -2 y / sigma^2 (the
+// reference's expression, one fp64 division each), are formed once in shared memory; every x then adds the ones of its set
+// bits in ascending bit order, which is the reference's summation order (Comm.cpp:361-372).
 template <typename T>
 __global__ void k_demap_bpsk(int B, int N, int q, int p, int ylen, const double *__restrict__ y, double sigma,
                              const int *__restrict__ ysym, T *lch /*[B][N][q] or null*/, double *out /*[B][N][q-1] or null*/) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)B * N * q) return;
-    const int x = (int)(i % q); const size_t fs = i / q; const int s = (int)(fs % N); const size_t f = fs / N;
+    extern __shared__ double s_bit[];                               // [SYMS][p]
+    const unsigned syms = blockDim.x / q;
+    const unsigned fs0 = blockIdx.x * syms;                         // first (frame, symbol) of this CTA; B * N < 2^31 (host check)
+    const unsigned nfs = (unsigned)B * (unsigned)N;
+    if (threadIdx.x < syms * p) {
+        const unsigned fs = fs0 + threadIdx.x / p;
+        const unsigned b = threadIdx.x % p;
+        double v = 0;
+        if (fs < nfs) {
+            const unsigned s = fs % N, f = fs / N;
+            const int off = ysym[s];
+            if (off >= 0) v = -2 * y[(size_t)f * ylen + off + b] / (sigma * sigma);
+        }
+        s_bit[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const unsigned ls = threadIdx.x / q, x = threadIdx.x % q;
+    const size_t fs = fs0 + ls;
+    if (ls >= syms || fs >= nfs) return;
     double a = 0;
-    const int off = ysym[s];
-    if (off >= 0 && x != 0)
+    if (ysym[(fs0 + ls) % N] >= 0) {                                // punctured symbols: all-zero LLRs
+#pragma unroll 4
         for (int b = 0; b < p; ++b)
-            if (x & (1 << b)) a += -2 * y[f * ylen + off + b] / (sigma * sigma);
-    if (lch) lch[i] = (T)a;
+            if (x & (1u << b)) a += s_bit[ls * p + b];
+    }
+    if (lch) lch[fs * q + x] = (T)a;
     if (out && x != 0) out[fs * (q - 1) + x - 1] = a;
 }
 template <typename T>
@@ -378,7 +398,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     d->it_ev.assign(2 * (size_t)cfg->max_iter, nullptr);
     for (auto &e : d->it_ev) if (cudaEventCreate(&e) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
     d->smem_iter = smem_for(d, q);
-    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && !getenv("NBLDPC_FORCE_GENERIC");
+    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !getenv("NBLDPC_FORCE_GENERIC");
     if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
     *out = d;
     return NBL_OK;
@@ -440,8 +460,10 @@ template <typename T, int Q, int DC, int DV> static int launch_iterate_warp_dc(n
     auto kern = k_iterate_tems_warp<T, Q, DC, DV>;
     constexpr size_t smem = TwSmem<T, Q>::bytes;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long rows = (long long)P.B * P.g.M;
-    kern<<<(unsigned)((rows + TW_WARPS - 1) / TW_WARPS), 32 * TW_WARPS, smem, d->stream>>>(P);
+    // grid: x = group of TW_WARPS check rows (fastest, so that the rows of a frame -- which share messages -- run together),
+    // y, z = frame
+    const dim3 grid((unsigned)((P.g.M + TW_WARPS - 1) / TW_WARPS), (unsigned)std::min(P.B, 65535), (unsigned)((P.B + 65534) / 65535));
+    kern<<<grid, 32 * TW_WARPS, smem, d->stream>>>(P);
     CK(cudaGetLastError());
     return NBL_OK;
 }
@@ -603,6 +625,7 @@ static int demap_common(nbl_decoder *d, int modulation, const double *y, int B, 
         return NBL_ERR_ARG;
     }
     if (!(sigma > 0)) { nbl_set_error("sigma must be positive"); return NBL_ERR_ARG; }
+    if ((long long)B * N >= (1LL << 31)) { nbl_set_error("batch too large: B * N must stay below 2^31"); return NBL_ERR_ARG; }
     int ylen, rc;
     if ((rc = setup_punct(d, modulation, punct_sym, n_punct, &ylen))) return rc;
     const size_t ydbl = (size_t)B * ylen * (modulation == 2 ? 1 : 2);
@@ -620,8 +643,11 @@ static int demap_common(nbl_decoder *d, int modulation, const double *y, int B, 
     const unsigned grid = (unsigned)((tot + 255) / 256);
     const bool f64 = d->cfg.precision == NBL_PREC_F64;
     if (modulation == 2) {
-        if (f64) k_demap_bpsk<double><<<grid, 256, 0, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
-        else k_demap_bpsk<float><<<grid, 256, 0, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
+        const int threads = q >= 256 ? q : 256, syms = threads / q;
+        const unsigned bgrid = (unsigned)(((size_t)B * N + syms - 1) / syms);
+        const size_t sh = (size_t)syms * d->g.p * sizeof(double);
+        if (f64) k_demap_bpsk<double><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
+        else k_demap_bpsk<float><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
     } else {
         if (f64) k_demap_qam<double><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
         else k_demap_qam<float><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);

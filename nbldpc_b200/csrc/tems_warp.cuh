@@ -34,7 +34,10 @@
 namespace nbl {
 
 constexpr int TW_DC = 4;      // maximum check degree served by the fast path
-constexpr int TW_WARPS = 4;   // warps (= check rows) per CTA
+#ifndef TW_WARPS_VALUE
+#define TW_WARPS_VALUE 4
+#endif
+constexpr int TW_WARPS = TW_WARPS_VALUE;   // warps (= check rows) per CTA
 constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, degree, up to 5 edge ids, 1 spare
                               // (spare of edge 0 = first edge id of the row, spare of edge 1 = row degree)
 constexpr int TW_HOIST = 2;   // messages of a variable fetched ahead (its degree may be larger: slow loop)
@@ -336,7 +339,7 @@ template <typename T, int VEC> __device__ __forceinline__ void ld_blk(const unsi
 // DC > 0: every check row has exactly DC edges (no degree guards in the unrolled stages); DC == 0: row degree from the
 // descriptor.  DV > 0: every variable has exactly DV <= TW_HOIST edges; DV == 0: variable degree from the descriptor.
 template <typename T, int Q, int DC, int DV>
-__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 1) k_iterate_tems_warp(const IterParams<T> P) {
+__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS * 4 / TW_WARPS : 1) k_iterate_tems_warp(const IterParams<T> P) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
     using S = TwSmem<T, Q>;
@@ -345,9 +348,8 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const DevGraph &g = P.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long w = (long long)blockIdx.x * TW_WARPS + warp;
-    if (w >= (long long)P.B * g.M) return;
-    const int f = (int)(w / g.M), row = (int)(w % g.M);
+    const int f = (int)(blockIdx.z * 65535u + blockIdx.y), row = (int)blockIdx.x * TW_WARPS + warp;   // see launch_iterate_warp_dc
+    if (f >= P.B || row >= g.M) return;
     if (P.early_stop && P.done[f]) return;
 
     unsigned char *slab = smem_raw + S::bytes_per_warp * warp;
@@ -636,11 +638,10 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS : 
 #pragma unroll
             for (int j = 0; j < VEC; ++j) out[j] = div_call(out[j], P.factor);
         }
+        // soft threshold toward 0 by the offset: sign(v) * max(|v| - offset, 0), the same roundings as v -+ offset; "+ 0"
+        // turns a -0 into the reference's +0.  (x = 0 needs no special case: h * 0 = 0 reads Tout[bs] itself.)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const T v = out[j];
-            out[j] = (x0 + j == 0) ? T(0) : (v < -P.offset ? v + P.offset : (v > P.offset ? v - P.offset : T(0)));
-        }
+        for (int j = 0; j < VEC; ++j) out[j] = copysign(fmax(fabs(out[j]) - P.offset, T(0)), out[j]) + T(0);
         st_vec<T, VEC>(coutf + (size_t)(e0 + d) * Q, out);
     }
 }
