@@ -1,0 +1,140 @@
+"""GPU parity tests for every instantiation of the T-EMS warp kernel (nbldpc_b200/csrc/tems_warp.cuh).
+
+The golden cases only reach the (check degree 4, variable degree 2) specialisation at q = 64 and q = 256.  Here the same
+kernel is driven through its degree-generic form, through all four vector widths (q = 32, 64, 128, 256) and through
+the n_r = 1 / n_c = 1 / factor != 1 branches, on random regular and irregular codes, against the C oracle (which is
+pinned bit for bit to the compiled reference on the golden cases).  fp64 parity mode: return code, iteration count and
+every hard decision must be identical; posteriors to 1e-8."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_lch, load_golden, load_product_code
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_code(q, M, rng, regular):
+    """check-side edge lists of a random code; regular: dc = 4, dv = 2 (N = 2M); else dc in 2..4, dv in 1..5"""
+    from oracle import pyoracle as po
+    N = 2 * M if regular else (3 * M) // 2
+    while True:
+        if regular:
+            stubs = rng.permutation(np.repeat(np.arange(N), 2))
+            rows = [list(stubs[4 * r:4 * r + 4]) for r in range(M)]
+        else:
+            deg = np.zeros(N, int)
+            rows = []
+            for r in range(M):
+                dc = int(rng.integers(2, 5))
+                order = sorted(range(N), key=lambda v: (deg[v], rng.random()))     # lowest degree first: dv stays small
+                pick = order[:dc]
+                for v in pick:
+                    deg[v] += 1
+                rows.append(pick)
+            if deg.min() < 1 or deg.max() > 5:
+                continue
+        if all(len(set(r)) == len(r) for r in rows):
+            break
+    chk = [[(int(v), int(rng.integers(1, q))) for v in sorted(r)] for r in rows]
+    return po.code_from_checks(N, M, q, chk)
+
+
+def _frames(code, F, sigma, rng):
+    """all-zero codeword over BPSK/AWGN -> channel LLRs [F][N][q-1] through the oracle's demapper"""
+    from oracle import pyoracle as po
+    p = code["q"].bit_length() - 1
+    return np.stack([po.demap_bpsk(code["q"], code["N"], 1.0 + sigma * rng.standard_normal(code["N"] * p), sigma) for _ in range(F)])
+
+
+def _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset, env=None, max_iter=6):
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    path = tmp_path / ("code_%d_%d.txt" % (code["q"], code["N"]))
+    path.write_text(po.code_text(code))
+    oc = po.OracleCode(code)
+    want = [oc.decode(4, max_iter, p0, p1, factor, offset, l) for l in lch]
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        dec = capi.Decoder(capi.Code.from_file(str(path)), 4, max_iter, p0, p1, factor, offset, precision=capi.PREC_F64,
+                           max_batch=len(lch))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    r = dec.decode(lch, want_post=True)
+    assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
+    assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
+    assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+    ref = np.stack([w[3] for w in want])
+    err = np.abs(r["post"] - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() < 1e-8, err.max()
+    return r
+
+
+@pytest.mark.parametrize("q", [32, 64, 128, 256])
+@pytest.mark.parametrize("regular", [True, False])
+def test_random_codes_all_vector_widths(q, regular, tmp_path):
+    rng = np.random.default_rng(1000 + q + regular)
+    code = _random_code(q, 8, rng, regular)
+    p = q.bit_length() - 1
+    sigma = 0.62 + 0.02 * p                                       # noisy enough for several iterations and some failures
+    lch = _frames(code, 10, sigma, rng)
+    r = _check_against_oracle(code, tmp_path, lch, 2, 2, 1.0, 0.5)
+    assert len(set(r["iterations"].tolist())) > 1                   # the cases are not all trivial
+
+
+@pytest.mark.parametrize("p0,p1,factor,offset", [(1, 2, 1.0, 0.5), (3, 2, 1.0, 0.25), (2, 1, 1.0, 0.5), (2, 2, 1.5, 0.0), (2, 2, 0.8, 0.3)])
+def test_parameter_branches(p0, p1, factor, offset, tmp_path):
+    """n_r = 1 (second column forbidden), n_r = 3, n_c = 1 (no pair search), factor != 1 (division), offset = 0"""
+    rng = np.random.default_rng(77)
+    for q, regular in ((64, True), (32, False)):
+        code = _random_code(q, 8, rng, regular)
+        lch = _frames(code, 6, 0.75, rng)
+        _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset)
+
+
+@pytest.mark.parametrize("env", [{"NBLDPC_WARP_GENERIC": "1"}, {"NBLDPC_FORCE_GENERIC": "1"}])
+@pytest.mark.parametrize("name", ["cfg3_tems_gf256", "cfg5_tems_hbit256"])
+def test_golden_through_the_other_kernels(name, env, code_files):
+    """the golden T-EMS frames through the degree-generic warp kernel and through the group kernel"""
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    F = len(z["ret"])
+    os.environ.update(env)
+    try:
+        dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                           precision=capi.PREC_F64, max_batch=F)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    r = dec.decode(golden_lch(z, meta))
+    assert np.array_equal(r["converged"], z["ret"].astype(np.int32))
+    assert np.array_equal(r["iterations"], z["iters"].astype(np.int32))
+    assert np.array_equal(r["sym"], z["dec_sym"].astype(np.int32))
+
+
+def test_fp32_regular_and_generic_kernels_agree(code_files):
+    """fp32 fast mode: both warp-kernel specialisations perform the same operations in the same order"""
+    from nbldpc_b200 import capi
+    z, meta = load_golden("cfg3_tems_gf256")
+    code = load_product_code(code_files, meta["code"])
+    F = len(z["ret"])
+    lch = golden_lch(z, meta)
+    outs = []
+    for env in ({}, {"NBLDPC_WARP_GENERIC": "1"}):
+        os.environ.update(env)
+        try:
+            dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                               precision=capi.PREC_F32, max_batch=F)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        outs.append(dec.decode(lch, want_post=True))
+    for k in ("sym", "converged", "iterations", "post"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
