@@ -277,8 +277,14 @@ def main_ours(args):
         k_ms = sum(it_ms) / max(1, len(it_ms))
         achieved = bytes_iter * B / (k_ms * 1e-3) / 1e9
         alu_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):                               # dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture,
+            t = json.load(open(tpath))                          # scaled from the captured batch to this launch's frames
+            traffic, traffic_src = t["bytes_per_frame_iteration"] * B, t["capture"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                    "traffic": None, "kernel": "k_iterate<float,256,T-EMS>", "kernel_ms": k_ms, "launches_timed": len(it_ms),
+                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": bytes_iter * B,
+                    "kernel": "k_iterate_tems_warp<float,256,4,2>", "kernel_ms": k_ms, "launches_timed": len(it_ms),
                     "peak_source": peak_src,
                     "alu": {"note": "T-EMS check node is FP32-issue bound (SURVEY 8d): reference leaf count x 2 lane-ops",
                             "achieved_tlaneops": ops_iter * B / (k_ms * 1e-3) / 1e12, "peak_tlaneops": alu_peak / 1e12,

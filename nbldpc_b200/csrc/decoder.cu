@@ -185,39 +185,39 @@ __global__ void k_finalize(int B, int N, int iter, int max_iter, int *flag, uint
 
 // ---- soft demapper (CComm::Demodulate, Comm.cpp:340-407); fp64 in the reference's operation order -----
 // ysym[s] = offset of symbol s's first sample in the frame's y array, or -1 when punctured
-// One CTA handles SYMS = blockDim / q symbols (thread <-> (symbol, x)).  The p bit LLRs of a symbol, -2 y / sigma^2 (the
-// reference's expression, one fp64 division each), are formed once in shared memory; every x then adds the ones of its set
-// bits in ascending bit order, which is the reference's summation order (Comm.cpp:361-372).
+// One CTA handles `syms` consecutive (frame, symbol) pairs.  The p bit LLRs of a symbol, -2 y / sigma^2 (the reference's
+// expression, one fp64 division each -- a long dependent sequence, hence many symbols per CTA), are formed once in shared
+// memory; then thread <-> (symbol slot, x) adds the ones of x's set bits in ascending bit order, which is the reference's
+// summation order (Comm.cpp:361-372).  B * N < 2^31 (host check).
 template <typename T>
-__global__ void k_demap_bpsk(int B, int N, int q, int p, int ylen, const double *__restrict__ y, double sigma,
+__global__ void k_demap_bpsk(int B, int N, int q, int p, int ylen, int syms, const double *__restrict__ y, double sigma,
                              const int *__restrict__ ysym, T *lch /*[B][N][q] or null*/, double *out /*[B][N][q-1] or null*/) {
-    extern __shared__ double s_bit[];                               // [SYMS][p]
-    const unsigned syms = blockDim.x / q;
-    const unsigned fs0 = blockIdx.x * syms;                         // first (frame, symbol) of this CTA; B * N < 2^31 (host check)
+    extern __shared__ double s_bit[];                               // [syms][p]
+    const unsigned fs0 = blockIdx.x * (unsigned)syms;               // first (frame, symbol) of this CTA
     const unsigned nfs = (unsigned)B * (unsigned)N;
-    if (threadIdx.x < syms * p) {
-        const unsigned fs = fs0 + threadIdx.x / p;
-        const unsigned b = threadIdx.x % p;
+    for (unsigned i = threadIdx.x; i < (unsigned)(syms * p); i += blockDim.x) {
+        const unsigned fs = fs0 + i / p, b = i % p;
         double v = 0;
         if (fs < nfs) {
             const unsigned s = fs % N, f = fs / N;
             const int off = ysym[s];
-            if (off >= 0) v = -2 * y[(size_t)f * ylen + off + b] / (sigma * sigma);
+            if (off >= 0) v = -2 * y[(size_t)f * ylen + off + b] / (sigma * sigma);     // punctured symbols: all-zero LLRs
         }
-        s_bit[threadIdx.x] = v;
+        s_bit[i] = v;
     }
     __syncthreads();
-    const unsigned ls = threadIdx.x / q, x = threadIdx.x % q;
-    const size_t fs = fs0 + ls;
-    if (ls >= syms || fs >= nfs) return;
-    double a = 0;
-    if (ysym[(fs0 + ls) % N] >= 0) {                                // punctured symbols: all-zero LLRs
+    const unsigned slots = blockDim.x / q, slot = threadIdx.x / q, x = threadIdx.x % q;
+    if (slot >= slots) return;
+    for (unsigned ls = slot; ls < (unsigned)syms; ls += slots) {
+        const size_t fs = fs0 + ls;
+        if (fs >= nfs) break;
+        double a = 0;
 #pragma unroll 4
         for (int b = 0; b < p; ++b)
             if (x & (1u << b)) a += s_bit[ls * p + b];
+        if (lch) lch[fs * q + x] = (T)a;
+        if (out && x != 0) out[fs * (q - 1) + x - 1] = a;
     }
-    if (lch) lch[fs * q + x] = (T)a;
-    if (out && x != 0) out[fs * (q - 1) + x - 1] = a;
 }
 template <typename T>
 __global__ void k_demap_qam(int B, int N, int q, int ylen, const double *__restrict__ y, const double *__restrict__ cs, double sigma,
@@ -643,11 +643,11 @@ static int demap_common(nbl_decoder *d, int modulation, const double *y, int B, 
     const unsigned grid = (unsigned)((tot + 255) / 256);
     const bool f64 = d->cfg.precision == NBL_PREC_F64;
     if (modulation == 2) {
-        const int threads = q >= 256 ? q : 256, syms = threads / q;
+        const int threads = 256, syms = 8 * (threads / q);          // q <= 256
         const unsigned bgrid = (unsigned)(((size_t)B * N + syms - 1) / syms);
         const size_t sh = (size_t)syms * d->g.p * sizeof(double);
-        if (f64) k_demap_bpsk<double><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
-        else k_demap_bpsk<float><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, ysrc, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
+        if (f64) k_demap_bpsk<double><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, syms, ysrc, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
+        else k_demap_bpsk<float><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, syms, ysrc, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
     } else {
         if (f64) k_demap_qam<double><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
         else k_demap_qam<float><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);

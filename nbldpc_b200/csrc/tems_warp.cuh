@@ -220,6 +220,9 @@ template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char 
 
 // q[i] = pc[c][i] + cost for the warp-uniform column c = bits 2*BL, 2*BL+1 of the block's column word: two UNIFORM branches
 // written in PTX, so that the four 4-instruction bodies are reached without a select chain.
+#ifndef TW_PREFETCH_VOLD
+#define TW_PREFETCH_VOLD 0
+#endif
 #ifndef TW_UNIFORM_CLS
 #define TW_UNIFORM_CLS 1
 #endif
@@ -393,6 +396,11 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS * 
     auto edge = [&](int d, int slot) {
         const int e = e0 + d, col = nd[slot].x, nv = DV ? DV : nd[slot].y;
         T post[VEC], vnew[VEC], own[VEC];
+#if TW_PREFETCH_VOLD
+        T vold[VEC];                                                // the damping operand, fetched before it is known to be needed
+        const bool damping = !P.first && P.w_old != T(0);
+        if (damping) ld_vec<T, VEC>(v2cf + (size_t)e * Q, vold);
+#endif
         const bool mine0 = nd[slot].z == e;                         // warp-uniform
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -421,8 +429,10 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS * 
         const int dpost = warp_decide<T, VEC>(post, lane);
         int dfin = warp_decide<T, VEC>(vnew, lane);
         if (!P.first && P.w_old != T(0) && dfin != nbefore[slot]) { // warp-uniform
+#if !TW_PREFETCH_VOLD
             T vold[VEC];
             ld_vec<T, VEC>(v2cf + (size_t)e * Q, vold);
+#endif
 #pragma unroll
             for (int i = 0; i < VEC; ++i) vnew[i] = P.w_old * vold[i] + P.w_new * vnew[i];   // -fmad=false
             dfin = warp_decide<T, VEC>(vnew, lane);
