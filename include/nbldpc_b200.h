@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NBL_ABI_VERSION 1
+#define NBL_ABI_VERSION 2
 
 typedef enum {
     NBL_OK = 0,
@@ -44,6 +44,7 @@ typedef enum {
 
 typedef struct nbl_code nbl_code;       /* GF(q) tables + parity-check graph, resident on one device */
 typedef struct nbl_decoder nbl_decoder; /* message workspace for up to max_batch frames + a stream    */
+typedef struct nbl_encoder nbl_encoder; /* systematic encoder of one code on one device                 */
 
 int nbl_abi_version(void);
 const char *nbl_last_error(void);
@@ -130,6 +131,19 @@ int nbl_demap_decode_batch(nbl_decoder *dec, int modulation, const double *y, in
                            double sigma, const int *punct_sym, int n_punct, int *out_sym, int *converged,
                            int *iterations);
 
+/* ---- systematic encoder: replaces CNBLDPC::InitialEncode (NBLDPC.cpp:477-560, 1474-1538: Gauss elimination with
+ *      the reference's pivot / row-swap / column-swap rules, on the host, once) and CNBLDPC::Encode
+ *      (NBLDPC.cpp:562-604) for B frames on the device.  Fails with "NB matrix is not full rank" where the
+ *      reference prints that and exits. ---- */
+int nbl_encoder_create(nbl_encoder **out, const nbl_code *code, int device, void *stream);
+void nbl_encoder_destroy(nbl_encoder *enc);
+/* K = N - M message symbols per frame; n_swaps = column swaps the elimination recorded (0 for every shipped code) */
+int nbl_encoder_get_info(const nbl_encoder *enc, int *K, int *n_swaps);
+/* msg [B][K] ints (as TX_MSG_SYM), code_sym [B][N] ints (as TX_CODE_SYM); host or device pointers.  Like the
+ * reference, the message a receiver recovers is code_sym[f][0..K-1] (NBLDPC.cpp:599-602 writes it back into
+ * msg_sym; identical to msg unless columns were swapped). */
+int nbl_encode_batch(nbl_encoder *enc, const int *msg, int B, int *code_sym);
+
 /* ---- device Monte-Carlo: the frame loop of main.cpp:43-55 (source -> map -> AWGN -> demap -> decode
  *      -> CComm::Err, Comm.cpp:446-503) for `frames` frames starting at global index first_frame.
  *      Noise is counter-based (Philox4x32-10 keyed by (seed, frame index)) so that counters do not
@@ -154,6 +168,9 @@ typedef struct {
     const int *codewords;       /* host [n_codewords][N] pool of valid codewords (NULL = all-zero codeword);
                                    frame f transmits codeword f % n_codewords                        */
     int n_codewords;
+    int random_msg;             /* with n_codewords == 0: 1 = every frame draws its own K message symbols on the
+                                   device (Philox keyed by (seed, frame index)) and encodes them there
+                                   (the reference's randomMsg = 1, Comm.cpp:214-249 + CNBLDPC::Encode); 0 = all-zero */
 } nbl_sim_config;
 
 /* counters: host uint64[NBL_NUM_COUNTERS], ACCUMULATED into (caller zeroes). */

@@ -34,7 +34,8 @@ class DecoderConfig(C.Structure):
 
 class SimConfig(C.Structure):
     _fields_ = [("ebn0_db", C.c_double), ("modulation", C.c_int), ("constellation", C.c_void_p), ("seed", C.c_uint64),
-                ("first_frame", C.c_uint64), ("frames", C.c_uint64), ("codewords", C.c_void_p), ("n_codewords", C.c_int)]
+                ("first_frame", C.c_uint64), ("frames", C.c_uint64), ("codewords", C.c_void_p), ("n_codewords", C.c_int),
+                ("random_msg", C.c_int)]
 
 
 def lib_path():
@@ -73,6 +74,11 @@ def lib():
         L.nbl_simulate_async.argtypes = [vp, C.POINTER(SimConfig), vp]
         L.nbl_decoder_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.nbl_decoder_iter_timing.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.nbl_encoder_create.argtypes = [C.POINTER(vp), vp, C.c_int, vp]
+        L.nbl_encoder_destroy.argtypes = [vp]
+        L.nbl_encoder_destroy.restype = None
+        L.nbl_encoder_get_info.argtypes = [vp, ip, ip]
+        L.nbl_encode_batch.argtypes = [vp, vp, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -175,6 +181,30 @@ class Code:
             pass
 
 
+class Encoder:
+    """nbl_encoder: the reference's systematic encoder (CNBLDPC::InitialEncode / Encode) for batches, on the device"""
+
+    def __init__(self, code, device=0, stream=None):
+        self.code = code
+        self._h = C.c_void_p()
+        _check(lib().nbl_encoder_create(C.byref(self._h), code._h, device, stream))
+        k, s = C.c_int(), C.c_int()
+        _check(lib().nbl_encoder_get_info(self._h, C.byref(k), C.byref(s)))
+        self.K, self.n_swaps = k.value, s.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().nbl_encoder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def encode(self, msg):
+        """msg [B][K] ints -> code words [B][N] int32 (host arrays)"""
+        msg = np.ascontiguousarray(msg, np.int32).reshape(-1, self.K)
+        out = np.zeros((msg.shape[0], self.code.N), np.int32)
+        _check(lib().nbl_encode_batch(self._h, _ptr(msg), msg.shape[0], _ptr(out)))
+        return out
+
+
 class Decoder:
     def __init__(self, code, method, max_iter=10, p0=0, p1=0, factor=1.0, offset=0.0, precision=PREC_F32, early_stop=1,
                  max_batch=1, device=0, stream=None):
@@ -236,18 +266,18 @@ class Decoder:
         _check(lib().nbl_demap_decode_batch(self._h, modulation, _ptr(y), B, _ptr(constellation), float(sigma), None, 0,
                                             _ptr(out_sym), _ptr(converged), _ptr(iterations)))
 
-    def simulate(self, ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, counters=None):
+    def simulate(self, ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, counters=None, random_msg=0):
         cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
         cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
-        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0])
+        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg))
         cnt = counters if counters is not None else np.zeros(NUM_COUNTERS, np.uint64)
         _check(lib().nbl_simulate(self._h, C.byref(cfg), _ptr(cnt)))
         return cnt
 
-    def simulate_async(self, ebn0_db, frames, dev_counters, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None):
+    def simulate_async(self, ebn0_db, frames, dev_counters, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, random_msg=0):
         cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
         cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
-        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0])
+        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg))
         _check(lib().nbl_simulate_async(self._h, C.byref(cfg), _ptr(dev_counters)))
 
     def sync(self):

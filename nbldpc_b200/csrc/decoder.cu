@@ -12,6 +12,7 @@
 // node (step D) on them while they are still in shared memory.  Messages stream HBM -> smem -> HBM once
 // per iteration, fully coalesced (thread x <-> element x).
 #include "internal.h"
+#include "enc_internal.h"
 #include "dev_common.cuh"
 #include "cn_tems.cuh"
 #include "cn_ems.cuh"
@@ -256,6 +257,8 @@ struct nbl_decoder {
     double *d_ystage = nullptr;  size_t ystage_bytes = 0;    // staging for host received samples
     std::vector<int> punct_cache; int punct_mod = -1, punct_ylen = 0;
     uint8_t *d_pool = nullptr; size_t pool_cap = 0;          // codeword pool of the Monte-Carlo path
+    uint8_t *d_tx = nullptr, *d_msg = nullptr;               // transmitted code words / messages of the running batch [max_batch][N], [max_batch][K]
+    nbl_encoder *sim_enc = nullptr;                          // device encoder of the random-message Monte-Carlo mode
     std::vector<int> pool_host;
     unsigned long long *d_counters = nullptr;
     bool timing_pending = false;
@@ -309,7 +312,8 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
     cudaSetDevice(d->cfg.device);
     void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_rowdesc, d->d_pfwd, d->d_pinv, d->d_pfwd_sw, d->d_pinv_sw, d->d_lch, d->d_v2c,
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
-                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters};
+                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg};
+    if (d->sim_enc) nbl_encoder_destroy(d->sim_enc);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : d->it_ev) if (e) cudaEventDestroy(e);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -720,16 +724,36 @@ __device__ inline void normal_pair(uint64_t seed, uint64_t frame, uint32_t idx, 
     z0 = rad * c; z1 = rad * s;
 }
 
+// transmitted code words of B frames: frame f takes pool entry (first_frame + f) % n_pool, or all zeros
+__global__ void k_sim_source_pool(int B, int N, uint64_t first_frame, const uint8_t *__restrict__ pool, int n_pool, uint8_t *__restrict__ tx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N) return;
+    const int f = (int)(i / N), s = (int)(i % N);
+    tx[i] = n_pool ? pool[(size_t)((first_frame + (uint64_t)f) % (uint64_t)n_pool) * N + s] : (uint8_t)0;
+}
+// K uniform message symbols per frame (the reference's randomMsg = 1 source, Comm.cpp:214-249, with a counter-based generator)
+__global__ void k_sim_message(int B, int K, int q, uint64_t seed, uint64_t first_frame, uint8_t *__restrict__ msg) {
+    const int per = (K + 3) / 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * per) return;
+    const int f = (int)(i / per), j = (int)(i % per);
+    const uint64_t gf = first_frame + (uint64_t)f;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)gf, (uint32_t)(gf >> 32), (uint32_t)j, 0x4D5347u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    for (int h = 0; h < 4; ++h)
+        if (4 * j + h < K) msg[(size_t)f * K + 4 * j + h] = (uint8_t)(r[h] & (uint32_t)(q - 1));
+}
+
 // received samples of B frames.  BPSK: y[f][N*p] = (1 - 2 bit) + sigma n  (0 -> +1, 1 -> -1, BPSK.txt; bit b of
 // symbol s is sample s*p+b, Comm.cpp:272-279).  QAM: y[f][N][2] = constellation[symbol] + sigma (n_re, n_im).
 __global__ void k_sim_channel(int B, int N, int p, int modulation, uint64_t seed, uint64_t first_frame, double sigma,
-                              const uint8_t *__restrict__ pool, int n_pool, const double *__restrict__ cs, double *__restrict__ y) {
+                              const uint8_t *__restrict__ tx, const double *__restrict__ cs, double *__restrict__ y) {
     const int per = modulation == 2 ? (N * p + 1) / 2 : N;          // Philox blocks per frame (2 normals each)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * per) return;
     const int f = (int)(i / per), j = (int)(i % per);
     const uint64_t gf = first_frame + (uint64_t)f;
-    const uint8_t *cw = n_pool ? pool + (size_t)(gf % (uint64_t)n_pool) * N : nullptr;
+    const uint8_t *cw = tx + (size_t)f * N;
     double z0, z1;
     normal_pair(seed, gf, (uint32_t)j, z0, z1);
     if (modulation == 2) {
@@ -737,18 +761,18 @@ __global__ void k_sim_channel(int B, int N, int p, int modulation, uint64_t seed
         for (int h = 0; h < 2; ++h) {
             const int b = 2 * j + h;
             if (b >= L) break;
-            const int bit = cw ? (cw[b / p] >> (b % p)) & 1 : 0;
+            const int bit = (cw[b / p] >> (b % p)) & 1;
             y[(size_t)f * L + b] = (bit ? -1.0 : 1.0) + sigma * (h ? z1 : z0);
         }
     } else {
-        const int sym = cw ? cw[j] : 0;
+        const int sym = cw[j];
         y[((size_t)f * N + j) * 2] = cs[2 * sym] + sigma * z0;
         y[((size_t)f * N + j) * 2 + 1] = cs[2 * sym + 1] + sigma * z1;
     }
 }
 
 // CComm::Err (Comm.cpp:446-503) per frame on the first K symbols, accumulated into uint64 counters
-__global__ void k_sim_count(int B, int N, int K, uint64_t first_frame, const uint8_t *__restrict__ pool, int n_pool,
+__global__ void k_sim_count(int B, int N, int K, const uint8_t *__restrict__ tx,
                             const int *__restrict__ out_sym, const int *__restrict__ conv, const int *__restrict__ iters,
                             unsigned long long *counters) {
     __shared__ unsigned long long acc[NBL_NUM_COUNTERS];
@@ -756,11 +780,10 @@ __global__ void k_sim_count(int B, int N, int K, uint64_t first_frame, const uin
     __syncthreads();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < B) {
-        const uint64_t gf = first_frame + (uint64_t)f;
-        const uint8_t *cw = n_pool ? pool + (size_t)(gf % (uint64_t)n_pool) * N : nullptr;
+        const uint8_t *cw = tx + (size_t)f * N;
         int es = 0, eb = 0;
         for (int s = 0; s < K; ++s) {
-            const int diff = out_sym[(size_t)f * N + s] ^ (cw ? cw[s] : 0);
+            const int diff = out_sym[(size_t)f * N + s] ^ cw[s];
             es += diff != 0; eb += __popc(diff);
         }
         atomicAdd(&acc[NBL_CNT_FRAMES], 1ULL);
@@ -802,21 +825,36 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
     if (cfg->modulation != 2) CK(cudaMemcpyAsync(d->d_cons, cfg->constellation, 2 * q * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     const size_t ydbl = (size_t)d->cfg.max_batch * ylen * (cfg->modulation == 2 ? 1 : 2);
     if ((rc = ensure_ystage(d, ydbl * sizeof(double)))) return rc;
+    const bool rnd = cfg->n_codewords == 0 && cfg->random_msg != 0;
+    if (!d->d_tx) CK(cudaMalloc((void **)&d->d_tx, (size_t)d->cfg.max_batch * N));
+    if (rnd) {
+        if (!d->sim_enc && (rc = nbl_encoder_create(&d->sim_enc, d->code, d->cfg.device, d->stream))) return rc;
+        if (!d->d_msg) CK(cudaMalloc((void **)&d->d_msg, (size_t)d->cfg.max_batch * K));
+    }
     int launches = 0;
     for (uint64_t done = 0; done < cfg->frames;) {
         const int B = (int)std::min<uint64_t>(d->cfg.max_batch, cfg->frames - done);
         const int per = cfg->modulation == 2 ? (N * p + 1) / 2 : N;
-        const long long nthr = (long long)B * per;
+        const long long nthr = (long long)B * per, nsym = (long long)B * N;
+        if (rnd) {
+            const long long nm = (long long)B * ((K + 3) / 4);
+            k_sim_message<<<(unsigned)((nm + 255) / 256), 256, 0, d->stream>>>(B, K, q, cfg->seed, cfg->first_frame + done, d->d_msg);
+            CK(cudaGetLastError());
+            if ((rc = nbl_encoder_launch_u8(d->sim_enc, d->d_msg, B, d->d_tx, d->stream))) return rc;
+            launches += 1;
+        } else {
+            k_sim_source_pool<<<(unsigned)((nsym + 255) / 256), 256, 0, d->stream>>>(B, N, cfg->first_frame + done, d->d_pool, cfg->n_codewords, d->d_tx);
+            CK(cudaGetLastError());
+        }
         k_sim_channel<<<(unsigned)((nthr + 255) / 256), 256, 0, d->stream>>>(B, N, p, cfg->modulation, cfg->seed, cfg->first_frame + done, sigma,
-                                                                            d->d_pool, cfg->n_codewords, d->d_cons, d->d_ystage);
+                                                                            d->d_tx, d->d_cons, d->d_ystage);
         CK(cudaGetLastError());
         if ((rc = demap_common(d, cfg->modulation, d->d_ystage, B, d->d_cons, sigma, nullptr, 0, true, nullptr))) return rc;
         rc = d->cfg.precision == NBL_PREC_F64 ? run_decode<double>(d, B, nullptr) : run_decode<float>(d, B, nullptr);
         if (rc) return rc;
-        k_sim_count<<<(B + 127) / 128, 128, 0, d->stream>>>(B, N, K, cfg->first_frame + done, d->d_pool, cfg->n_codewords, d->d_out, d->d_conv,
-                                                           d->d_iters, dev_counters);
+        k_sim_count<<<(B + 127) / 128, 128, 0, d->stream>>>(B, N, K, d->d_tx, d->d_out, d->d_conv, d->d_iters, dev_counters);
         CK(cudaGetLastError());
-        launches += d->last_launches + 3;
+        launches += d->last_launches + 4;
         done += B;
     }
     d->last_launches = launches;
