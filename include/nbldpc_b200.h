@@ -42,6 +42,10 @@ typedef enum {
 #define NBL_PREC_F32 0 /* fast mode: fp32 messages and arithmetic (QSPA transform in fp64)               */
 #define NBL_PREC_F64 1 /* parity mode: fp64 everywhere, reference operation order, no FMA contraction   */
 
+#define NBL_TIES_AUTO 0
+#define NBL_TIES_FAST 1
+#define NBL_TIES_REFERENCE 2
+
 typedef struct nbl_code nbl_code;       /* GF(q) tables + parity-check graph, resident on one device */
 typedef struct nbl_decoder nbl_decoder; /* message workspace for up to max_batch frames + a stream    */
 typedef struct nbl_encoder nbl_encoder; /* systematic encoder of one code on one device                 */
@@ -98,6 +102,12 @@ typedef struct {
                            (decision / iteration count latched at the first zero syndrome)       */
     int max_batch;   /* frames per nbl_decode_batch call that the workspace is sized for        */
     int device;      /* CUDA device ordinal                                                     */
+    int tie_mode;    /* T-EMS, exactly tied configuration costs (punctured symbols, quantised LLRs):
+                        NBL_TIES_REFERENCE: the recorded path is the one the reference's depth-first
+                        enumeration keeps (NBLDPC.cpp:1892-1944) -- served by the group kernel;
+                        NBL_TIES_FAST: first in the fast kernel's scan order (identical results whenever no
+                        two configurations of a syndrome tie exactly, i.e. for continuous LLRs);
+                        NBL_TIES_AUTO (0): REFERENCE in the fp64 parity mode, FAST in the fp32 mode         */
 } nbl_decoder_config;
 
 /* stream: a cudaStream_t (as void*) to launch on, or NULL for a private non-blocking stream */

@@ -12,6 +12,7 @@ from . import build as _build
 
 METHOD_QSPA, METHOD_EMS, METHOD_TEMS = 1, 2, 4
 PREC_F32, PREC_F64 = 0, 1
+TIES_AUTO, TIES_FAST, TIES_REFERENCE = 0, 1, 2
 NUM_COUNTERS = 8
 COUNTER_NAMES = ["frames", "err_frames", "err_syms", "err_bits", "converged", "undetected", "iterations", "reserved"]
 
@@ -29,7 +30,7 @@ class CodeInfo(C.Structure):
 class DecoderConfig(C.Structure):
     _fields_ = [("method", C.c_int), ("max_iter", C.c_int), ("p0", C.c_int), ("p1", C.c_int), ("factor", C.c_double),
                 ("offset", C.c_double), ("precision", C.c_int), ("early_stop", C.c_int), ("max_batch", C.c_int),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("tie_mode", C.c_int)]
 
 
 class SimConfig(C.Structure):
@@ -207,9 +208,9 @@ class Encoder:
 
 class Decoder:
     def __init__(self, code, method, max_iter=10, p0=0, p1=0, factor=1.0, offset=0.0, precision=PREC_F32, early_stop=1,
-                 max_batch=1, device=0, stream=None):
+                 max_batch=1, device=0, stream=None, tie_mode=TIES_AUTO):
         self.code = code
-        self.cfg = DecoderConfig(method, max_iter, p0, p1, factor, offset, precision, early_stop, max_batch, device)
+        self.cfg = DecoderConfig(method, max_iter, p0, p1, factor, offset, precision, early_stop, max_batch, device, tie_mode)
         h = C.c_void_p()
         _check(lib().nbl_decoder_create(C.byref(h), code._h, C.byref(self.cfg), stream))
         self._h = h

@@ -4,14 +4,13 @@
 // stage of Decoding_TEMS (reference NBLDPC.cpp:1055-1130, 1789-1944).  Same result, different algorithm:
 //   * the reference enumerates every configuration (<= n_c deviations, each eta deviating only in its n_r
 //     cheapest columns) with a recursive depth-first search, ~94 k leaves per GF(256) check;
-//   * here deltaW[s] = min(single deviation, best pair) is computed by all q threads at once as a
-//     min-plus XOR-convolution: for column d, thread s scans the compact list of deviations (b, dU[d][b])
-//     allowed in column d against P_d[s^b], the running minimum over the allowed deviations of the columns
-//     before d.  Same candidate set, so the same minimum; the winning path (two (column, eta) pairs) is kept
-//     for the output stage exactly as TEMS_Eta is.  n_c >= 3 uses the column DP in cn_tems_dp().
-// Tie-breaking among exactly equal path costs follows the scan order here (column, then eta ascending) and
-// the depth-first order in the reference; with continuous LLRs exact ties have probability zero
-// (see DESIGN.md "exact ties").
+//   * here deltaW[s] = min(single deviation, best pair) is computed by all q threads at once: for column fd,
+//     thread s scans the compact list of deviations (b, dU[fd][b]) allowed in column fd and pairs each with the
+//     allowed columns d2 > fd of s ^ b.  Same candidate set, so the same minimum; the winning path (two (column, eta)
+//     pairs) is kept for the output stage exactly as TEMS_Eta is.  n_c >= 3 uses the column DP in cn_tems_dp().
+// For n_c <= 2 the candidates are scanned in the reference's depth-first visiting order, so exactly tied path costs
+// (punctured symbols, quantised LLRs) record the same path as the reference; the n_c >= 3 DP resolves ties in its own
+// scan order (see DESIGN.md "exact ties").
 #pragma once
 #include "dev_common.cuh"
 
@@ -161,41 +160,43 @@ __device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, in
     }
     T *Tout = S.V;
     if (nc <= 2) {
-        // -- configuration search for n_c <= 2 ---------------------------------------------------------
-        T best = INF; int bb = 0, bd = 0;
-        if (nc >= 2) {
-            for (int d = 1; d < dcn; ++d) {
-                Grp<Q>::sync(gid);                                  // previous scan done with P / list
-                {   // fold column d-1 into the running minimum (strict '<': lower column wins ties)
-                    const T u = (x != 0 && ((S.amask[x] >> (d - 1)) & 1)) ? S.dU[(d - 1) * Q + x] : INF;
-                    if (u < S.P[x]) S.P[x] = u;
-                }
-                const bool in = x != 0 && ((S.amask[x] >> d) & 1);
-                int len;
-                const int pos = group_prefix_count<Q>(in, x, gid, S.wtot, len);
-                if (in) { S.lb[pos] = (uint8_t)x; S.lc[pos] = S.dU[d * Q + x]; }
-                Grp<Q>::sync(gid);
+        // -- configuration search for n_c <= 2, in the reference's own visiting order ------------------------
+        // TEMS_ConstructConf walks (eta_0, eta_1, ...) depth first, every eta_d ascending from 0, and keeps the first
+        // configuration that attains the minimum (strict '<', NBLDPC.cpp:1897).  For one syndrome s that order is: the
+        // LAST deviating column first ("first deviating column" fd descending), then eta_fd ascending -- the single
+        // deviation (fd, s) sits at eta_fd = s --, then the column of the second deviation descending.  Scanning the
+        // candidates in exactly that order with the same strict comparison reproduces the recorded path also when
+        // costs tie exactly (punctured symbols, quantised LLRs).
+        T best = INF; int bx = 0, bfd = 0, bd2 = -1;
+        for (int fd = dcn - 1; fd >= 0; --fd) {
+            Grp<Q>::sync(gid);                                      // previous scan done with the list
+            const bool in = x != 0 && ((S.amask[x] >> fd) & 1);
+            int len;
+            const int pos = group_prefix_count<Q>(in, x, gid, S.wtot, len);
+            if (in) { S.lb[pos] = (uint8_t)x; S.lc[pos] = S.dU[fd * Q + x]; }
+            Grp<Q>::sync(gid);
+            if (x != 0)
                 for (int i = 0; i < len; ++i) {
                     const int b = S.lb[i];
-                    const T cand = S.P[x ^ b] + S.lc[i];
-                    if (cand < best) { best = cand; bb = b; bd = d; }
+                    const T ub = S.lc[i];
+                    if (b == x) { if (ub < best) { best = ub; bx = b; bfd = fd; bd2 = -1; } }
+                    else if (nc >= 2) {
+                        const int y = x ^ b;
+                        const unsigned am = S.amask[y];
+                        for (int d2 = dcn - 1; d2 > fd; --d2)
+                            if ((am >> d2) & 1) {
+                                const T cand = ub + S.dU[d2 * Q + y];
+                                if (cand < best) { best = cand; bx = b; bfd = fd; bd2 = d2; }
+                            }
+                    }
                 }
-            }
         }
         // -- deltaW and the recorded path ------------------------------------------------------------------
         {
-            const int k0 = S.c0[x];
-            const T m0 = S.dU[k0 * Q + x];
-            T w; int nd, pc = 0;
+            T w; int nd, pc = 0, bb = 0;
             if (x == 0) { w = T(0); nd = 0; }
-            else if (best < m0) {
-                const int a = x ^ bb;                               // first deviation: cheapest allowed column before bd
-                T m = INF; int ca = 0;
-                const unsigned am = S.amask[a];
-                for (int c = 0; c < bd; ++c)
-                    if ((am >> c) & 1) { const T u = S.dU[c * Q + a]; if (u < m) { m = u; ca = c; } }
-                w = best; nd = 2; pc = ca | (bd << 4);
-            } else { w = m0; nd = 1; pc = k0; }
+            else if (bd2 >= 0) { w = best; nd = 2; pc = bfd | (bd2 << 4); bb = x ^ bx; }   // a = bx in column bfd, b in column bd2
+            else { w = best; nd = 1; pc = bfd; }
             S.dW[x] = w; S.pb[x] = (uint8_t)bb; S.pcol[x] = (uint8_t)pc; S.pnd[x] = (uint8_t)nd;
         }
         Grp<Q>::sync(gid);                                          // everyone is done with V and P

@@ -402,7 +402,9 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     d->it_ev.assign(2 * (size_t)cfg->max_iter, nullptr);
     for (auto &e : d->it_ev) if (cudaEventCreate(&e) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
     d->smem_iter = smem_for(d, q);
-    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !getenv("NBLDPC_FORCE_GENERIC");
+    if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_REFERENCE) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
+    const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
+    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
     if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
     *out = d;
     return NBL_OK;

@@ -8,10 +8,10 @@ from conftest import golden_lch, golden_names, load_golden, load_product_code
 pytestmark = pytest.mark.gpu
 
 
-def _decoder(code, meta, precision, max_batch, early_stop=1):
+def _decoder(code, meta, precision, max_batch, early_stop=1, tie_mode=0):
     from nbldpc_b200 import capi
     return capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
-                        precision=precision, early_stop=early_stop, max_batch=max_batch)
+                        precision=precision, early_stop=early_stop, max_batch=max_batch, tie_mode=tie_mode)
 
 
 def _post_tolerance(meta):
@@ -20,14 +20,19 @@ def _post_tolerance(meta):
     return 1e-6 if meta["method"] == 1 else 1e-8
 
 
+@pytest.mark.parametrize("tie_mode", [1, 2])
 @pytest.mark.parametrize("name", golden_names())
-def test_fp64_matches_reference_decisions_and_iterations(name, code_files):
-    """fp64 parity mode: return code, iteration count and every hard decision bit-exact with the reference."""
+def test_fp64_matches_reference_decisions_and_iterations(name, tie_mode, code_files):
+    """fp64 parity mode: return code, iteration count and every hard decision bit-exact with the reference.
+    tie_mode 1 = the fast kernels (T-EMS: one warp per check row), 2 = reference tie order (T-EMS: group kernel);
+    the golden frames have continuous LLRs, so both must agree with the reference."""
     from nbldpc_b200 import capi
     z, meta = load_golden(name)
+    if tie_mode == 2 and meta["method"] != 4:
+        pytest.skip("tie_mode only selects between the T-EMS kernels")
     code = load_product_code(code_files, meta["code"])
     F = len(z["ret"])
-    dec = _decoder(code, meta, capi.PREC_F64, F)
+    dec = _decoder(code, meta, capi.PREC_F64, F, tie_mode=tie_mode)
     lch = golden_lch(z, meta)
     r = dec.decode(lch, want_post=True)
     assert np.array_equal(r["converged"], z["ret"].astype(np.int32))

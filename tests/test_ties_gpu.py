@@ -1,0 +1,83 @@
+"""Exactly tied configuration costs: punctured symbols (all-zero LLR vectors) and quantised LLRs.
+
+With continuous LLRs two T-EMS configurations of a syndrome never have exactly the same cost; with erasures or integer
+LLRs they do all the time, and which of the tied paths is RECORDED changes the messages.  tie_mode = REFERENCE must
+reproduce the path the reference's depth-first enumeration keeps (NBLDPC.cpp:1892-1944).  All values in these tests are
+dyadic rationals, so fp32 and fp64 arithmetic are both exact and BOTH precisions must match the oracle decision for
+decision.  EMS and QSPA have one kernel each; their tie rules (insertion-sort order, NBLDPC.cpp:1715-1746; first
+maximum) are checked on the same inputs."""
+import numpy as np
+import pytest
+
+from test_warp_paths_gpu import _random_code
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(code, tmp_path, lch, method, p0, p1, offset, precision, max_iter=5, tie_mode=2):
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    path = tmp_path / ("tie_%d_%d.txt" % (code["q"], code["N"]))
+    path.write_text(po.code_text(code))
+    oc = po.OracleCode(code)
+    want = [oc.decode(method, max_iter, p0, p1, 1.0, offset, l) for l in lch]
+    dec = capi.Decoder(capi.Code.from_file(str(path)), method, max_iter, p0, p1, 1.0, offset, precision=precision,
+                       max_batch=len(lch), tie_mode=tie_mode)
+    r = dec.decode(lch, want_post=True)
+    return r, want
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("q,regular,p0,p1", [(16, False, 2, 2), (32, False, 2, 2), (64, True, 2, 2), (256, True, 2, 2),
+                                             (64, True, 1, 2), (64, True, 3, 2), (32, False, 2, 1), (64, False, 3, 2)])
+def test_tems_integer_llrs_and_erasures(q, regular, p0, p1, precision, tmp_path):
+    rng = np.random.default_rng(4000 + q + 10 * p0 + p1)
+    code = _random_code(q, 8, rng, regular)
+    F = 16
+    lch = rng.integers(-6, 3, size=(F, code["N"], q - 1)).astype(np.float64)     # integer LLRs: ties everywhere
+    lch[:, ::3, :] = 0.0                                                          # every third symbol erased
+    r, want = _run(code, tmp_path, lch, 4, p0, p1, 0.5, precision)
+    assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
+    assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
+    assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+    assert np.array_equal(r["post"], np.stack([w[3] for w in want]))              # exact arithmetic: identical posteriors
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_ems_integer_llrs_and_erasures(precision, tmp_path):
+    rng = np.random.default_rng(4100)
+    for q, regular in ((16, False), (64, True)):
+        code = _random_code(q, 8, rng, regular)
+        lch = rng.integers(-6, 3, size=(12, code["N"], q - 1)).astype(np.float64)
+        lch[:, ::3, :] = 0.0
+        r, want = _run(code, tmp_path, lch, 2, 8, 3, 0.5, precision)
+        assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
+        assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+        assert np.array_equal(r["post"], np.stack([w[3] for w in want]))
+
+
+def test_punctured_frames_through_the_front_end(tmp_path):
+    """BPSK frames with punctured symbols: demapper (zero LLR vectors) + T-EMS, fp64, against the oracle chain"""
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(4200)
+    for q, regular in ((64, True), (256, True), (32, False)):
+        code = _random_code(q, 8, rng, regular)
+        p = q.bit_length() - 1
+        N = code["N"]
+        punct = sorted(rng.choice(N, size=N // 4, replace=False).tolist())
+        path = tmp_path / ("pun_%d.txt" % q)
+        path.write_text(po.code_text(code))
+        F, sigma = 10, 0.55
+        y = 1.0 + sigma * rng.standard_normal((F, (N - len(punct)) * p))
+        oc = po.OracleCode(code)
+        want = []
+        for f in range(F):
+            L = po.demap_bpsk(q, N, y[f], sigma, punct)
+            assert not L[punct].any()
+            want.append(oc.decode(4, 8, 2, 2, 1.0, 0.5, L))
+        dec = capi.Decoder(capi.Code.from_file(str(path)), 4, 8, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=F)
+        r = dec.demap_decode(2, y, sigma, punct=punct)
+        assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32)), q
+        assert np.array_equal(r["sym"], np.stack([w[2] for w in want])), q
+        assert len(set(r["iterations"].tolist())) > 1

@@ -48,7 +48,7 @@ def _frames(code, F, sigma, rng):
     return np.stack([po.demap_bpsk(code["q"], code["N"], 1.0 + sigma * rng.standard_normal(code["N"] * p), sigma) for _ in range(F)])
 
 
-def _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset, env=None, max_iter=6):
+def _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset, env=None, max_iter=6, tie_mode=1):
     from nbldpc_b200 import capi
     from oracle import pyoracle as po
     path = tmp_path / ("code_%d_%d.txt" % (code["q"], code["N"]))
@@ -59,7 +59,7 @@ def _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset, env=None,
     os.environ.update(env or {})
     try:
         dec = capi.Decoder(capi.Code.from_file(str(path)), 4, max_iter, p0, p1, factor, offset, precision=capi.PREC_F64,
-                           max_batch=len(lch))
+                           max_batch=len(lch), tie_mode=tie_mode)               # 1: the warp kernel also in fp64
     finally:
         for k, v in old.items():
             if v is None:
@@ -109,7 +109,7 @@ def test_golden_through_the_other_kernels(name, env, code_files):
     os.environ.update(env)
     try:
         dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
-                           precision=capi.PREC_F64, max_batch=F)
+                           precision=capi.PREC_F64, max_batch=F, tie_mode=1)
     finally:
         for k in env:
             os.environ.pop(k, None)
