@@ -128,6 +128,7 @@ int CNBLDPC::ensure_decoder(int batch) {
     nbl_decoder_config cfg{};
     cfg.method = DecodeMethod; cfg.max_iter = maxIter; cfg.precision = precision_; cfg.early_stop = 1; cfg.max_batch = batch; cfg.device = 0;
     if (const char *dv = getenv("NBLDPC_DEVICE")) cfg.device = atoi(dv);
+    if (PunctureLen > 0) cfg.tie_mode = NBL_TIES_REFERENCE;    // erased symbols make configuration costs tie exactly
     if (DecodeMethod == EMS_DECODE) { cfg.p0 = EMS_Nm; cfg.p1 = EMS_Nc; cfg.factor = EMS_Correction_Factor; cfg.offset = EMS_Correction_Offset; }
     else if (DecodeMethod == T_EMS_DECODE) { cfg.p0 = TEMS_Nr; cfg.p1 = TEMS_Nc; cfg.factor = TEMS_Factor; cfg.offset = TEMS_Offset; }
     else { cfg.factor = 1; }
