@@ -81,3 +81,31 @@ def test_punctured_frames_through_the_front_end(tmp_path):
         assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32)), q
         assert np.array_equal(r["sym"], np.stack([w[2] for w in want])), q
         assert len(set(r["iterations"].tolist())) > 1
+
+
+def test_64qam_front_end_with_punctured_symbols(code_files, tmp_path):
+    """GF(64) + Gray 64-QAM: device demapper bit-exact with the oracle's, punctured symbols included,
+    and T-EMS / EMS decisions identical to the oracle on the resulting LLRs (fp64)"""
+    from conftest import constellation, get_code_dict, load_product_code
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    cs = constellation("GRAY_64QAM")
+    cd = get_code_dict("BDS.576.288.GF.64")
+    code = load_product_code(code_files, "BDS.576.288.GF.64")
+    rng = np.random.default_rng(4300)
+    N, F = cd["N"], 6
+    punct = sorted(rng.choice(N, size=6, replace=False).tolist())
+    sigma = 0.11
+    sent = rng.integers(0, 64, size=(F, N))                       # not code words: the decoder is compared, not the code
+    keep = [s for s in range(N) if s not in punct]
+    y = cs[sent[:, keep]] + sigma * rng.standard_normal((F, len(keep), 2))
+    oc = po.OracleCode(cd)
+    L = np.stack([po.demap_qam(64, N, y[f], cs, sigma, punct) for f in range(F)])
+    for method, p0, p1 in ((4, 2, 2), (2, 8, 3)):
+        dec = capi.Decoder(code, method, 6, p0, p1, 1.0, 0.5, precision=capi.PREC_F64, max_batch=F)
+        got = dec.demap_qam(y, cs, sigma, punct=punct)
+        assert np.array_equal(got, L)
+        want = [oc.decode(method, 6, p0, p1, 1.0, 0.5, L[f]) for f in range(F)]
+        r = dec.demap_decode(64, y, sigma, constellation=cs, punct=punct)
+        assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
+        assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
