@@ -38,6 +38,7 @@ typedef enum {
 #define NBL_METHOD_QSPA 1 /* BP_DECODE    -> CNBLDPC::Decoding_BP   NBLDPC.cpp:643-776  (FWHT check node)   */
 #define NBL_METHOD_EMS 2  /* EMS_DECODE   -> CNBLDPC::Decoding_EMS  NBLDPC.cpp:778-927                      */
 #define NBL_METHOD_TEMS 4 /* T_EMS_DECODE -> CNBLDPC::Decoding_TEMS NBLDPC.cpp:929-1143                     */
+#define NBL_METHOD_BSTEMS 7 /* BS_TEMS_DECODE -> CNBLDPC::Decoding_BS_TEMS NBLDPC.cpp:1145-1396 (basic-set T-EMS) */
 
 #define NBL_PREC_F32 0 /* fast mode: fp32 messages and arithmetic (QSPA transform in fp64)               */
 #define NBL_PREC_F64 1 /* parity mode: fp64 everywhere, reference operation order, no FMA contraction   */
@@ -92,10 +93,10 @@ int nbl_code_puncture_set(const nbl_code *code, int punct_degree, int *positions
 typedef struct {
     int method;      /* NBL_METHOD_*                                                           */
     int max_iter;    /* maxIter of the profile                                                 */
-    int p0;          /* EMS: n_m            T-EMS: n_r            QSPA: ignored                */
-    int p1;          /* EMS: n_c            T-EMS: n_c            QSPA: ignored                */
-    double factor;   /* EMS/T-EMS correction factor (divide)                                   */
-    double offset;   /* EMS/T-EMS offset (soft threshold)                                      */
+    int p0;          /* EMS: n_m      T-EMS: n_r      BS-TEMS: basic_set_Nm      QSPA: ignored */
+    int p1;          /* EMS: n_c      T-EMS: n_c      BS-TEMS: basic_set_Nc      QSPA: ignored */
+    double factor;   /* EMS / T-EMS / BS-TEMS correction factor (divide)                       */
+    double offset;   /* EMS / T-EMS / BS-TEMS offset (soft threshold)                          */
     int precision;   /* NBL_PREC_*                                                             */
     int early_stop;  /* 1: frames leave the batch when their syndrome is zero (reference rule);
                         0: every frame runs max_iter iterations, outputs are still the reference's

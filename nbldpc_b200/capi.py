@@ -10,7 +10,7 @@ import numpy as np
 
 from . import build as _build
 
-METHOD_QSPA, METHOD_EMS, METHOD_TEMS = 1, 2, 4
+METHOD_QSPA, METHOD_EMS, METHOD_TEMS, METHOD_BSTEMS = 1, 2, 4, 7
 PREC_F32, PREC_F64 = 0, 1
 TIES_AUTO, TIES_FAST, TIES_REFERENCE = 0, 1, 2
 NUM_COUNTERS = 8

@@ -13,6 +13,8 @@
 // scan order (see DESIGN.md "exact ties").
 #pragma once
 #include "dev_common.cuh"
+#include <cstring>
+#include <type_traits>
 
 namespace nbl {
 
@@ -223,6 +225,149 @@ __device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, in
     }
     // -- fill-in (NBLDPC.cpp:1095-1102), back to the normal domain, un-permute, correct (1105-1128) -----
     for (int d = 0; d < dcn; ++d) {
+        const int e = e0 + d;
+        const int bs = syn ^ g.pfwd[(size_t)e * Q + S.sdec[d]];
+        auto getT = [&](int t) -> T {
+            T v = Tout[d * Q + t];
+            if (v == INF) { const int k0 = S.c0[t], k1 = S.c1[t]; v = (d == k0) ? S.dU[k1 * Q + t] : S.dU[k0 * Q + t]; }
+            return v;
+        };
+        T out = T(0);
+        if (x != 0) {
+            const int t = g.pfwd[(size_t)e * Q + x] ^ bs;
+            out = soft_threshold<T>(getT(bs) - getT(t), factor, offset);
+        }
+        c2v_out[(size_t)e * Q + x] = out;
+    }
+}
+
+
+// ---- BS-TEMS check node (CNBLDPC::Decoding_BS_TEMS, NBLDPC.cpp:1145-1396; Construct_BasicSet :2023-2101;
+//      BasicSet_TEMS_ConstructConf :2102-2147) ----------------------------------------------------------------------------
+// What the reference computes in this mode (TEMS_Nr is never set there, so the T-EMS stage only leaves the all-zero
+// configuration): the "basic set" = the n_m cheapest eta by m0(eta) = dU[c0(eta)][eta] -- for n_m <= log2 q chosen
+// greedily so that they are linearly independent over GF(2) --, then every subset of it with at most n_c elements and
+// no column used twice is a configuration; syndromes no subset reaches keep deltaW = +inf and take the fill-in value.
+// The subset enumeration is tiny (2^n_m leaves) and its running sum is formed by add / subtract exactly in the
+// reference's order, so one thread walks it with the same recursion; everything around it is data parallel.
+template <typename T> __device__ inline void atomic_min_any(T *addr, T v) {      // values of either sign (CAS loop)
+    using U = typename std::conditional<sizeof(T) == 4, unsigned, unsigned long long>::type;
+    U *a = reinterpret_cast<U *>(addr);
+    U old = *a;
+    while (true) {
+        T cur;
+        memcpy(&cur, &old, sizeof(T));
+        if (!(v < cur)) return;
+        U nv; memcpy(&nv, &v, sizeof(T));
+        const U prev = atomicCAS(a, old, nv);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+template <typename T, int Q> struct BsWalk {
+    TemsSmem<T, Q> &S;
+    int nm, nc, dcn;
+    unsigned col_sel; int diff, sum_sym; T sum;
+    uint8_t cand[16];
+    __device__ void walk(int begin) {
+        if (begin >= nm) {
+            if (sum < S.dW[sum_sym]) {
+                S.dW[sum_sym] = sum;
+                for (int d = 0; d < dcn; ++d) S.eta[d * Q + sum_sym] = cand[d];
+            }
+            return;
+        }
+        const int col = S.pb[begin], bq = S.lb[begin];
+        const T bL = S.lc[begin];
+        if (!((col_sel >> col) & 1)) {
+            diff += 1;
+            if (diff <= nc) {
+                col_sel |= 1u << col;
+                sum_sym ^= bq; sum = sum + bL; cand[col] = (uint8_t)bq;
+                walk(begin + 1);
+                sum_sym ^= bq; sum = sum - bL; col_sel &= ~(1u << col);
+                diff -= 1; cand[col] = 0;
+                walk(begin + 1);
+            } else {
+                diff -= 1; cand[col] = 0;
+                walk(begin + 1);
+            }
+        } else walk(begin + 1);
+    }
+};
+
+// Inputs as cn_tems.  nm = basic_set_Nm (1 .. min(q-1, 16)), nc = basic_set_Nc.
+template <typename T, int Q>
+__device__ void cn_bstems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, int e0, int dcn, int nm, int nc,
+                          T factor, T offset, int &phase, T *__restrict__ c2v_out) {
+    using K = typename Real<T>::key_t;
+    const T INF = Real<T>::inf();
+    int syn = 0;
+    for (int d = 0; d < dcn; ++d) syn ^= g.pfwd[(size_t)(e0 + d) * Q + S.sdec[d]];
+    for (int d = 0; d < dcn; ++d) {                                 // TEMS_Get_deltaU
+        const int sd = S.sdec[d];
+        const int beta = g.pfwd[(size_t)(e0 + d) * Q + sd];
+        const T vmax = S.V[d * Q + sd];
+        const int k = g.pinv[(size_t)(e0 + d) * Q + (x ^ beta)];
+        S.dU[d * Q + x] = vmax - S.V[d * Q + k];
+    }
+    Grp<Q>::sync(gid);
+    T m0;
+    {   // TEMS_Get_Min: stable order of the columns by dU[.][x]
+        int k0 = 0, k1 = 0;
+        for (int d = 0; d < dcn; ++d) {
+            const T ud = S.dU[d * Q + x];
+            int rank = 0;
+            for (int c = 0; c < dcn; ++c) { const T uc = S.dU[c * Q + x]; rank += (uc < ud) || (uc == ud && c < d); }
+            if (rank == 0) k0 = d;
+            if (rank == 1) k1 = d;
+        }
+        S.c0[x] = (uint8_t)k0; S.c1[x] = (uint8_t)k1;
+        m0 = S.dU[k0 * Q + x];
+        S.dW[x] = x == 0 ? T(0) : INF;                              // the T-EMS stage of this mode: all-zero configuration only
+        for (int d = 0; d < dcn; ++d) S.eta[d * Q + x] = 0;
+        S.bp[x] = 0;                                                // span flags of the greedy basis
+    }
+    Grp<Q>::sync(gid);
+    // Construct_BasicSet: the nm cheapest eta != 0 (ascending m0), linearly independent when nm <= log2 q
+    bool avail = x != 0;
+    int found = 0;
+    for (int k = 0; k < nm; ++k) {
+        K key[2] = {avail ? (K)~order_key(m0) : K(0), K(0)}, kmax[2]; int xw[2];
+        group_argmax<Q, K, 2, true>(key, x, gid, S.red, phase, kmax, xw);
+        if (kmax[0] == K(0)) break;                                 // nothing left (nm > number of candidates)
+        found = k + 1;
+        const int w = xw[0];
+        if (x == 0) { S.lb[k] = (uint8_t)w; S.pb[k] = S.c0[w]; S.lc[k] = S.dU[(size_t)S.c0[w] * Q + w]; }
+        if (nm > g.p) avail = avail && x != w;
+        else {
+            const int in = S.bp[x] | S.bp[x ^ w] | (x == w);        // span of the chosen elements (without 0)
+            Grp<Q>::sync(gid);
+            S.bp[x] = (uint8_t)in;
+            avail = avail && !in;
+            Grp<Q>::sync(gid);
+        }
+    }
+    Grp<Q>::sync(gid);
+    if (x == 0) {
+        BsWalk<T, Q> wk{S, found, nc, dcn, 0u, 0, 0, T(0), {0}};
+        wk.walk(0);
+    }
+    Grp<Q>::sync(gid);                                              // deltaW / Eta complete; V is free from here on
+    T *Tout = S.V;
+    for (int d = 0; d < dcn; ++d) Tout[d * Q + x] = INF;
+    Grp<Q>::sync(gid);
+    {
+        const T w = S.dW[x];
+        if (w < INF)
+            for (int d = 0; d < dcn; ++d) {
+                const int dev = S.eta[d * Q + x];
+                atomic_min_any(&Tout[d * Q + (x ^ dev)], w - S.dU[d * Q + dev]);
+            }
+    }
+    Grp<Q>::sync(gid);
+    for (int d = 0; d < dcn; ++d) {                                 // fill-in, normal domain, un-permute, correct
         const int e = e0 + d;
         const int bs = syn ^ g.pfwd[(size_t)e * Q + S.sdec[d]];
         auto getT = [&](int t) -> T {

@@ -74,9 +74,10 @@ __global__ void __launch_bounds__(Grp<Q>::THREADS) k_iterate(const IterParams<T>
     size_t per_group;
     TemsSmem<T, Q> St; EmsSmem<T, Q> Se; QspaSmem<T, Q> Sq;
     T *V; int *sdec; RedScratch<typename Real<T>::key_t, Grp<Q>::WARPS, 2> *red;
-    if (METHOD == NBL_METHOD_TEMS) {
-        per_group = TemsSmem<T, Q>::bytes(g.max_dc, P.p1);
-        St.carve(smem_raw + per_group * gid, g.max_dc, P.p1); V = St.V; sdec = St.sdec; red = St.red;
+    if (METHOD == NBL_METHOD_TEMS || METHOD == NBL_METHOD_BSTEMS) {
+        const int nca = METHOD == NBL_METHOD_BSTEMS ? 3 : P.p1;           // BS-TEMS uses the eta / back-pointer arrays of the n_c >= 3 layout
+        per_group = TemsSmem<T, Q>::bytes(g.max_dc, nca);
+        St.carve(smem_raw + per_group * gid, g.max_dc, nca); V = St.V; sdec = St.sdec; red = St.red;
     } else if (METHOD == NBL_METHOD_EMS) {
         per_group = EmsSmem<T, Q>::bytes(g.max_dc, P.p0, P.p1);
         Se.carve(smem_raw + per_group * gid, g.max_dc, P.p0, P.p1); V = Se.V; sdec = Se.sdec; red = Se.red;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(Grp<Q>::THREADS) k_iterate(const IterParams<T>
     // ---- step D: check node ---------------------------------------------------------------------------
     T *out = P.c2v_out + fE * Q;
     if (METHOD == NBL_METHOD_TEMS) cn_tems<T, Q>(St, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, out);
+    else if (METHOD == NBL_METHOD_BSTEMS) cn_bstems<T, Q>(St, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, phase, out);
     else if (METHOD == NBL_METHOD_EMS) cn_ems<T, Q>(Se, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, phase, out);
     else cn_qspa<T, Q>(Sq, g, gid, x, e0, dcn, out);
 }
@@ -299,6 +301,7 @@ static size_t smem_for(const nbl_decoder *d, int Q) {
 #define PER(QQ)                                                                                              \
     if (Q == QQ) {                                                                                           \
         if (d->cfg.method == NBL_METHOD_TEMS) per = f64 ? TemsSmem<double, QQ>::bytes(mdc, d->cfg.p1) : TemsSmem<float, QQ>::bytes(mdc, d->cfg.p1); \
+        else if (d->cfg.method == NBL_METHOD_BSTEMS) per = f64 ? TemsSmem<double, QQ>::bytes(mdc, 3) : TemsSmem<float, QQ>::bytes(mdc, 3); \
         else if (d->cfg.method == NBL_METHOD_EMS) per = f64 ? EmsSmem<double, QQ>::bytes(mdc, d->cfg.p0, d->cfg.p1) : EmsSmem<float, QQ>::bytes(mdc, d->cfg.p0, d->cfg.p1); \
         else per = f64 ? QspaSmem<double, QQ>::bytes(mdc) : QspaSmem<float, QQ>::bytes(mdc);              \
     }
@@ -324,8 +327,11 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
 
 extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const nbl_decoder_config *cfg, void *stream) {
     if (!out || !code || !cfg) { nbl_set_error("nbl_decoder_create: null argument"); return NBL_ERR_ARG; }
-    if (cfg->method != NBL_METHOD_QSPA && cfg->method != NBL_METHOD_EMS && cfg->method != NBL_METHOD_TEMS) {
-        nbl_set_error("nbl_decoder_create: decode method not supported (1 QSPA, 2 EMS, 4 T-EMS)"); return NBL_ERR_ARG;
+    if (cfg->method != NBL_METHOD_QSPA && cfg->method != NBL_METHOD_EMS && cfg->method != NBL_METHOD_TEMS && cfg->method != NBL_METHOD_BSTEMS) {
+        nbl_set_error("nbl_decoder_create: decode method not supported (1 QSPA, 2 EMS, 4 T-EMS, 7 BS-TEMS)"); return NBL_ERR_ARG;
+    }
+    if (cfg->method == NBL_METHOD_BSTEMS && (cfg->p0 < 1 || cfg->p0 > 16 || cfg->p0 > code->q - 1 || cfg->p1 < 1 || code->max_dc > 16)) {
+        nbl_set_error("BS-TEMS needs 1 <= basic_set_Nm <= min(q - 1, 16), basic_set_Nc >= 1 and check degree <= 16"); return NBL_ERR_ARG;
     }
     if (cfg->max_iter < 1 || cfg->max_batch < 1) { nbl_set_error("nbl_decoder_create: max_iter and max_batch must be >= 1"); return NBL_ERR_ARG; }
     if (cfg->method == NBL_METHOD_EMS && (cfg->p0 < 1 || cfg->p0 > code->q || cfg->p1 < 1)) {
@@ -485,6 +491,7 @@ template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const 
     if (d->warp_path) return launch_iterate_warp<T, Q>(d, P);
     switch (d->cfg.method) {
         case NBL_METHOD_TEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_TEMS>(d, P);
+        case NBL_METHOD_BSTEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_BSTEMS>(d, P);
         case NBL_METHOD_EMS: return launch_iterate_tqm<T, Q, NBL_METHOD_EMS>(d, P);
         default: return launch_iterate_tqm<T, Q, NBL_METHOD_QSPA>(d, P);
     }
@@ -518,7 +525,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
     CK(cudaEventRecord(d->ev0, d->stream));
     T w_old = 0, w_new = 1;
     if (c.method == NBL_METHOD_QSPA) { w_old = (T)0.5; w_new = (T)0.5; }          // NBLDPC.cpp:739
-    if (c.method == NBL_METHOD_TEMS) { w_old = (T)0.25; w_new = (T)0.75; }        // NBLDPC.cpp:1046
+    if (c.method == NBL_METHOD_TEMS || c.method == NBL_METHOD_BSTEMS) { w_old = (T)0.25; w_new = (T)0.75; }   // NBLDPC.cpp:1046, 1262
     for (int it = 1; it <= c.max_iter; ++it) {
         const T *cin = (const T *)d->d_c2v[(it - 1) & 1];
         T *cout = (T *)d->d_c2v[it & 1];

@@ -49,6 +49,7 @@ bool CNBLDPC::Initial(CSimulation &sim) {
     DecodeMethod = sim.decodeMethod;
     EMS_Nm = sim.ems_nm; EMS_Nc = sim.ems_nc; EMS_Correction_Factor = sim.ems_factor; EMS_Correction_Offset = sim.ems_offset;
     TEMS_Nr = sim.tems_nr; TEMS_Nc = sim.tems_nc; TEMS_Factor = sim.tems_factor; TEMS_Offset = sim.tems_offset;
+    basic_set_Nm = sim.bs_tems_nm; basic_set_Nc = sim.bs_tems_nc; basic_set_factor = sim.bs_tems_factor; basic_set_offset = sim.bs_tems_offset;   // NBLDPC.cpp:334-337
     OSD_Order = sim.OSD_order;
     precision_ = sim.precision;
     if (DecodeMethod == EMS_DECODE && EMS_Nm > GFq) { std::cerr << "EMS configuration error! EMS_Nm is too large!" << std::endl; exit(-1); }
@@ -131,6 +132,7 @@ int CNBLDPC::ensure_decoder(int batch) {
     if (PunctureLen > 0) cfg.tie_mode = NBL_TIES_REFERENCE;    // erased symbols make configuration costs tie exactly
     if (DecodeMethod == EMS_DECODE) { cfg.p0 = EMS_Nm; cfg.p1 = EMS_Nc; cfg.factor = EMS_Correction_Factor; cfg.offset = EMS_Correction_Offset; }
     else if (DecodeMethod == T_EMS_DECODE) { cfg.p0 = TEMS_Nr; cfg.p1 = TEMS_Nc; cfg.factor = TEMS_Factor; cfg.offset = TEMS_Offset; }
+    else if (DecodeMethod == BS_TEMS_DECODE) { cfg.p0 = basic_set_Nm; cfg.p1 = basic_set_Nc; cfg.factor = basic_set_factor; cfg.offset = basic_set_offset; }
     else { cfg.factor = 1; }
     if (nbl_decoder_create(&dec_, code_, &cfg, nullptr) != NBL_OK) die("decoder");
     dec_batch_ = batch;
@@ -155,6 +157,7 @@ int CNBLDPC::run_method(int method, double **L_ch, int *out) {
 int CNBLDPC::Decoding_BP(double **L_ch, int *DecodeOutput) { return run_method(BP_DECODE, L_ch, DecodeOutput); }
 int CNBLDPC::Decoding_EMS(double **L_ch, int *DecodeOutput, int *) { return run_method(EMS_DECODE, L_ch, DecodeOutput); }
 int CNBLDPC::Decoding_TEMS(double **L_ch, int *DecodeOutput, int *, int *) { return run_method(T_EMS_DECODE, L_ch, DecodeOutput); }
+int CNBLDPC::Decoding_BS_TEMS(double **L_ch, int *DecodeOutput, int *, int *) { return run_method(BS_TEMS_DECODE, L_ch, DecodeOutput); }
 
 int CNBLDPC::Decoding(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, int *RelySeri_bit) {
     switch (DecodeMethod) {                      // NBLDPC.cpp:607-641
@@ -163,7 +166,8 @@ int CNBLDPC::Decoding(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, in
     case T_EMS_DECODE: return Decoding_TEMS(L_ch, DecodeOutput, RelySeri_symbol, RelySeri_bit);
     case MinMax_DECODE: std::cout << "Min Max algorithm has not been developed" << std::endl; exit(-1);
     case T_MinMax_DECODE: std::cout << "Trellis Min Max algorithm has not been developed" << std::endl; exit(-1);
-    case OSD_DECODE: case BS_TEMS_DECODE: std::cout << "Decode method " << DecodeMethod << " is outside this decode path" << std::endl; exit(-1);
+    case BS_TEMS_DECODE: return Decoding_BS_TEMS(L_ch, DecodeOutput, RelySeri_symbol, RelySeri_bit);
+    case OSD_DECODE: std::cout << "Decode method " << DecodeMethod << " is outside this decode path" << std::endl; exit(-1);
     default: std::cout << "Decode Method is not specified!" << std::endl; exit(-1);
     }
     return 0;

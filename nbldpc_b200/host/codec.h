@@ -29,6 +29,7 @@ public:
     double **L_post = nullptr;                 // posterior of the last Decoding() call, [CodeLen][GFq-1]
     int EMS_Nm = 0, EMS_Nc = 0; double EMS_Correction_Factor = 1, EMS_Correction_Offset = 0;
     int TEMS_Nr = 0, TEMS_Nc = 0; double TEMS_Factor = 1, TEMS_Offset = 0;
+    int basic_set_Nm = 0, basic_set_Nc = 0; double basic_set_factor = 1, basic_set_offset = 0;   // NBLDPC.h:169-172
     int OSD_Order = -1;
     double tems_route_num = 0;                 // kept for source compatibility; the GPU search does not count leaves
     int lastIterations = 0;                    // iteration count of the last Decoding() call (not exposed by the reference)
@@ -39,6 +40,7 @@ public:
     int Decoding(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, int *RelySeri_bit);
     int Decoding_BP(double **L_ch, int *DecodeOutput);
     int Decoding_EMS(double **L_ch, int *DecodeOutput, int *RelySeri_bit);
+    int Decoding_BS_TEMS(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, int *RelySeri_bit);   // NBLDPC.h (BS_TEMS_DECODE)
     int Decoding_TEMS(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, int *RelySeri_bit);
     int DecideLLRVector(double *LLR);
 

@@ -433,7 +433,145 @@ static void cn_tems(state *s, tems_ctx *t, double factor, double offset) {
     }
 }
 
-/* ------------------------------------------------- the three decoders */
+
+/* ------------------------------------------------- BS-TEMS check node (Decoding_BS_TEMS, NBLDPC.cpp:1145-1396) */
+typedef struct {
+    tems_ctx *t; int nm, nc;
+    int *bq, *bcol; double *bL;           /* basicSet_q / basicSet_col / basicSet_L */
+    unsigned char *col_sel;
+    int *order; unsigned char *avail; int *R;
+} bs_ctx;
+
+/* Construct_BasicSet, NBLDPC.cpp:2023-2101.  std::sort there; any comparison sort gives the same order when no two
+ * LLV tie (continuous LLRs); ties other than that are implementation-defined in the reference itself. */
+static const double *g_sort_key;
+static int cmp_order(const void *a, const void *b) {
+    double x = g_sort_key[*(const int *)a], y = g_sort_key[*(const int *)b];
+    if (x < y) return -1;
+    if (x > y) return 1;
+    return *(const int *)a - *(const int *)b;
+}
+static void bs_construct(bs_ctx *b, double *LLV) {
+    tems_ctx *t = b->t; int q = t->s->c->q;
+    for (int i = 0; i < q; ++i) { LLV[i] = t->dU[t->ord[i][0]][i]; b->order[i] = i; b->avail[i] = 1; }
+    b->avail[0] = 0;
+    g_sort_key = LLV;
+    qsort(b->order, q, sizeof(int), cmp_order);
+    int bit_len = 0; while ((1 << bit_len) < q) ++bit_len;
+    if (b->nm > bit_len) {
+        for (int i = 0; i < q - 1; ++i) { int e = b->order[i + 1]; b->bq[i] = e; b->bcol[i] = t->ord[e][0]; b->bL[i] = LLV[e]; }
+    } else {
+        int e0 = b->order[1];
+        b->bq[0] = e0; b->bcol[0] = t->ord[e0][0]; b->bL[0] = LLV[e0];
+        int rn = 0; b->R[rn++] = e0; b->avail[e0] = 0;
+        int R_num = 1, n = 1;
+        for (int i = 2; i < q; ++i) {
+            if (R_num >= q - 1) break;
+            int tq = b->order[i];
+            if (b->avail[tq]) {
+                b->bq[n] = tq; b->bcol[n] = t->ord[tq][0]; b->bL[n] = LLV[tq]; ++n;
+                for (int j = 0; j < R_num; ++j) { int sq = tq ^ b->R[j]; b->R[rn++] = sq; b->avail[sq] = 0; }
+                b->R[rn++] = tq; b->avail[tq] = 0;
+                R_num = 2 * R_num + 1;
+            }
+        }
+    }
+}
+/* BasicSet_TEMS_ConstructConf, NBLDPC.cpp:2102-2147: include-first recursion over the first nm basic elements */
+static void bs_conf(bs_ctx *b, int begin, int end, int maxdc) {
+    tems_ctx *t = b->t;
+    if (begin > end) {
+        if (t->sum < t->dW[t->sum_sym]) {
+            t->dW[t->sum_sym] = t->sum;
+            for (int d = 0; d < maxdc; ++d) t->eta[t->sum_sym][d] = t->cand[d];
+        }
+        return;
+    }
+    int col = b->bcol[begin];
+    if (!b->col_sel[col]) {
+        t->diff += 1;
+        if (t->diff <= b->nc) {
+            b->col_sel[col] = 1;
+            t->sum_sym ^= b->bq[begin];
+            t->sum += b->bL[begin];
+            t->cand[col] = b->bq[begin];
+            bs_conf(b, begin + 1, end, maxdc);
+            t->sum_sym ^= b->bq[begin];
+            t->sum -= b->bL[begin];
+            b->col_sel[col] = 0;
+            t->diff -= 1;
+            t->cand[col] = 0;
+            bs_conf(b, begin + 1, end, maxdc);
+        } else {
+            t->diff -= 1;
+            t->cand[col] = 0;
+            bs_conf(b, begin + 1, end, maxdc);
+        }
+    } else bs_conf(b, begin + 1, end, maxdc);
+}
+
+static void cn_bstems(state *s, bs_ctx *b, double *LLV, double factor, double offset) {
+    tems_ctx *t = b->t;
+    const orc_code *c = s->c; int q = c->q;
+    for (int row = 0; row < c->M; ++row) {
+        int dcn = c->cdeg[row];
+        t->syn = 0;                                           /* TEMS_Get_Beta */
+        for (int d = 0; d < dcn; ++d) {
+            const double *v = V2C(s, c->clink[row * c->maxdc + d], c->cdv[row * c->maxdc + d]);
+            int h = c->ccoef[row * c->maxdc + d];
+            double mx = 0; int me = 0;
+            for (int k = 1; k < q; ++k) if (v[k - 1] > mx) { mx = v[k - 1]; me = MUL(c, k, h); }
+            t->beta[d] = me; t->syn ^= me;
+        }
+        for (int d = 0; d < dcn; ++d) {                       /* TEMS_Get_deltaU */
+            const double *v = V2C(s, c->clink[row * c->maxdc + d], c->cdv[row * c->maxdc + d]);
+            int hi = INV(c, c->ccoef[row * c->maxdc + d]);
+            int bp = MUL(c, hi, t->beta[d]);
+            double mx = bp == 0 ? 0 : v[bp - 1];
+            t->dU[d][t->beta[d]] = mx - 0;
+            for (int x = 1; x < q; ++x) t->dU[d][x ^ t->beta[d]] = mx - v[MUL(c, hi, x) - 1];
+        }
+        for (int e = 0; e < q; ++e) {                         /* TEMS_Get_Min: column order; TEMS_Nr is 0 in this mode */
+            for (int d = 0; d < dcn; ++d) t->ord[e][d] = d;
+            for (int d = 1; d < dcn; ++d)
+                for (int k = d; k >= 1; --k) {
+                    if (t->dU[t->ord[e][k]][e] < t->dU[t->ord[e][k - 1]][e]) {
+                        int tmp = t->ord[e][k]; t->ord[e][k] = t->ord[e][k - 1]; t->ord[e][k - 1] = tmp;
+                    } else break;
+                }
+        }
+        for (int d = 0; d < dcn; ++d) t->allowed[0][d] = 1;
+        for (int e = 1; e < q; ++e) for (int d = 0; d < dcn; ++d) t->allowed[e][d] = 0;
+        for (int e = 0; e < q; ++e) { t->dW[e] = DBL_MAX; t->used[e] = 0; }
+        for (int d = 0; d < c->maxdc; ++d) b->col_sel[d] = 0;
+        t->sum_sym = 0; t->diff = 0; t->sum = 0.0; t->end = dcn - 1; t->nc = 1;
+        tems_conf(t, 0);                                      /* TEMS_ConstructConf(1, 1, ...): only the all-zero configuration */
+        bs_construct(b, LLV);
+        t->sum_sym = 0; t->diff = 0; t->sum = 0.0;
+        bs_conf(b, 0, b->nm - 1, c->maxdc);
+        for (int d = 0; d < dcn; ++d) {                       /* outputs, NBLDPC.cpp:1330-1384 */
+            for (int e = 0; e < q; ++e) { t->T[e] = DBL_MAX; t->hit[e] = 0; }
+            for (int e = 0; e < q; ++e) {
+                int dev = t->eta[e][d], tgt = e ^ dev;
+                double m = t->dW[e] - t->dU[d][dev];
+                if (t->T[tgt] > m) { t->T[tgt] = m; t->hit[tgt] = 1; }
+            }
+            for (int e = 0; e < q; ++e)
+                if (!t->hit[e]) t->T[e] = (d == t->ord[e][0]) ? t->dU[t->ord[e][1]][e] : t->dU[t->ord[e][0]][e];
+            int hi = INV(c, c->ccoef[row * c->maxdc + d]);
+            int bs = t->syn ^ t->beta[d];
+            double L0 = -1.0 * t->T[bs];
+            double *o = C2V(s, row, d);
+            for (int e = 0; e < q; ++e)
+                if (e != bs) {
+                    int k = MUL(c, hi, e ^ bs);
+                    o[k - 1] = soft_threshold(-1.0 * t->T[e] - L0, factor, offset);
+                }
+        }
+    }
+}
+
+/* ------------------------------------------------- the decoders */
 static void *alloc2(int rows, int cols, size_t esz, void ***index) {
     char *blk = calloc((size_t)rows * cols, esz);
     void **ix = malloc(sizeof(void *) * rows);
@@ -464,7 +602,7 @@ int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, doub
         blk[nblk++] = alloc2(c->maxdc, q, sizeof(int), (void ***)&e.sym);
         e.best = malloc(sizeof(double) * q);
     } else {
-        t.s = &s; t.nr = p0; t.nc = p1;
+        t.s = &s; t.nr = method == 7 ? 0 : p0; t.nc = p1;
         blk[nblk++] = alloc2(c->maxdc, q, sizeof(double), (void ***)&t.dU);
         blk[nblk++] = alloc2(q, c->maxdc, sizeof(int), (void ***)&t.ord);
         blk[nblk++] = alloc2(q, c->maxdc, 1, (void ***)&t.allowed);
@@ -474,6 +612,14 @@ int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, doub
         t.used = calloc(q, 1); t.hit = calloc(q, 1);
         g_tems_leaves = 0;
     }
+    bs_ctx bs; memset(&bs, 0, sizeof bs);
+    double *LLV = 0;
+    if (method == 7) {                                   /* BS-TEMS: p0 = basic_set_Nm, p1 = basic_set_Nc */
+        bs.t = &t; bs.nm = p0; bs.nc = p1;
+        bs.bq = calloc(q, sizeof(int)); bs.bcol = calloc(q, sizeof(int)); bs.bL = calloc(q, sizeof(double));
+        bs.col_sel = calloc(c->maxdc, 1); bs.order = calloc(q, sizeof(int)); bs.avail = calloc(q, 1); bs.R = calloc(2 * q, sizeof(int));
+        LLV = calloc(q, sizeof(double));
+    }
 
     int ok = 0, it = 0;
     while (it++ < max_iter) {
@@ -481,6 +627,7 @@ int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, doub
         if (ok) break;
         if (method == 1) { var_to_check(&s, L_post, 0.5, 0.5); cn_qspa(&s, &b); }
         else if (method == 2) { var_to_check(&s, L_post, 0, 1); cn_ems(&s, &e, factor, offset); }
+        else if (method == 7) { var_to_check(&s, L_post, 0.25, 0.75); cn_bstems(&s, &bs, LLV, factor, offset); }
         else { var_to_check(&s, L_post, 0.25, 0.75); cn_tems(&s, &t, factor, offset); }
     }
     *iters = ok ? it : max_iter;
@@ -490,6 +637,7 @@ int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, doub
     free(e.srt); free(e.sym); free(e.best);
     free(t.dU); free(t.ord); free(t.allowed); free(t.eta); free(t.beta); free(t.cand);
     free(t.dW); free(t.T); free(t.used); free(t.hit);
+    free(bs.bq); free(bs.bcol); free(bs.bL); free(bs.col_sel); free(bs.order); free(bs.avail); free(bs.R); free(LLV);
     for (int i = 0; i < nblk; ++i) free(blk[i]);
     return ok;
 }

@@ -34,8 +34,8 @@ void orc_demap_bpsk(int q, int N, const double *y_re, double sigma, const int *p
 void orc_demap_qam(int q, int N, const double *y, const double *constellation, double sigma,
                    const int *punct_sym, int n_punct, double *L_ch);
 
-/* CNBLDPC::Decoding (NBLDPC.cpp:607-641) for method 1 (QSPA), 2 (EMS), 4 (T-EMS).
- * p0,p1 = (n_m,n_c) for EMS, (n_r,n_c) for T-EMS; factor/offset as in the profile.
+/* CNBLDPC::Decoding (NBLDPC.cpp:607-641) for method 1 (QSPA), 2 (EMS), 4 (T-EMS), 7 (BS-TEMS).
+ * p0,p1 = (n_m,n_c) for EMS, (n_r,n_c) for T-EMS, (basic_set_Nm, basic_set_Nc) for BS-TEMS; factor/offset as in the profile.
  * L_ch, L_post: [N][q-1] doubles.  Returns 1 converged / 0 not (as the reference);
  * *iters = value of the reference's iter_number when it returned (maxIter on failure). */
 int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, double factor, double offset,

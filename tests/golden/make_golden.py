@@ -43,6 +43,9 @@ CASES = {
     "x_ems_gf16_dc5": dict(code="divsalar.UNBLDPC.128.64.GF.16", GFq=16, method=2, snr=2.0, frames=24, ems_nm=6, ems_nc=2, ems_offset=0.2),
     "x_ems_gf256": dict(code="divsalar.UNBLDPC.128.64.GF.256", GFq=256, method=2, snr=2.5, frames=6, ems_nm=8, ems_nc=3),
     "x_qspa_gf64": dict(code="BDS.576.288.GF.64", GFq=64, method=1, snr=1.5, frames=3),
+    "f2_bstems_gf256": dict(code="divsalar.UNBLDPC.512.256.GF.256", GFq=256, method=7, snr=2.75, frames=10, bs_nm=4, bs_nc=3, bs_offset=0.2),
+    "f2_bstems_gf64_nm9": dict(code="BDS.576.288.GF.64", GFq=64, method=7, snr=2.0, frames=12, bs_nm=9, bs_nc=2, bs_factor=1.25, bs_offset=0.1),
+    "f2_bstems_gf16": dict(code="divsalar.UNBLDPC.128.64.GF.16", GFq=16, method=7, snr=2.5, frames=24, bs_nm=3, bs_nc=3, bs_offset=0.0),
 }
 
 
@@ -95,6 +98,7 @@ def run_case(name, cfg):
     oc = po.OracleCode(code)
     if method == 1: p0, p1, fac, ofs = 0, 0, 1.0, 0.0
     elif method == 2: p0, p1, fac, ofs = d["ems_nm"], d["ems_nc"], d["ems_factor"], d["ems_offset"]
+    elif method == 7: p0, p1, fac, ofs = d["bs_nm"], d["bs_nc"], d["bs_factor"], d["bs_offset"]
     else: p0, p1, fac, ofs = d["tems_nr"], d["tems_nc"], d["tems_factor"], d["tems_offset"]
     cons = None
     if d["nqam"] != 2:

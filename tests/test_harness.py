@@ -12,7 +12,7 @@ from conftest import ROOT, bundle, get_code_dict, load_golden
 from oracle import pyoracle as po
 from oracle.refprofile import profile_text
 
-CASES = ["cfg1_qspa_gf16", "cfg1_qspa_gf16_allzero", "cfg2_ems_gf64", "cfg3_tems_gf256", "cfg4_qspa_gf256_qam", "cfg5_tems_hbit256"]
+CASES = ["cfg1_qspa_gf16", "cfg1_qspa_gf16_allzero", "cfg2_ems_gf64", "cfg3_tems_gf256", "cfg4_qspa_gf256_qam", "cfg5_tems_hbit256", "f2_bstems_gf64_nm9"]
 
 
 def _workdir(tmp_path, meta, extra=None):
@@ -27,6 +27,8 @@ def _workdir(tmp_path, meta, extra=None):
         cfg.update(ems_nm=meta["p0"], ems_nc=meta["p1"], ems_factor=meta["factor"], ems_offset=meta["offset"])
     if meta["method"] == 4:
         cfg.update(tems_nr=meta["p0"], tems_nc=meta["p1"], tems_factor=meta["factor"], tems_offset=meta["offset"])
+    if meta["method"] == 7:
+        cfg.update(bs_nm=meta["p0"], bs_nc=meta["p1"], bs_factor=meta["factor"], bs_offset=meta["offset"])
     cfg.update(extra or {})
     (tmp_path / "prof.txt").write_text(profile_text(cfg))
     return cfg
