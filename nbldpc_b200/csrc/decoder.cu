@@ -52,6 +52,7 @@ template <typename T> struct IterParams {
 };
 
 #include "tems_warp.cuh"
+#include "ems_warp.cuh"
 
 // channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
 template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
@@ -271,6 +272,7 @@ struct nbl_decoder {
     float last_ms = 0; int last_launches = 0;
     size_t smem_iter = 0;
     bool warp_path = false;      // T-EMS n_c <= 2, dc <= 4, q >= 32: one warp per check row (tems_warp.cuh)
+    bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
 };
 
@@ -411,6 +413,13 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_REFERENCE) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
     const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
     d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
+    {
+        const bool pow2 = cfg->p0 >= 1 && (cfg->p0 & (cfg->p0 - 1)) == 0;
+        long long combos = 1;
+        for (int i = 0; i + 1 < code->max_dc; ++i) combos *= cfg->p0;
+        d->ems_warp_path = cfg->method == NBL_METHOD_EMS && desc_ok && q >= 32 && pow2 && cfg->p0 <= EW_MAXNM && cfg->p0 <= q &&
+                           combos <= EW_MAXCOMBOS && !getenv("NBLDPC_FORCE_GENERIC");
+    }
     if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
     *out = d;
     return NBL_OK;
@@ -487,8 +496,26 @@ template <typename T, int Q> static int launch_iterate_warp(nbl_decoder *d, cons
         return NBL_ERR_ARG;
     }
 }
+template <typename T, int Q, int DC, int DV> static int launch_iterate_ems_warp_dc(nbl_decoder *d, const IterParams<T> &P) {
+    auto kern = k_iterate_ems_warp<T, Q, DC, DV>;
+    constexpr size_t smem = EwSmem<T, Q>::bytes;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid((unsigned)((P.g.M + TW_WARPS - 1) / TW_WARPS), (unsigned)std::min(P.B, 65535), (unsigned)((P.B + 65534) / 65535));
+    kern<<<grid, 32 * TW_WARPS, smem, d->stream>>>(P);
+    CK(cudaGetLastError());
+    return NBL_OK;
+}
+template <typename T, int Q> static int launch_iterate_ems_warp(nbl_decoder *d, const IterParams<T> &P) {
+    if constexpr (Q >= 32) {
+        return d->warp_regular ? launch_iterate_ems_warp_dc<T, Q, TW_DC, TW_HOIST>(d, P) : launch_iterate_ems_warp_dc<T, Q, 0, 0>(d, P);
+    } else {
+        nbl_set_error("internal: warp path needs q >= 32");
+        return NBL_ERR_ARG;
+    }
+}
 template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const IterParams<T> &P) {
     if (d->warp_path) return launch_iterate_warp<T, Q>(d, P);
+    if (d->ems_warp_path) return launch_iterate_ems_warp<T, Q>(d, P);
     switch (d->cfg.method) {
         case NBL_METHOD_TEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_TEMS>(d, P);
         case NBL_METHOD_BSTEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_BSTEMS>(d, P);

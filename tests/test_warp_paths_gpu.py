@@ -138,3 +138,43 @@ def test_fp32_regular_and_generic_kernels_agree(code_files):
         outs.append(dec.decode(lch, want_post=True))
     for k in ("sym", "converged", "iterations", "post"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def _check_ems(code, tmp_path, lch, nm, nc, factor, offset, env=None, max_iter=6):
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    path = tmp_path / ("ems_%d_%d.txt" % (code["q"], code["N"]))
+    path.write_text(po.code_text(code))
+    oc = po.OracleCode(code)
+    want = [oc.decode(2, max_iter, nm, nc, factor, offset, l) for l in lch]
+    os.environ.update(env or {})
+    try:
+        dec = capi.Decoder(capi.Code.from_file(str(path)), 2, max_iter, nm, nc, factor, offset, precision=capi.PREC_F64, max_batch=len(lch))
+    finally:
+        for k in (env or {}):
+            os.environ.pop(k, None)
+    r = dec.decode(lch, want_post=True)
+    assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
+    assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
+    assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+    ref = np.stack([w[3] for w in want])
+    err = np.abs(r["post"] - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() < 1e-8, err.max()
+    return r
+
+
+@pytest.mark.parametrize("q", [32, 64, 128, 256])
+@pytest.mark.parametrize("regular", [True, False])
+def test_ems_warp_kernel_random_codes(q, regular, tmp_path):
+    """the EMS warp kernel (ems_warp.cuh): all vector widths, both degree specialisations, n_m / n_c / factor branches"""
+    rng = np.random.default_rng(2000 + q + regular)
+    code = _random_code(q, 8, rng, regular)
+    p = q.bit_length() - 1
+    lch = _frames(code, 8, 0.62 + 0.02 * p, rng)
+    r = _check_ems(code, tmp_path, lch, 8, 3, 1.0, 0.5)
+    assert len(set(r["iterations"].tolist())) > 1
+    _check_ems(code, tmp_path, lch[:4], 4, 2, 1.0, 0.25)
+    _check_ems(code, tmp_path, lch[:4], 8, 1, 1.3, 0.0)
+    _check_ems(code, tmp_path, lch[:4], 16, 2, 1.0, 0.5)
+    _check_ems(code, tmp_path, lch[:4], 6, 3, 1.0, 0.5)                              # n_m not a power of two: group kernel
+    _check_ems(code, tmp_path, lch[:4], 8, 3, 1.0, 0.5, env={"NBLDPC_WARP_GENERIC": "1"})
