@@ -135,8 +135,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) if (j == lj) key[j] = K(0);                  // taken
             }
-            const int sy = row_byte<VEC>(tf, xw);
-            if (lane == 0) { sval[d * EW_MAXNM + r] = key_value(kmax); ssyn[d * EW_MAXNM + r] = sy; }
+            if (lane == 0) { sval[d * EW_MAXNM + r] = key_value(kmax); ssyn[d * EW_MAXNM + r] = xw; }   // symbol; h * symbol below
         }
     };
 #pragma unroll
@@ -150,6 +149,11 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
         }
     }
     if (lane == 0 && syn_dec != 0) P.flag[f] = 1;
+    __syncwarp();
+    for (int i = lane; i < dcn * EW_MAXNM; i += 32) {               // symbols -> syndromes h_d * symbol, all lists at once
+        const int d = i / EW_MAXNM, r = i % EW_MAXNM;
+        if (r < nm) ssyn[i] = g.pfwd[(size_t)(e0 + d) * Q + ssyn[i]];
+    }
     unsigned long long tiv[TW_DC];                                  // the lane's own bytes of the rows h^-1 * x
 #pragma unroll
     for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + x0); }
@@ -195,20 +199,36 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
                 }
             }
             __syncwarp();
-            // conf(n_m, n_c): every combination of the n_m best of the other inputs with at most n_c non-best picks
+            // conf(n_m, n_c): every combination of the n_m best of the other inputs with at most n_c non-best picks.
+            // A lane takes prefixes (picks of all but the last input) and walks the last input's list; sums are formed
+            // left to right over the inputs.  A sum is never -0 (it starts from +0), so its key needs no normalisation.
+            {
+                const int last = no - 1;
+                const int prefixes = 1 << (lg * last);
+                const T *lv = sval + o[last < 0 ? 0 : last] * EW_MAXNM;
+                const int *ls = ssyn + o[last < 0 ? 0 : last] * EW_MAXNM;
 #pragma unroll 1
-            for (int c = lane; c < combos; c += 32) {
-                int dev = 0, sy = 0; T sum = T(0);
+                for (int c = lane; c < prefixes; c += 32) {
+                    int dev = 0, sy = 0; T sum = T(0);
 #pragma unroll
-                for (int mi = 0; mi < TW_DC - 1; ++mi) {
-                    if (mi < no) {
-                        const int k = (c >> (lg * mi)) & (nm - 1);
-                        dev += k != 0;
-                        sum = sum + sval[o[mi] * EW_MAXNM + k];
-                        sy ^= ssyn[o[mi] * EW_MAXNM + k];
+                    for (int mi = 0; mi < TW_DC - 2; ++mi) {
+                        if (mi < last) {
+                            const int k = (c >> (lg * mi)) & (nm - 1);
+                            dev += k != 0;
+                            sum = sum + sval[o[mi] * EW_MAXNM + k];
+                            sy ^= ssyn[o[mi] * EW_MAXNM + k];
+                        }
+                    }
+                    const int kend = dev < nc ? nm : (dev == nc ? 1 : 0);   // the last input may deviate only if dev < n_c
+#pragma unroll 1
+                    for (int k = 0; k < kend; ++k) {
+                        const T t = sum + lv[k];
+                        K key;
+                        if constexpr (sizeof(T) == 4) { const unsigned u = __float_as_uint(t); key = u ^ ((unsigned)((int)u >> 31) | 0x80000000u); }
+                        else key = order_key(t);
+                        atomicMax(&Bk[sy ^ ls[k]], key);
                     }
                 }
-                if (dev <= nc) atomicMax(&Bk[sy], order_key(sum));
             }
             __syncwarp();
             // merge, back to values (in place), then un-permute and correct
