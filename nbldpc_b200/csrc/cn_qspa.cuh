@@ -53,10 +53,107 @@ template <int Q> __device__ inline void group_wht(double *buf, int n, int x, int
     Grp<Q>::sync(gid);
 }
 
+// Q-point WHT of up to NV vectors held one element per thread in registers (v[i] = vector i at index x); unnormalised.
+// The stages inside a warp are shuffles; only the stages that cross warps (bit >= 32, q >= 64) go through shared memory
+// (scratch [NV][Q]).  Same butterflies in the same order as group_wht.
+template <int Q, int NV> __device__ inline void group_wht_reg(double (&v)[NV], int n, double *scratch, int x, int gid) {
+    const unsigned m = Grp<Q>::mask();
+#pragma unroll
+    for (int bit = 1; bit < (Q < 32 ? Q : 32); bit <<= 1) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (i < n) {
+                const double other = __shfl_xor_sync(m, v[i], bit);
+                v[i] = (x & bit) ? (other - v[i]) : (v[i] + other);
+            }
+    }
+#pragma unroll
+    for (int bit = 32; bit < Q; bit <<= 1) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) if (i < n) scratch[i * Q + x] = v[i];
+        Grp<Q>::sync(gid);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (i < n) {
+                const double other = scratch[i * Q + (x ^ bit)];
+                v[i] = (x & bit) ? (other - v[i]) : (v[i] + other);
+            }
+        Grp<Q>::sync(gid);
+    }
+}
+
+// exp / log of the probability-domain transform.  Parity mode (T = double): fp64 library routines.  Fast mode (T = float): the
+// messages are fp32 anyway, so fp32 ACCURACY (relative error ~1e-7) is enough -- but not fp32 RANGE: with 256-QAM the
+// inputs span hundreds of nats and the tails between e^-87 and e^-745 still steer the decoder (measured: an fp32-range
+// exp raises the FER of cfg4 from 0 to 3e-2 at 16 dB).  So: 2^n from the fp64 exponent field, 2^frac / log(mantissa)
+// from the fp32 special-function unit.
+template <typename T> __device__ inline double qspa_exp(double x);              // x <= 0
+template <> __device__ inline double qspa_exp<double>(double x) { return exp(x); }
+template <> __device__ inline double qspa_exp<float>(double x) {
+    const double t = x * 1.4426950408889634;                         // log2(e)
+    if (t < -1021.0) return 0.0;                                     // below the normal range: flush (fp64 exp would give a denormal)
+    const double fn = floor(t);
+    const float p = exp2f((float)(t - fn));                          // [1, 2)
+    const double d = (double)p;
+    return __hiloint2double(__double2hiint(d) + ((int)fn << 20), __double2loint(d));
+}
+template <typename T> __device__ inline double qspa_log(double x);              // x > 0, normal
+template <> __device__ inline double qspa_log<double>(double x) { return log(x); }
+template <> __device__ inline double qspa_log<float>(double x) {
+    const int hi = __double2hiint(x);
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
+    return (double)e * 0.6931471805599453 + (double)logf((float)m);
+}
+
+constexpr int QSPA_REG_DC = 8;      // check degrees served by the register / shuffle form (larger ones: shared-memory form)
+
 template <typename T, int Q>
 __device__ void cn_qspa(QspaSmem<T, Q> &S, const DevGraph &g, int gid, int x, int e0, int dcn,
                         T *__restrict__ c2v_out) {
-    // distributions in the syndrome domain, maximum normalised to 1 (the scale cancels in the LLR)
+    if (dcn <= QSPA_REG_DC) {
+        // distributions in the syndrome domain, maximum normalised to 1 (the scale cancels in the LLR); all inputs are
+        // transformed together, all dcn products are formed in registers and transformed back together.
+        double F[QSPA_REG_DC], R[QSPA_REG_DC];
+#pragma unroll
+        for (int d = 0; d < QSPA_REG_DC; ++d) {
+            F[d] = 1.0;
+            if (d < dcn) {
+                const double vmax = (double)S.V[d * Q + S.sdec[d]];
+                const int k = g.pinv[(size_t)(e0 + d) * Q + x];     // P[s] = p[h^-1 s]
+                F[d] = qspa_exp<T>((double)S.V[d * Q + k] - vmax);
+            }
+        }
+        group_wht_reg<Q, QSPA_REG_DC>(F, dcn, S.F, x, gid);
+#pragma unroll
+        for (int d = 0; d < QSPA_REG_DC; ++d) {
+            double r = 1.0;
+#pragma unroll
+            for (int l = 0; l < QSPA_REG_DC; ++l) if (l != d && l < dcn) r *= F[l];
+            R[d] = r;
+        }
+        group_wht_reg<Q, QSPA_REG_DC>(R, dcn, S.F, x, gid);
+#pragma unroll
+        for (int d = 0; d < QSPA_REG_DC; ++d) if (d < dcn) S.F[d * Q + x] = R[d];
+        Grp<Q>::sync(gid);
+#pragma unroll
+        for (int d = 0; d < QSPA_REG_DC; ++d) {
+            if (d < dcn) {
+                // The true inverse transform is a sum of non-negative products; entries whose probability is below the
+                // fp64 rounding noise of the transform (~2^-53 of the total) come out as noise of either sign, so they
+                // are floored there before the log (their LLR saturates near -37 relative to symbol 0).
+                const double tot = S.F[d * Q];
+                const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
+                T out = T(0);
+                if (x != 0) {
+                    const double a = S.F[d * Q + g.pfwd[(size_t)(e0 + d) * Q + x]];
+                    out = (T)(qspa_log<T>(a > fl ? a : fl) - qspa_log<T>(tot > fl ? tot : fl));
+                }
+                c2v_out[(size_t)(e0 + d) * Q + x] = out;
+            }
+        }
+        return;
+    }
     for (int d = 0; d < dcn; ++d) {
         const double vmax = (double)S.V[d * Q + S.sdec[d]];
         const int k = g.pinv[(size_t)(e0 + d) * Q + x];         // P[s] = p[h^-1 s]
@@ -68,9 +165,6 @@ __device__ void cn_qspa(QspaSmem<T, Q> &S, const DevGraph &g, int gid, int x, in
         for (int l = 0; l < dcn; ++l) if (l != d) r *= S.F[l * Q + x];
         S.R[x] = r;
         group_wht<Q>(S.R, 1, x, gid);
-        // The true inverse transform is a sum of non-negative products; entries whose probability is below
-        // the fp64 rounding noise of the transform (~2^-53 of the total) come out as noise of either sign,
-        // so they are floored there before the log (their LLR saturates near -37 relative to symbol 0).
         const double tot = S.R[0];
         const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
         T out = T(0);
