@@ -53,6 +53,7 @@ template <typename T> struct IterParams {
 
 #include "tems_warp.cuh"
 #include "ems_warp.cuh"
+#include "qspa_warp.cuh"
 
 // channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
 template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
@@ -272,6 +273,7 @@ struct nbl_decoder {
     float last_ms = 0; int last_launches = 0;
     size_t smem_iter = 0;
     bool warp_path = false;      // T-EMS n_c <= 2, dc <= 4, q >= 32: one warp per check row (tems_warp.cuh)
+    bool qspa_warp_path = false; // QSPA, dc <= 4, q >= 32: one warp per check row (qspa_warp.cuh)
     bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
 };
@@ -417,6 +419,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
         const bool pow2 = cfg->p0 >= 1 && (cfg->p0 & (cfg->p0 - 1)) == 0;
         long long combos = 1;
         for (int i = 0; i + 1 < code->max_dc; ++i) combos *= cfg->p0;
+        d->qspa_warp_path = cfg->method == NBL_METHOD_QSPA && desc_ok && q >= 32 && !getenv("NBLDPC_FORCE_GENERIC");
         d->ems_warp_path = cfg->method == NBL_METHOD_EMS && desc_ok && q >= 32 && pow2 && cfg->p0 <= EW_MAXNM && cfg->p0 <= q &&
                            combos <= EW_MAXCOMBOS && !getenv("NBLDPC_FORCE_GENERIC");
     }
@@ -513,9 +516,27 @@ template <typename T, int Q> static int launch_iterate_ems_warp(nbl_decoder *d, 
         return NBL_ERR_ARG;
     }
 }
+template <typename T, int Q, int DC, int DV> static int launch_iterate_qspa_warp_dc(nbl_decoder *d, const IterParams<T> &P) {
+    auto kern = k_iterate_qspa_warp<T, Q, DC, DV>;
+    constexpr size_t smem = QwSmem<T, Q>::bytes;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid((unsigned)((P.g.M + TW_WARPS - 1) / TW_WARPS), (unsigned)std::min(P.B, 65535), (unsigned)((P.B + 65534) / 65535));
+    kern<<<grid, 32 * TW_WARPS, smem, d->stream>>>(P);
+    CK(cudaGetLastError());
+    return NBL_OK;
+}
+template <typename T, int Q> static int launch_iterate_qspa_warp(nbl_decoder *d, const IterParams<T> &P) {
+    if constexpr (Q >= 32) {
+        return d->warp_regular ? launch_iterate_qspa_warp_dc<T, Q, TW_DC, TW_HOIST>(d, P) : launch_iterate_qspa_warp_dc<T, Q, 0, 0>(d, P);
+    } else {
+        nbl_set_error("internal: warp path needs q >= 32");
+        return NBL_ERR_ARG;
+    }
+}
 template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const IterParams<T> &P) {
     if (d->warp_path) return launch_iterate_warp<T, Q>(d, P);
     if (d->ems_warp_path) return launch_iterate_ems_warp<T, Q>(d, P);
+    if (d->qspa_warp_path) return launch_iterate_qspa_warp<T, Q>(d, P);
     switch (d->cfg.method) {
         case NBL_METHOD_TEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_TEMS>(d, P);
         case NBL_METHOD_BSTEMS: return launch_iterate_tqm<T, Q, NBL_METHOD_BSTEMS>(d, P);

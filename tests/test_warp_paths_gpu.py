@@ -178,3 +178,50 @@ def test_ems_warp_kernel_random_codes(q, regular, tmp_path):
     _check_ems(code, tmp_path, lch[:4], 16, 2, 1.0, 0.5)
     _check_ems(code, tmp_path, lch[:4], 6, 3, 1.0, 0.5)                              # n_m not a power of two: group kernel
     _check_ems(code, tmp_path, lch[:4], 8, 3, 1.0, 0.5, env={"NBLDPC_WARP_GENERIC": "1"})
+
+
+@pytest.mark.parametrize("q", [32, 64, 128])
+@pytest.mark.parametrize("regular", [True, False])
+def test_qspa_warp_kernel_random_codes(q, regular, tmp_path):
+    """the QSPA warp kernel (qspa_warp.cuh) against the oracle's log-domain box-plus: decisions and iteration counts
+    identical, posteriors to 1e-6 on the part above the transform's noise floor"""
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(3000 + q + regular)
+    code = _random_code(q, 6, rng, regular)
+    p = q.bit_length() - 1
+    lch = _frames(code, 5 if q < 128 else 3, 0.60 + 0.02 * p, rng)
+    path = tmp_path / ("qspa_%d.txt" % q)
+    path.write_text(po.code_text(code))
+    oc = po.OracleCode(code)
+    want = [oc.decode(1, 5, 0, 0, 1.0, 0.0, l) for l in lch]
+    dec = capi.Decoder(capi.Code.from_file(str(path)), 1, 5, precision=capi.PREC_F64, max_batch=len(lch))
+    r = dec.decode(lch, want_post=True)
+    assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
+    assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
+    assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+    ref = np.stack([w[3] for w in want])
+    sel = ref > -25.0
+    err = np.abs(r["post"] - ref)[sel] / np.maximum(np.abs(ref[sel]), 1.0)
+    assert err.max() < 1e-6, err.max()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_qspa_warp_and_group_kernels_are_bit_identical(precision, code_files):
+    """same butterflies in the same order: the warp form and the group form of the Walsh-Hadamard check node agree bit for bit"""
+    from conftest import constellation
+    from nbldpc_b200 import capi
+    z, meta = load_golden("cfg4_qspa_gf256_qam")
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)
+    outs = []
+    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
+        os.environ.update(env)
+        try:
+            dec = capi.Decoder(code, 1, meta["max_iter"], precision=precision, max_batch=len(lch))
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        outs.append(dec.decode(lch, want_post=True))
+    for k in ("sym", "converged", "iterations", "post"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
