@@ -103,7 +103,7 @@ template <> __device__ inline double qspa_log<float>(double x) {
     const int hi = __double2hiint(x);
     const int e = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
-    return (double)e * 0.6931471805599453 + (double)logf((float)m);
+    return (double)e * 0.6931471805599453 + (double)(__log2f((float)m) * 0.693147181f);   // lg2.approx: abs error < 3e-7
 }
 
 constexpr int QSPA_REG_DC = 8;      // check degrees served by the register / shuffle form (larger ones: shared-memory form)

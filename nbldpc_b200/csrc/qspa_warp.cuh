@@ -13,9 +13,11 @@
 namespace nbl {
 
 template <typename T, int Q> struct QwSmem {
-    // per-warp slab:  V [TW_DC][Q] v2c of the row (natural order);  R [Q] doubles: one output vector for the gather
-    static constexpr size_t off_r = (size_t)Q * TW_DC * sizeof(T);
-    static constexpr size_t raw = off_r + (size_t)Q * sizeof(double);
+    // per-warp slab:  V [TW_DC][Q] v2c of the row (natural order), later R [Q] doubles: one output vector for the gather;
+    //                 F [TW_DC][Q] doubles: the transformed inputs (split layout: a lane's own points, 16-byte pieces)
+    static constexpr size_t v_bytes = (size_t)Q * TW_DC * sizeof(T) < (size_t)Q * sizeof(double) ? (size_t)Q * sizeof(double) : (size_t)Q * TW_DC * sizeof(T);
+    static constexpr size_t off_f = v_bytes;
+    static constexpr size_t raw = off_f + (size_t)Q * TW_DC * sizeof(double);
     static constexpr size_t vec_align = (size_t)Q * sizeof(T) <= 1024 ? (size_t)Q * sizeof(T) : 16;
     static constexpr bool xor_gather = (size_t)Q * sizeof(T) <= 1024;
     static constexpr size_t bytes_per_warp = ((raw + vec_align - 1) / vec_align) * vec_align;
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_qspa_warp(const IterP
 
     unsigned char *slab = smem_raw + S::bytes_per_warp * warp;
     T *V = reinterpret_cast<T *>(slab);
-    double *R = reinterpret_cast<double *>(slab + S::off_r);
+    double *R = reinterpret_cast<double *>(slab);                  // reuses V once every input is transformed
+    double *Fs = reinterpret_cast<double *>(slab + S::off_f);
     const unsigned slab32 = smem_u32(slab);
 
     const int *rd = g.rowdesc + (size_t)row * 32;
@@ -149,51 +152,56 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_qspa_warp(const IterP
     for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(g.pinv + (size_t)(e0 + d) * Q + x0); }
     __syncwarp();
     // ---- check node: distributions in the syndrome domain, maximum normalised to 1, transformed -------------------------
-    double F[TW_DC][VEC];
+    // (loops over the edges are kept rolled: straight-line code for four transforms does not fit the instruction cache)
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        const int sd = (sdecw >> (8 * d)) & 255;
+        const double vmax = (double)V[d * Q + sd];
+        const G gv(slab32 + d * VB, 0);
+        unsigned long long tv = 0;
 #pragma unroll
-    for (int d = 0; d < TW_DC; ++d) {
-        if (DC || d < dcn) {
-            const int sd = (sdecw >> (8 * d)) & 255;
-            const double vmax = (double)V[d * Q + sd];
-            const G gv(slab32 + d * VB, 0);
+        for (int m = 0; m < TW_DC; ++m) if (m == d) tv = tiv[m];
+        double Fd[VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) F[d][j] = qspa_exp<T>((double)gv.at(tiv[d], j) - vmax);   // P[s] = p[h^-1 s]
-            warp_wht<VEC>(F[d], lane);
-        } else {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) F[d][j] = 1.0;
-        }
+        for (int j = 0; j < VEC; ++j) Fd[j] = qspa_exp<T>((double)gv.at(tv, j) - vmax);   // P[s] = p[h^-1 s]
+        warp_wht<VEC>(Fd, lane);
+        st_split<double, VEC>(Fs + d * Q, lane, Fd);
     }
+    __syncwarp();                                                  // V is dead from here on: R may overwrite it
     T *coutf = P.c2v_out + (size_t)f * g.E * Q + VEC * lane;
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        double r[VEC];
 #pragma unroll
-    for (int d = 0; d < TW_DC; ++d) {
-        if (DC || d < dcn) {
-            double r[VEC];
+        for (int j = 0; j < VEC; ++j) r[j] = 1.0;
+#pragma unroll 1
+        for (int l = 0; l < dcn; ++l) {
+            if (l == d) continue;
+            double Fl[VEC];
+            ld_split<double, VEC>(Fs + l * Q, lane, Fl);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                double p = 1.0;
-#pragma unroll
-                for (int l = 0; l < TW_DC; ++l) if (l != d && (DC || l < dcn)) p *= F[l][j];
-                r[j] = p;
-            }
-            warp_wht<VEC>(r, lane);
-            __syncwarp();                                           // the previous output's gathers are done
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) R[x0 + j] = r[j];
-            __syncwarp();
-            // floor at the fp64 noise of the transform (see cn_qspa.cuh), log, un-permute
-            const double tot = R[0];
-            const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
-            const double lt = qspa_log<T>(tot > fl ? tot : fl);
-            T out[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const double a = R[byte_of(tfw[d], j)];
-                out[j] = (T)(qspa_log<T>(a > fl ? a : fl) - lt);
-            }
-            if (lane == 0) out[0] = T(0);
-            st_vec<T, VEC>(coutf + (size_t)(e0 + d) * Q, out);
+            for (int j = 0; j < VEC; ++j) r[j] *= Fl[j];
         }
+        warp_wht<VEC>(r, lane);
+        __syncwarp();                                               // the previous output's gathers are done
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) R[x0 + j] = r[j];
+        __syncwarp();
+        // floor at the fp64 noise of the transform (see cn_qspa.cuh), log, un-permute
+        const double tot = R[0];
+        const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
+        const double lt = qspa_log<T>(tot > fl ? tot : fl);
+        unsigned long long tf = 0;
+#pragma unroll
+        for (int m = 0; m < TW_DC; ++m) if (m == d) tf = tfw[m];
+        T out[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const double a = R[byte_of(tf, j)];
+            out[j] = (T)(qspa_log<T>(a > fl ? a : fl) - lt);
+        }
+        if (lane == 0) out[0] = T(0);
+        st_vec<T, VEC>(coutf + (size_t)(e0 + d) * Q, out);
     }
 }
 
