@@ -46,6 +46,7 @@ typedef enum {
 #define NBL_TIES_AUTO 0
 #define NBL_TIES_FAST 1
 #define NBL_TIES_REFERENCE 2
+#define NBL_TIES_BITEXACT 3
 
 typedef struct nbl_code nbl_code;       /* GF(q) tables + parity-check graph, resident on one device */
 typedef struct nbl_decoder nbl_decoder; /* message workspace for up to max_batch frames + a stream    */
@@ -108,7 +109,13 @@ typedef struct {
                         enumeration keeps (NBLDPC.cpp:1892-1944) -- served by the group kernel;
                         NBL_TIES_FAST: first in the fast kernel's scan order (identical results whenever no
                         two configurations of a syndrome tie exactly, i.e. for continuous LLRs);
-                        NBL_TIES_AUTO (0): REFERENCE in the fp64 parity mode, FAST in the fp32 mode         */
+                        NBL_TIES_AUTO (0): REFERENCE in the fp64 parity mode, FAST in the fp32 mode;
+                        NBL_TIES_BITEXACT: a verification mode.  The reference forms a configuration's cost in ONE
+                        running sum (+= going down, -= coming back), whose rounding residue decides between
+                        configurations that are equal in exact arithmetic -- which T-EMS produces by itself
+                        after two iterations, because outputs are copies and sums of inputs.  This mode replays
+                        that search sequentially (one thread per check row) and so reproduces the reference's
+                        messages bit for bit in fp64 for any n_c; orders of magnitude slower                 */
 } nbl_decoder_config;
 
 /* stream: a cudaStream_t (as void*) to launch on, or NULL for a private non-blocking stream */

@@ -12,7 +12,7 @@ from . import build as _build
 
 METHOD_QSPA, METHOD_EMS, METHOD_TEMS, METHOD_BSTEMS = 1, 2, 4, 7
 PREC_F32, PREC_F64 = 0, 1
-TIES_AUTO, TIES_FAST, TIES_REFERENCE = 0, 1, 2
+TIES_AUTO, TIES_FAST, TIES_REFERENCE, TIES_BITEXACT = 0, 1, 2, 3
 NUM_COUNTERS = 8
 COUNTER_NAMES = ["frames", "err_frames", "err_syms", "err_bits", "converged", "undetected", "iterations", "reserved"]
 

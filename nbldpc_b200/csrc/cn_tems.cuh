@@ -125,10 +125,90 @@ __device__ void cn_tems_dp(TemsSmem<T, Q> &S, int gid, int x, int dcn, int nc, T
     Grp<Q>::sync(gid);
 }
 
+// Configuration search of tie mode BITEXACT: the reference's depth-first search itself, replayed by one thread.
+// TEMS_ConstructConf (NBLDPC.cpp:1892-1944) keeps ONE running cost that it adds to on the way down and subtracts from on
+// the way up, so after the first non-trivial pair of operations that sum carries a rounding residue (~1e-14 after a
+// GF(256) row) which every later configuration inherits.  T-EMS copies input values into its outputs, so from the
+// third iteration on rows meet configurations whose exact costs are equal (a + b against a stored a + b), and the
+// reference's choice among them depends on that residue.  Reproducing it needs the same additions in the same order:
+// strictly sequential, so this mode is for verification, not for throughput (one thread per check row walks the
+// ~1e5 leaves; the other q - 1 threads build the per-column candidate lists before and the output trellis after).
+template <typename T, int Q>
+__device__ void cn_tems_exact(TemsSmem<T, Q> &S, int gid, int x, int dcn, int nc, T *Tout) {
+    const T INF = Real<T>::inf();
+    uint8_t *list = S.bp;                                           // [maxdc][Q]: allowed eta of column d, ascending (0 first)
+    int *lens = reinterpret_cast<int *>(S.P);                       // [maxdc]
+    for (int d = 0; d < dcn; ++d) {
+        Grp<Q>::sync(gid);
+        const bool in = x == 0 || ((S.amask[x] >> d) & 1);
+        int len;
+        const int pos = group_prefix_count<Q>(in, x, gid, S.wtot, len);
+        if (in) list[d * Q + pos] = (uint8_t)x;
+        if (x == 0) lens[d] = len;
+    }
+    S.dW[x] = INF;
+    Grp<Q>::sync(gid);
+    if (x == 0) {
+        unsigned used[Q / 32 > 0 ? Q / 32 : 1];
+        for (int i = 0; i < (Q + 31) / 32; ++i) used[i] = 0;
+        int pos[16]; uint8_t cur[16];
+        T sum = T(0); int sym = 0, diff = 0, lvl = 0;
+        pos[0] = 0;
+        while (lvl >= 0) {
+            bool down = false;
+            if (lvl == dcn) {                                       // a leaf: strict '<' keeps the first of equal costs
+                if (sum < S.dW[sym]) {
+                    S.dW[sym] = sum;
+                    for (int d = 0; d < dcn; ++d) S.eta[d * Q + sym] = cur[d];
+                }
+            } else {
+                const uint8_t *lst = list + lvl * Q;
+                const int len = lens[lvl];
+                int p = pos[lvl];
+                while (p < len && ((used[lst[p] >> 5] >> (lst[p] & 31)) & 1)) ++p;
+                if (p < len) {
+                    const int e = lst[p];
+                    if (diff + (e != 0) <= nc) {                    // else: the reference leaves this column's loop
+                        if (e) { ++diff; used[e >> 5] |= 1u << (e & 31); }
+                        sym ^= e;
+                        sum = sum + S.dU[lvl * Q + e];
+                        cur[lvl] = (uint8_t)e; pos[lvl] = p;
+                        ++lvl;
+                        if (lvl < dcn) pos[lvl] = 0;
+                        down = true;
+                    }
+                }
+            }
+            if (!down) {                                            // back to the parent: undo its choice, next candidate
+                --lvl;
+                if (lvl >= 0) {
+                    const int e = cur[lvl];
+                    sym ^= e;
+                    sum = sum - S.dU[lvl * Q + e];
+                    if (e) { --diff; used[e >> 5] &= ~(1u << (e & 31)); }
+                    ++pos[lvl];
+                }
+            }
+        }
+    }
+    Grp<Q>::sync(gid);                                              // V is free from here on
+    for (int d = 0; d < dcn; ++d) Tout[d * Q + x] = INF;
+    Grp<Q>::sync(gid);
+    {
+        const T w = S.dW[x];
+        if (w < INF)
+            for (int d = 0; d < dcn; ++d) {
+                const int dev = S.eta[d * Q + x];
+                atomic_min_any(&Tout[d * Q + (x ^ dev)], w - S.dU[d * Q + dev]);   // the residue can make this negative
+            }
+    }
+    Grp<Q>::sync(gid);
+}
+
 // Inputs: S.V[d][x] (final v2c, slot 0 == 0) and S.sdec[d] = decide(V_d) for d < dcn, visible to the group.
 // Output: c2v_out[(e0+d)*Q + x] for d < dcn.
 template <typename T, int Q>
-__device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, int e0, int dcn, int nr, int nc,
+__device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, int e0, int dcn, int nr, int nc, bool bitexact,
                         T factor, T offset, T *__restrict__ c2v_out /* frame base, [E][Q] */) {
     const T INF = Real<T>::inf();
     // -- beta, syndrome of the most reliable symbols (TEMS_Get_Beta) --------------------------------
@@ -161,7 +241,9 @@ __device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, in
         S.P[x] = INF;
     }
     T *Tout = S.V;
-    if (nc <= 2) {
+    if (bitexact) {
+        cn_tems_exact<T, Q>(S, gid, x, dcn, nc, Tout);
+    } else if (nc <= 2) {
         // -- configuration search for n_c <= 2, in the reference's own visiting order ------------------------
         // TEMS_ConstructConf walks (eta_0, eta_1, ...) depth first, every eta_d ascending from 0, and keeps the first
         // configuration that attains the minimum (strict '<', NBLDPC.cpp:1897).  For one syndrome s that order is: the
@@ -250,21 +332,6 @@ __device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, in
 // no column used twice is a configuration; syndromes no subset reaches keep deltaW = +inf and take the fill-in value.
 // The subset enumeration is tiny (2^n_m leaves) and its running sum is formed by add / subtract exactly in the
 // reference's order, so one thread walks it with the same recursion; everything around it is data parallel.
-template <typename T> __device__ inline void atomic_min_any(T *addr, T v) {      // values of either sign (CAS loop)
-    using U = typename std::conditional<sizeof(T) == 4, unsigned, unsigned long long>::type;
-    U *a = reinterpret_cast<U *>(addr);
-    U old = *a;
-    while (true) {
-        T cur;
-        memcpy(&cur, &old, sizeof(T));
-        if (!(v < cur)) return;
-        U nv; memcpy(&nv, &v, sizeof(T));
-        const U prev = atomicCAS(a, old, nv);
-        if (prev == old) return;
-        old = prev;
-    }
-}
-
 template <typename T, int Q> struct BsWalk {
     TemsSmem<T, Q> &S;
     int nm, nc, dcn;

@@ -40,6 +40,7 @@ using namespace nbl;
 template <typename T> struct IterParams {
     DevGraph g;
     int B, iter, first, early_stop, method, p0, p1;
+    int bitexact;                       // T-EMS tie mode BITEXACT: the sequential replay of the reference's search
     T factor, offset, w_old, w_new;
     const T *lch;
     T *v2c;
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(Grp<Q>::THREADS) k_iterate(const IterParams<T>
     TemsSmem<T, Q> St; EmsSmem<T, Q> Se; QspaSmem<T, Q> Sq;
     T *V; int *sdec; RedScratch<typename Real<T>::key_t, Grp<Q>::WARPS, 2> *red;
     if (METHOD == NBL_METHOD_TEMS || METHOD == NBL_METHOD_BSTEMS) {
-        const int nca = METHOD == NBL_METHOD_BSTEMS ? 3 : P.p1;           // BS-TEMS uses the eta / back-pointer arrays of the n_c >= 3 layout
+        // BS-TEMS and the bit-exact T-EMS search use the eta / back-pointer arrays of the n_c >= 3 layout
+        const int nca = METHOD == NBL_METHOD_BSTEMS || (P.bitexact && P.p1 < 3) ? 3 : P.p1;
         per_group = TemsSmem<T, Q>::bytes(g.max_dc, nca);
         St.carve(smem_raw + per_group * gid, g.max_dc, nca); V = St.V; sdec = St.sdec; red = St.red;
     } else if (METHOD == NBL_METHOD_EMS) {
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(Grp<Q>::THREADS) k_iterate(const IterParams<T>
     Grp<Q>::sync(gid);
     // ---- step D: check node ---------------------------------------------------------------------------
     T *out = P.c2v_out + fE * Q;
-    if (METHOD == NBL_METHOD_TEMS) cn_tems<T, Q>(St, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, out);
+    if (METHOD == NBL_METHOD_TEMS) cn_tems<T, Q>(St, g, gid, x, e0, dcn, P.p0, P.p1, P.bitexact != 0, P.factor, P.offset, out);
     else if (METHOD == NBL_METHOD_BSTEMS) cn_bstems<T, Q>(St, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, phase, out);
     else if (METHOD == NBL_METHOD_EMS) cn_ems<T, Q>(Se, g, gid, x, e0, dcn, P.p0, P.p1, P.factor, P.offset, phase, out);
     else cn_qspa<T, Q>(Sq, g, gid, x, e0, dcn, out);
@@ -302,9 +304,10 @@ static size_t smem_for(const nbl_decoder *d, int Q) {
     const int mdc = d->code->max_dc;
     size_t per = 0;
     const bool f64 = d->cfg.precision == NBL_PREC_F64;
+    const int tnc = d->cfg.tie_mode == NBL_TIES_BITEXACT && d->cfg.p1 < 3 ? 3 : d->cfg.p1;
 #define PER(QQ)                                                                                              \
     if (Q == QQ) {                                                                                           \
-        if (d->cfg.method == NBL_METHOD_TEMS) per = f64 ? TemsSmem<double, QQ>::bytes(mdc, d->cfg.p1) : TemsSmem<float, QQ>::bytes(mdc, d->cfg.p1); \
+        if (d->cfg.method == NBL_METHOD_TEMS) per = f64 ? TemsSmem<double, QQ>::bytes(mdc, tnc) : TemsSmem<float, QQ>::bytes(mdc, tnc); \
         else if (d->cfg.method == NBL_METHOD_BSTEMS) per = f64 ? TemsSmem<double, QQ>::bytes(mdc, 3) : TemsSmem<float, QQ>::bytes(mdc, 3); \
         else if (d->cfg.method == NBL_METHOD_EMS) per = f64 ? EmsSmem<double, QQ>::bytes(mdc, d->cfg.p0, d->cfg.p1) : EmsSmem<float, QQ>::bytes(mdc, d->cfg.p0, d->cfg.p1); \
         else per = f64 ? QspaSmem<double, QQ>::bytes(mdc) : QspaSmem<float, QQ>::bytes(mdc);              \
@@ -336,6 +339,9 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     }
     if (cfg->method == NBL_METHOD_BSTEMS && (cfg->p0 < 1 || cfg->p0 > 16 || cfg->p0 > code->q - 1 || cfg->p1 < 1 || code->max_dc > 16)) {
         nbl_set_error("BS-TEMS needs 1 <= basic_set_Nm <= min(q - 1, 16), basic_set_Nc >= 1 and check degree <= 16"); return NBL_ERR_ARG;
+    }
+    if (cfg->method == NBL_METHOD_TEMS && cfg->tie_mode == NBL_TIES_BITEXACT && code->max_dc > 16) {
+        nbl_set_error("tie mode BITEXACT needs check degree <= 16"); return NBL_ERR_ARG;
     }
     if (cfg->max_iter < 1 || cfg->max_batch < 1) { nbl_set_error("nbl_decoder_create: max_iter and max_batch must be >= 1"); return NBL_ERR_ARG; }
     if (cfg->method == NBL_METHOD_EMS && (cfg->p0 < 1 || cfg->p0 > code->q || cfg->p1 < 1)) {
@@ -412,8 +418,8 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     d->it_ev.assign(2 * (size_t)cfg->max_iter, nullptr);
     for (auto &e : d->it_ev) if (cudaEventCreate(&e) != cudaSuccess) { nbl_set_error("cudaEventCreate failed"); return fail(NBL_ERR_CUDA); }
     d->smem_iter = smem_for(d, q);
-    if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_REFERENCE) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
-    const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
+    if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_BITEXACT) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
+    const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || cfg->tie_mode == NBL_TIES_BITEXACT || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
     d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
     {
         const bool pow2 = cfg->p0 >= 1 && (cfg->p0 & (cfg->p0 - 1)) == 0;
@@ -581,7 +587,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
         if (it < c.max_iter) {
             IterParams<T> P;
             P.g = d->g; P.B = B; P.iter = it; P.first = it == 1; P.early_stop = c.early_stop; P.method = c.method;
-            P.p0 = c.p0; P.p1 = c.p1; P.factor = (T)c.factor; P.offset = (T)c.offset; P.w_old = w_old; P.w_new = w_new;
+            P.p0 = c.p0; P.p1 = c.p1; P.bitexact = c.tie_mode == NBL_TIES_BITEXACT; P.factor = (T)c.factor; P.offset = (T)c.offset; P.w_old = w_old; P.w_new = w_new;
             P.lch = (const T *)d->d_lch; P.v2c = (T *)d->d_v2c; P.c2v_in = cin; P.c2v_out = cout;
             P.vdec = d->d_vdec; P.dec = d->d_dec; P.flag = d->d_flag; P.done = d->d_done;
             P.pfwd_sw = d->d_pfwd_sw; P.pinv_sw = d->d_pinv_sw;

@@ -170,6 +170,21 @@ __device__ inline void atomic_min_nonneg(double *addr, double v) {
     atomicMin((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
 }
 
+template <typename T> __device__ inline void atomic_min_any(T *addr, T v) {      // values of either sign (CAS loop)
+    using U = typename std::conditional<sizeof(T) == 4, unsigned, unsigned long long>::type;
+    U *a = reinterpret_cast<U *>(addr);
+    U old = *a;
+    while (true) {
+        T cur;
+        memcpy(&cur, &old, sizeof(T));
+        if (!(v < cur)) return;
+        U nv; memcpy(&nv, &v, sizeof(T));
+        const U prev = atomicCAS(a, old, nv);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace nbl

@@ -133,3 +133,19 @@ def test_noiseless_all_zero_returns_at_iteration_one(code_files):
         dec = capi.Decoder(code, method, 10, p0, p1, 1.0, 0.5, precision=capi.PREC_F32, max_batch=2)
         r = dec.decode(lch)
         assert (r["sym"] == 0).all() and (r["converged"] == 1).all() and (r["iterations"] == 1).all()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if load_golden(n)[1]["method"] == 4])
+def test_tems_bitexact_mode_reproduces_reference_posteriors_bit_for_bit(name, code_files):
+    """tie mode BITEXACT replays the reference's depth-first search with its one running sum, so the posteriors the
+    compiled reference dumped (tests/golden) must come back identical to the last bit, not merely within a tolerance."""
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    F = min(8, len(z["ret"]))
+    dec = _decoder(code, meta, capi.PREC_F64, F, tie_mode=capi.TIES_BITEXACT)
+    r = dec.decode(golden_lch(z, meta, F), want_post=True)
+    assert np.array_equal(r["converged"], z["ret"][:F].astype(np.int32))
+    assert np.array_equal(r["iterations"], z["iters"][:F].astype(np.int32))
+    assert np.array_equal(r["sym"], z["dec_sym"][:F].astype(np.int32))
+    assert np.array_equal(r["post"][:, :, z["lpost_idx"]], z["lpost_sample"][:F])

@@ -109,3 +109,32 @@ def test_64qam_front_end_with_punctured_symbols(code_files, tmp_path):
         r = dec.demap_decode(64, y, sigma, constellation=cs, punct=punct)
         assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
         assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+
+
+@pytest.mark.parametrize("q,regular,p0,p1,factor", [(16, True, 3, 2, 1.25), (32, False, 2, 2, 0.8), (64, True, 2, 3, 1.25), (16, False, 1, 3, 1.0)])
+def test_tems_bitexact_mode_on_inputs_no_scan_order_can_promise(q, regular, p0, p1, factor, tmp_path):
+    """Quantised samples with a non-dyadic scaling factor and punctured symbols with continuous samples: the costs of
+    tied configurations differ only by the rounding residue the reference's running sum carries at that point of its
+    search.  Tie mode BITEXACT replays the search, so posteriors must equal the oracle's bit for bit (the oracle is
+    pinned bit for bit to the compiled reference)."""
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(4300 + q + p0 + 7 * p1)
+    code = _random_code(q, 8, rng, regular)
+    p = q.bit_length() - 1
+    N = code["N"]
+    punct = [1, N // 2]
+    F = 6
+    y = 1.0 + 0.8 * rng.standard_normal((F, (N - len(punct)) * p))
+    y[F // 2:] = np.round(y[F // 2:] * 2) / 2                                     # half of the frames quantised
+    lch = np.stack([po.demap_bpsk(q, N, yy, 0.8, punct) for yy in y])
+    path = tmp_path / "bx.txt"
+    path.write_text(po.code_text(code))
+    oc = po.OracleCode(code)
+    want = [oc.decode(4, 7, p0, p1, factor, 0.25, l) for l in lch]
+    dec = capi.Decoder(capi.Code.from_file(str(path)), 4, 7, p0, p1, factor, 0.25, precision=capi.PREC_F64, max_batch=F,
+                       tie_mode=capi.TIES_BITEXACT)
+    r = dec.decode(lch, want_post=True)
+    assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
+    assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+    assert np.array_equal(r["post"], np.stack([w[3] for w in want]))
