@@ -121,6 +121,24 @@ typedef struct {
 /* stream: a cudaStream_t (as void*) to launch on, or NULL for a private non-blocking stream */
 int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const nbl_decoder_config *cfg, void *stream);
 void nbl_decoder_destroy(nbl_decoder *dec);
+
+/* Bit-level ordered-statistics post-processing of the frames the iterative decoder fails on -- replaces
+ * CNBLDPC::Decoding_OSD_bit (OSD.h:5-199) and the "if (OSD_Order >= 0 && !decode_correct)" tail of every Decoding_*
+ * (NBLDPC.cpp:770-775, 921-925, 1135-1139).  Fields are the reference profile's (Simulation.cpp:57-108):
+ * once enabled, nbl_decode_batch / nbl_demap_decode_* / nbl_simulate replace the symbols of every frame whose syndrome
+ * never became zero by the OSD decision; `converged` stays 0 for them, as the reference's return value does.           */
+typedef struct {
+    int order;            /* OSD_order 0..3 (number of simultaneously flipped reliable bits); < 0 switches OSD off      */
+    double factor;        /* OSD_factor: LLR_Sym_sum = factor * LLR_Sym_sum + L_post at every iteration                 */
+    int flag;             /* OSD_flag 1: start from the channel's hard decisions and rank by the channel LLRs           */
+    int crc_len;          /* crcLen: 8, 16 or 24 (the reference does not start with another value)           */
+    int crc_correct_len;  /* crc_correctLen: CRC parity rows stacked on H (0..crc_len)                                  */
+    int fix_matrepr;      /* 0: the reference's binary image of H, in which the block of the field element 1/alpha is
+                             all-zero because Mat.Repr is read one record short (GF.cpp:137); 1: correct one */
+} nbl_osd_config;
+int nbl_decoder_enable_osd(nbl_decoder *dec, const nbl_osd_config *cfg);
+/* decode method 6 (NBLDPC.cpp:625-627): OSD alone, from the channel LLRs, on every frame.  L_ch [B][N][q-1], out [B][N] */
+int nbl_osd_batch(nbl_decoder *dec, const double *L_ch, int B, int *out_sym);
 void *nbl_decoder_stream(nbl_decoder *dec);
 int nbl_decoder_sync(nbl_decoder *dec);
 

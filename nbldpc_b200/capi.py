@@ -33,6 +33,11 @@ class DecoderConfig(C.Structure):
                 ("device", C.c_int), ("tie_mode", C.c_int)]
 
 
+class OsdConfig(C.Structure):
+    _fields_ = [("order", C.c_int), ("factor", C.c_double), ("flag", C.c_int), ("crc_len", C.c_int),
+                ("crc_correct_len", C.c_int), ("fix_matrepr", C.c_int)]
+
+
 class SimConfig(C.Structure):
     _fields_ = [("ebn0_db", C.c_double), ("modulation", C.c_int), ("constellation", C.c_void_p), ("seed", C.c_uint64),
                 ("first_frame", C.c_uint64), ("frames", C.c_uint64), ("codewords", C.c_void_p), ("n_codewords", C.c_int),
@@ -68,6 +73,8 @@ def lib():
         L.nbl_decoder_stream.restype = vp
         L.nbl_decoder_sync.argtypes = [vp]
         L.nbl_decode_batch.argtypes = [vp, dp, C.c_int, vp, vp, vp, dp]
+        L.nbl_decoder_enable_osd.argtypes = [vp, C.POINTER(OsdConfig)]
+        L.nbl_osd_batch.argtypes = [vp, dp, C.c_int, vp]
         L.nbl_demap_bpsk.argtypes = [vp, dp, C.c_int, C.c_double, ip, C.c_int, dp]
         L.nbl_demap_qam.argtypes = [vp, dp, C.c_int, dp, C.c_double, ip, C.c_int, dp]
         L.nbl_demap_decode_batch.argtypes = [vp, C.c_int, dp, C.c_int, dp, C.c_double, ip, C.c_int, vp, vp, vp]
@@ -228,6 +235,20 @@ class Decoder:
         if want_post:
             out["post"] = post
         return out
+
+    def enable_osd(self, order, factor=1.0, flag=0, crc_len=8, crc_correct_len=0, fix_matrepr=0):
+        """OSD post-processing of failed frames in every later decode call (profile keys OSD_order, OSD_factor, OSD_flag,
+        crcLen, crc_correctLen); order < 0 switches it off again"""
+        cfg = OsdConfig(order, float(factor), flag, crc_len, crc_correct_len, fix_matrepr)
+        _check(lib().nbl_decoder_enable_osd(self._h, C.byref(cfg)))
+
+    def osd(self, L_ch):
+        """decode method 6: OSD alone on the channel LLRs [B][N][q-1] -> symbols [B][N]"""
+        N, q1 = self.code.N, self.code.q - 1
+        L_ch = np.ascontiguousarray(L_ch, np.float64).reshape(-1, N, q1)
+        sym = np.zeros((L_ch.shape[0], N), np.int32)
+        _check(lib().nbl_osd_batch(self._h, _ptr(L_ch), L_ch.shape[0], _ptr(sym)))
+        return sym
 
     def decode_raw(self, L_ch, B, out_sym, converged=None, iterations=None, L_post=None):
         """pointer-level call (numpy arrays, torch tensors or raw addresses; host or device)"""

@@ -17,6 +17,7 @@
 #include "cn_tems.cuh"
 #include "cn_ems.cuh"
 #include "cn_qspa.cuh"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,6 +56,7 @@ template <typename T> struct IterParams {
 #include "tems_warp.cuh"
 #include "ems_warp.cuh"
 #include "qspa_warp.cuh"
+#include "osd.cuh"
 
 // channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
 template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
@@ -278,6 +280,14 @@ struct nbl_decoder {
     bool qspa_warp_path = false; // QSPA, dc <= 4, q >= 32: one warp per check row (qspa_warp.cuh)
     bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
+    // OSD post-processing of failed frames (osd.cuh); off until nbl_decoder_enable_osd
+    bool osd_on = false;
+    nbl_osd_config osd_cfg{};
+    OsdDev osd{};
+    unsigned *d_osd_H0 = nullptr;
+    double *d_osd_sum = nullptr;                             // LLR_Sym_sum, the entries OSD reads: [max_batch][N p]
+    int *d_osd_status = nullptr;
+    size_t osd_smem = 0;
 };
 
 extern "C" int nbl_device_count(void) {
@@ -322,7 +332,7 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
     cudaSetDevice(d->cfg.device);
     void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_rowdesc, d->d_pfwd, d->d_pinv, d->d_pfwd_sw, d->d_pinv_sw, d->d_lch, d->d_v2c,
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
-                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg};
+                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg, d->d_osd_H0, d->d_osd_sum, d->d_osd_status};
     if (d->sim_enc) nbl_encoder_destroy(d->sim_enc);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : d->it_ev) if (e) cudaEventDestroy(e);
@@ -576,6 +586,8 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
     d->last_launches = 0; d->it_recorded = 0;
     CK(cudaMemsetAsync(d->d_flag, 0, (size_t)B * sizeof(int), d->stream));
     CK(cudaMemsetAsync(d->d_done, 0, (size_t)B, d->stream));
+    const bool osd_acc = d->osd_on && d->osd.order >= 0 && !d->osd.flag;
+    if (osd_acc) CK(cudaMemsetAsync(d->d_osd_sum, 0, (size_t)B * d->osd.nbit * sizeof(double), d->stream));
     CK(cudaEventRecord(d->ev0, d->stream));
     T w_old = 0, w_new = 1;
     if (c.method == NBL_METHOD_QSPA) { w_old = (T)0.5; w_new = (T)0.5; }          // NBLDPC.cpp:739
@@ -584,6 +596,12 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
         const T *cin = (const T *)d->d_c2v[(it - 1) & 1];
         T *cout = (T *)d->d_c2v[it & 1];
         int rc;
+        if (osd_acc) {                                              // LLR_Sym_sum += this iteration's posterior, frames still decoding
+            const long long n = (long long)B * d->osd.nbit;
+            k_osd_accumulate<T><<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>(d->g, B, it == 1, d->osd.alpha, d->d_done, (const T *)d->d_lch, cin, d->d_osd_sum);
+            CK(cudaGetLastError());
+            d->last_launches += 1;
+        }
         if (it < c.max_iter) {
             IterParams<T> P;
             P.g = d->g; P.B = B; P.iter = it; P.first = it == 1; P.early_stop = c.early_stop; P.method = c.method;
@@ -614,8 +632,87 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
             d->last_launches += 1;
         }
     }
+    if (d->osd_on && d->osd.order >= 0) {                           // NBLDPC.cpp:770-775, 921-925, 1135-1139: failed frames only
+        k_osd<T><<<B, 256, d->osd_smem, d->stream>>>(d->osd, q, d->d_conv, (const T *)d->d_lch, d->d_osd_sum, d->d_out, d->d_osd_status);
+        CK(cudaGetLastError());
+        d->last_launches += 1;
+    }
     CK(cudaEventRecord(d->ev1, d->stream));
     d->timing_pending = true;
+    return NBL_OK;
+}
+
+// ---- OSD set-up (NBLDPC.cpp:380-457, OSD.h:440-510) --------------------------------------------------------------------
+// CRC parity rows as the reference derives them: the (kbit - crc_len) x kbit band matrix of the CRC generator polynomial
+// is brought to systematic form by G_GaussEliminate_bit (rows are added, never swapped; OSD.h:257-313); row i of the
+// result says which message bits CRC bit (kbit - crc_rate + i) is the parity of.
+static std::vector<std::vector<uint8_t>> osd_crc_rows(int kbit, int crc_len, int crc_rate) {
+    const int gr = kbit - crc_len;
+    std::vector<std::vector<uint8_t>> G(gr, std::vector<uint8_t>(kbit, 0));
+    static const int t8[] = {0, 1, 4, 5, 7, 8}, t16[] = {0, 4, 11, 16}, t24[] = {0, 1, 18, 19, 23, 24};
+    const int *taps = crc_len == 8 ? t8 : crc_len == 16 ? t16 : t24;
+    const int ntap = crc_len == 16 ? 4 : 6;
+    for (int i = 0; i < gr; ++i) for (int t = 0; t < ntap; ++t) G[i][i + taps[t]] = 1;
+    // the band matrix has ones on its diagonal, so every pivot is in place: forward and backward elimination only
+    for (int r = 0; r < gr; ++r)
+        for (int up = r + 1; up < gr; ++up)
+            if (G[up][r]) for (int i = 0; i < kbit; ++i) G[up][i] ^= G[r][i];
+    for (int r = gr - 1; r > 0; --r)
+        for (int up = r - 1; up >= 0; --up)
+            if (G[up][r]) for (int i = 0; i < kbit; ++i) G[up][i] ^= G[r][i];
+    std::vector<std::vector<uint8_t>> rows(crc_rate, std::vector<uint8_t>(kbit, 0));
+    for (int i = 0; i < crc_rate; ++i) {
+        rows[i][i + kbit - crc_rate] = 1;
+        for (int j = 0; j < gr; ++j) rows[i][j] = G[j][kbit - crc_rate + i];
+    }
+    return rows;
+}
+
+extern "C" int nbl_decoder_enable_osd(nbl_decoder *d, const nbl_osd_config *cfg) {
+    if (!d || !cfg) { nbl_set_error("nbl_decoder_enable_osd: null argument"); return NBL_ERR_ARG; }
+    if (cfg->order < 0) { d->osd_on = false; return NBL_OK; }
+    if (cfg->order > 3) { nbl_set_error("OSD order must be 0..3"); return NBL_ERR_ARG; }
+    if (cfg->crc_len != 8 && cfg->crc_len != 16 && cfg->crc_len != 24) {
+        nbl_set_error("OSD needs crcLen 8, 16 or 24 (the reference's CRC matrix set-up does not terminate otherwise, OSD.h:472-499)"); return NBL_ERR_ARG;
+    }
+    const nbl_code *c = d->code;
+    const int P = c->p, nbit = c->N * P, mbit = c->M * P, kbit = nbit - mbit, R = cfg->crc_correct_len + mbit, W = (nbit + 31) / 32;
+    if (cfg->crc_correct_len < 0 || cfg->crc_correct_len > cfg->crc_len || kbit <= cfg->crc_len) { nbl_set_error("OSD: bad crc_correct_len"); return NBL_ERR_ARG; }
+    if (nbit > 2048) { nbl_set_error("OSD: more than 2048 code bits"); return NBL_ERR_ARG; }
+    const size_t smem = OsdSmem::bytes(nbit, kbit, R, W);
+    if (smem > 200 * 1024) { nbl_set_error("OSD: the bit matrices of this code do not fit into shared memory"); return NBL_ERR_ARG; }
+    CK(cudaSetDevice(d->cfg.device));
+    std::vector<unsigned> H0((size_t)R * W, 0u);
+    auto setbit = [&](int r, int col) { H0[(size_t)r * W + (col >> 5)] |= 1u << (col & 31); };
+    const auto crc = osd_crc_rows(kbit, cfg->crc_len, cfg->crc_correct_len);
+    for (int i = 0; i < cfg->crc_correct_len; ++i) for (int j = 0; j < kbit; ++j) if (crc[i][j]) setbit(i, j);
+    // binary image of H: block (check, variable) = matrix of the coefficient, entry [k][l] = bit k of g * x^l
+    // (NBLDPC.cpp:416-430); the reference's table lacks the matrix of 1/alpha (GF.cpp:137)
+    const int dead = cfg->fix_matrepr ? -1 : c->inv[2];
+    for (int r = 0; r < c->M; ++r)
+        for (int e = c->chk_ptr[r]; e < c->chk_ptr[r + 1]; ++e) {
+            const int v = c->chk_var[e], g = c->chk_coef[e];
+            if (g == dead) continue;
+            for (int l = 0; l < P; ++l) {
+                const int prod = c->mul[(size_t)g * c->q + (1 << l)];
+                for (int k = 0; k < P; ++k) if ((prod >> k) & 1) setbit(cfg->crc_correct_len + P * r + k, P * v + l);
+            }
+        }
+    if (d->d_osd_H0) { cudaFree(d->d_osd_H0); d->d_osd_H0 = nullptr; }
+    if (d->d_osd_sum) { cudaFree(d->d_osd_sum); d->d_osd_sum = nullptr; }
+    int rc;
+    if ((rc = upload(&d->d_osd_H0, H0))) return rc;
+    CK(cudaMalloc((void **)&d->d_osd_sum, (size_t)d->cfg.max_batch * nbit * sizeof(double)));
+    if (!d->d_osd_status) { CK(cudaMalloc((void **)&d->d_osd_status, sizeof(int))); CK(cudaMemset(d->d_osd_status, 0, sizeof(int))); }
+    CK(cudaFuncSetAttribute(k_osd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_osd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    d->osd_cfg = *cfg;
+    d->osd.order = cfg->order; d->osd.flag = cfg->flag ? 1 : 0; d->osd.nbit = nbit; d->osd.kbit = kbit; d->osd.R = R; d->osd.W = W;
+    d->osd.p = P; d->osd.N = c->N; d->osd.alpha = cfg->factor; d->osd.H0 = d->d_osd_H0;
+    // compute_min_distance_bit's own bit length: multiplication first, then truncation (OSD.h:420) -- see osd.cuh
+    d->osd.dist_len = (int)(c->N * std::log((double)c->q) / std::log(2.0));
+    d->osd_smem = smem;
+    d->osd_on = true;
     return NBL_OK;
 }
 
@@ -662,6 +759,37 @@ extern "C" int nbl_decode_batch(nbl_decoder *d, const double *L_ch, int B, int *
     else k_convert_lch<float><<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(src, (float *)d->d_lch, nvec, (int)q);
     CK(cudaGetLastError());
     return decode_common(d, B, out_sym, converged, iterations, L_post);
+}
+
+// Decoding_OSD_bit with flag 1 (decode method 6, NBLDPC.cpp:625-627): OSD alone on the channel LLRs, every frame
+extern "C" int nbl_osd_batch(nbl_decoder *d, const double *L_ch, int B, int *out_sym) {
+    if (!d || !L_ch || !out_sym) { nbl_set_error("nbl_osd_batch: null argument"); return NBL_ERR_ARG; }
+    if (!d->osd_on) { nbl_set_error("nbl_osd_batch: call nbl_decoder_enable_osd first"); return NBL_ERR_ARG; }
+    if (B < 0 || B > d->cfg.max_batch) { nbl_set_error("nbl_osd_batch: B exceeds max_batch"); return NBL_ERR_ARG; }
+    if (B == 0) return NBL_OK;
+    CK(cudaSetDevice(d->cfg.device));
+    const size_t nvec = (size_t)B * d->g.N, q = d->g.q;
+    const double *src = L_ch;
+    int rc;
+    if (!is_device_ptr(L_ch)) {
+        if ((rc = ensure_stage(d, nvec * (q - 1) * sizeof(double)))) return rc;
+        CK(cudaMemcpyAsync(d->d_stage, L_ch, nvec * (q - 1) * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        src = d->d_stage;
+    }
+    const size_t tot = nvec * q;
+    OsdDev o = d->osd;
+    o.flag = 1;
+    if (d->cfg.precision == NBL_PREC_F64) {
+        k_convert_lch<double><<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(src, (double *)d->d_lch, nvec, (int)q);
+        k_osd<double><<<B, 256, d->osd_smem, d->stream>>>(o, (int)q, nullptr, (const double *)d->d_lch, d->d_osd_sum, d->d_out, d->d_osd_status);
+    } else {
+        k_convert_lch<float><<<(unsigned)((tot + 255) / 256), 256, 0, d->stream>>>(src, (float *)d->d_lch, nvec, (int)q);
+        k_osd<float><<<B, 256, d->osd_smem, d->stream>>>(o, (int)q, nullptr, (const float *)d->d_lch, d->d_osd_sum, d->d_out, d->d_osd_status);
+    }
+    CK(cudaGetLastError());
+    if ((rc = give_ints(d, out_sym, d->d_out, nvec))) return rc;
+    if (!is_device_ptr(out_sym)) CK(cudaStreamSynchronize(d->stream));
+    return NBL_OK;
 }
 
 // ---- front end -------------------------------------------------------------------------------------

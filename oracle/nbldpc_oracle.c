@@ -580,8 +580,220 @@ static void *alloc2(int rows, int cols, size_t esz, void ***index) {
     return blk;
 }
 
-int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, double factor, double offset,
-               const double *L_ch, int *out, double *L_post, int *iters) {
+/* ------------------------------------------------- bit-level OSD post-processing (OSD.h; set-up NBLDPC.cpp:380-457) */
+struct orc_osd {
+    const orc_code *c;
+    int nbit, mbit, kbit, crc_len, crc_rate, R;
+    int *H0;                              /* [R][nbit]: CRC rows on top of the binary image of H (OSD.h:44-59) */
+    int *H;                               /* [R][nbit] work copy */
+    int *order;                           /* ReliableSeri_BIT */
+    int *info, *tmp, *best;               /* infor_record_bit, OSD_temp_out_bit, near_optimal_bit */
+    double *lbit;                         /* L_ch_bit */
+    int min_distance;                     /* an int in the reference (NBLDPC.h:127): the best distance is stored TRUNCATED */
+};
+
+/* G_GaussEliminate_bit, OSD.h:257-313 (rows ^= instead of swaps; a dependent column is rotated to the end) */
+static void gauss_g(int *Mx, int cols, int rows, int *order) {
+    for (int row = 0; row < rows; ++row) {
+        int col = order[row];
+        if (Mx[row * cols + col] == 0) {
+            int exchanged = 0;
+            for (int up = row + 1; up < rows; ++up)
+                if (Mx[up * cols + col] != 0) {
+                    for (int i = 0; i < cols; ++i) Mx[row * cols + i] ^= Mx[up * cols + i];
+                    exchanged = 1;
+                    break;
+                }
+            if (!exchanged) {
+                int flag = row;
+                row--;
+                for (int i = flag; i < cols - 1; ++i) { int t = order[i]; order[i] = order[i + 1]; order[i + 1] = t; }
+            }
+        }
+        for (int up = row + 1; up < rows; ++up)
+            if (up >= 0 && Mx[up * cols + col] != 0 && row >= 0)
+                for (int i = 0; i < cols; ++i) Mx[up * cols + i] ^= Mx[row * cols + i];
+    }
+    for (int row = rows - 1; row > 0; --row)
+        for (int up = row - 1; up >= 0; --up)
+            if (Mx[up * cols + order[row]] == 1)
+                for (int i = 0; i < cols; ++i) Mx[up * cols + i] ^= Mx[row * cols + i];
+}
+
+/* H_GaussEliminate_bit, OSD.h:326-384: pivots from the bottom row / the LEAST reliable position upwards; a column with
+ * no pivot left is rotated to the front of the order */
+static void gauss_h(int *Mx, int cols, int rows, int *order) {
+    for (int row = rows - 1; row >= 0; --row) {
+        int nt = row + cols - rows;
+        int col = order[nt];
+        if (Mx[row * cols + col] == 0) {
+            int exchanged = 0;
+            for (int up = row - 1; up >= 0; --up)
+                if (Mx[up * cols + col] != 0) {
+                    for (int i = 0; i < cols; ++i) Mx[row * cols + i] ^= Mx[up * cols + i];
+                    exchanged = 1;
+                    break;
+                }
+            if (!exchanged) {
+                row++;
+                for (int i = nt - 1; i >= 0; --i) { int t = order[i]; order[i] = order[i + 1]; order[i + 1] = t; }
+            }
+        }
+        if (row < rows)                   /* (after row++ the column is zero in every row above: nothing to clear) */
+            for (int up = row - 1; up >= 0; --up)
+                if (Mx[up * cols + col] != 0)
+                    for (int i = 0; i < cols; ++i) Mx[up * cols + i] ^= Mx[row * cols + i];
+    }
+    for (int i = 0; i < rows; ++i)
+        for (int j = i + 1; j < rows; ++j) {
+            int pos = order[cols - rows + i];
+            if (Mx[j * cols + pos] == 1)
+                for (int k = 0; k < cols; ++k) Mx[j * cols + k] ^= Mx[i * cols + k];
+        }
+}
+
+orc_osd *orc_osd_create(const orc_code *c, int crc_len, int crc_rate, int fix_matrepr) {
+    if (crc_len != 8 && crc_len != 16 && crc_len != 24) return NULL;      /* the reference hangs otherwise (OSD.h:472-499) */
+    orc_osd *o = calloc(1, sizeof *o);
+    int P = c->p;
+    o->c = c; o->nbit = c->N * P; o->mbit = c->M * P; o->kbit = o->nbit - o->mbit;
+    o->crc_len = crc_len; o->crc_rate = crc_rate; o->R = crc_rate + o->mbit;
+    if (crc_rate < 0 || crc_rate > crc_len || o->kbit <= crc_len) { free(o); return NULL; }
+    int nb = o->nbit, kb = o->kbit;
+    o->H0 = calloc((size_t)o->R * nb, sizeof(int)); o->H = calloc((size_t)o->R * nb, sizeof(int));
+    o->order = calloc(nb, sizeof(int)); o->info = calloc(nb, sizeof(int)); o->tmp = calloc(nb, sizeof(int));
+    o->best = calloc(nb, sizeof(int)); o->lbit = calloc(nb, sizeof(double));
+    /* H_origin_bit (NBLDPC.cpp:416-430): block (chk, var) = the matrix representation of the coefficient,
+     * ValueMatric[l][k] = bit k of g * x^l.  The reference's Mat.Repr reader stops one record early (GF.cpp:137), so
+     * the block of alpha^(q-2) = 1/alpha stays all-zero there. */
+    int dead = fix_matrepr ? -1 : c->inv[2];
+    for (int i = 0; i < c->N; ++i)
+        for (int j = 0; j < c->vdeg[i]; ++j) {
+            int chk = c->vlink[i * c->maxdv + j], g = c->vcoef[i * c->maxdv + j];
+            for (int k = 0; k < P; ++k)
+                for (int l = 0; l < P; ++l)
+                    o->H0[(size_t)(crc_rate + P * chk + k) * nb + P * i + l] = g == dead ? 0 : (MUL(c, g, 1 << l) >> k) & 1;
+        }
+    /* CRCMatrixGen (OSD.h:472-510) */
+    int gr = kb - crc_len;
+    int *G = calloc((size_t)gr * kb, sizeof(int)), *seri = calloc(kb, sizeof(int));
+    static const int t8[] = {0, 1, 4, 5, 7, 8}, t16[] = {0, 4, 11, 16}, t24[] = {0, 1, 18, 19, 23, 24};
+    const int *taps = crc_len == 8 ? t8 : crc_len == 16 ? t16 : t24;
+    int ntap = crc_len == 16 ? 4 : 6;
+    for (int i = 0; i < gr; ++i) for (int t = 0; t < ntap; ++t) G[(size_t)i * kb + i + taps[t]] = 1;
+    for (int i = 0; i < kb; ++i) seri[i] = i;
+    gauss_g(G, kb, gr, seri);
+    for (int i = 0; i < crc_rate; ++i) {
+        o->H0[(size_t)i * nb + i + kb - crc_rate] = 1;
+        for (int j = 0; j < gr; ++j) o->H0[(size_t)i * nb + j] = G[(size_t)j * kb + kb - crc_rate + i];
+    }
+    free(G); free(seri);
+    return o;
+}
+
+void orc_osd_destroy(orc_osd *o) {
+    if (!o) return;
+    free(o->H0); free(o->H); free(o->order); free(o->info); free(o->tmp); free(o->best); free(o->lbit); free(o);
+}
+
+static void osd_encode(orc_osd *o) {                       /* OSD_Encode_bit, OSD.h:386-401 */
+    int nb = o->nbit, dep = nb - o->R;
+    memcpy(o->tmp, o->info, sizeof(int) * nb);
+    for (int i = 0; i < o->R; ++i) {
+        int t = 0;
+        for (int j = 0; j < dep; ++j) t ^= o->H[(size_t)i * nb + o->order[j]] * o->tmp[o->order[j]];
+        o->tmp[o->order[dep + i]] = t;
+    }
+}
+static void osd_distance(orc_osd *o) {                     /* compute_min_distance_bit, OSD.h:403-420 */
+    /* The function recomputes the bit length as int(CodeLen * log(GFq) / log(2)) -- multiplication first -- which
+     * rounds down to N p - 1 for some (N, q), e.g. 96 * log(64) / log(2) = 575.9999999999999: the last bit is then
+     * neither counted in the distance nor copied into the best candidate. */
+    int len = (int)(o->c->N * log((double)o->c->q) / log(2.0));
+    double d = 0;
+    for (int i = 0; i < len; ++i)
+        if ((o->lbit[i] < 0 && o->tmp[i] == 1) || (o->lbit[i] > 0 && o->tmp[i] == 0)) d = d + fabs(o->lbit[i]);
+    if (d < o->min_distance) { memcpy(o->best, o->tmp, sizeof(int) * len); o->min_distance = (int)d; }
+}
+
+typedef struct { double key; int idx; } osd_key;
+static int osd_key_cmp(const void *a, const void *b) {      /* descending reliability; equal keys: the reference's
+                                                               std::sort leaves their order unspecified, here by index */
+    const osd_key *x = a, *y = b;
+    if (x->key > y->key) return -1;
+    if (x->key < y->key) return 1;
+    return x->idx - y->idx;
+}
+
+/* Decoding_OSD_bit, OSD.h:5-199.  sym: in = the iterative decoder's decisions (ignored when flag != 0),
+ * out = the OSD decision.  sym_sum = LLR_Sym_sum [N][q-1] (ignored when flag != 0: the channel LLRs are used). */
+void orc_osd_run(orc_osd *o, int order, int flag, const double *L_ch, const double *sym_sum, int *sym) {
+    const orc_code *c = o->c; int P = c->p, q1 = c->q - 1, nb = o->nbit, kb = o->kbit;
+    const double *rel = flag ? L_ch : sym_sum;
+    for (int i = 0; i < c->N; ++i) {
+        int rec = flag ? decide(L_ch + (size_t)i * q1, c->q) : sym[i];
+        for (int j = 0; j < P; ++j) {
+            o->info[i * P + j] = (rec >> j) & 1;
+            o->best[i * P + j] = (rec >> j) & 1;
+            o->lbit[i * P + j] = L_ch[(size_t)i * q1 + (1 << j) - 1];
+        }
+    }
+    o->min_distance = 1000000;
+    osd_key *keys = malloc(sizeof(osd_key) * nb);           /* OSD_permute, OSD.h:202-231 */
+    for (int j = 0; j < c->N; ++j)
+        for (int k = 0; k < P; ++k) { keys[j * P + k].key = fabs(rel[(size_t)j * q1 + (1 << k) - 1]); keys[j * P + k].idx = j * P + k; }
+    qsort(keys, nb, sizeof(osd_key), osd_key_cmp);
+    for (int i = 0; i < nb; ++i) o->order[i] = keys[i].idx;
+    free(keys);
+    memcpy(o->H, o->H0, sizeof(int) * (size_t)o->R * nb);
+    gauss_h(o->H, nb, o->R, o->order);
+    osd_encode(o); osd_distance(o);
+    if (order >= 1)
+        for (int i = 0; i < kb; ++i) {
+            o->info[o->order[i]] ^= 1;
+            osd_encode(o); osd_distance(o);
+            o->info[o->order[i]] ^= 1;
+        }
+    if (order >= 2)
+        for (int i = 0; i < kb; ++i) {
+            o->info[o->order[i]] ^= 1;
+            for (int j = i + 1; j < kb; ++j) {
+                o->info[o->order[j]] ^= 1;
+                osd_encode(o); osd_distance(o);
+                o->info[o->order[j]] ^= 1;
+            }
+            o->info[o->order[i]] ^= 1;
+        }
+    if (order >= 3)
+        for (int i = 0; i < kb; ++i) {
+            o->info[o->order[i]] ^= 1;
+            for (int j = i + 1; j < kb; ++j) {
+                o->info[o->order[j]] ^= 1;
+                for (int k = j + 1; k < kb; ++k) {
+                    o->info[o->order[k]] ^= 1;
+                    osd_encode(o); osd_distance(o);
+                    o->info[o->order[k]] ^= 1;
+                }
+                o->info[o->order[j]] ^= 1;
+            }
+            o->info[o->order[i]] ^= 1;
+        }
+    for (int i = 0; i < c->N; ++i) {
+        int v = 0;
+        for (int j = 0; j < P; ++j) v = 2 * v + o->best[i * P + P - 1 - j];
+        sym[i] = v;
+    }
+}
+
+/* The ordering the last orc_osd_run ended with (ReliableSeri_BIT after the elimination) and its best distance */
+void orc_osd_last(const orc_osd *o, int *order, int *min_distance) {
+    if (order) memcpy(order, o->order, sizeof(int) * o->nbit);
+    if (min_distance) *min_distance = o->min_distance;
+}
+
+int orc_decode_osd(const orc_code *c, int method, int max_iter, int p0, int p1, double factor, double offset,
+                   const double *L_ch, int *out, double *L_post, int *iters,
+                   orc_osd *osd, int osd_order, double osd_alpha, int osd_flag) {
     int q = c->q, q1 = q - 1;
     state s; s.c = c;
     s.v2c = malloc(sizeof(double) * c->N * c->maxdv * q1);
@@ -621,9 +833,13 @@ int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, doub
         LLV = calloc(q, sizeof(double));
     }
 
+    /* LLR_Sym_sum: every decoder accumulates alpha * sum + L_post at each tentative decision (NBLDPC.cpp:687, 820, 989, 1205) */
+    double *sym_sum = osd ? calloc((size_t)c->N * q1, sizeof(double)) : NULL;
     int ok = 0, it = 0;
     while (it++ < max_iter) {
         ok = posterior_and_syndrome(&s, L_ch, L_post, out);
+        if (sym_sum)
+            for (size_t i = 0; i < (size_t)c->N * q1; ++i) sym_sum[i] = osd_alpha * sym_sum[i] + L_post[i];
         if (ok) break;
         if (method == 1) { var_to_check(&s, L_post, 0.5, 0.5); cn_qspa(&s, &b); }
         else if (method == 2) { var_to_check(&s, L_post, 0, 1); cn_ems(&s, &e, factor, offset); }
@@ -631,6 +847,8 @@ int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, doub
         else { var_to_check(&s, L_post, 0.25, 0.75); cn_tems(&s, &t, factor, offset); }
     }
     *iters = ok ? it : max_iter;
+    if (osd && osd_order >= 0 && !ok) orc_osd_run(osd, osd_order, osd_flag, L_ch, sym_sum, out);   /* NBLDPC.cpp:770, 921, 1135 */
+    free(sym_sum);
 
     free(s.v2c); free(s.c2v); free(s.tmp);
     free(b.sigma); free(b.rho); free(b.llrv);
@@ -640,4 +858,9 @@ int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, doub
     free(bs.bq); free(bs.bcol); free(bs.bL); free(bs.col_sel); free(bs.order); free(bs.avail); free(bs.R); free(LLV);
     for (int i = 0; i < nblk; ++i) free(blk[i]);
     return ok;
+}
+
+int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, double factor, double offset,
+               const double *L_ch, int *out, double *L_post, int *iters) {
+    return orc_decode_osd(c, method, max_iter, p0, p1, factor, offset, L_ch, out, L_post, iters, NULL, -1, 1.0, 0);
 }

@@ -41,6 +41,22 @@ void orc_demap_qam(int q, int N, const double *y, const double *constellation, d
 int orc_decode(const orc_code *c, int method, int max_iter, int p0, int p1, double factor, double offset,
                const double *L_ch, int *out_sym, double *L_post, int *iters);
 
+/* Bit-level ordered-statistics post-processing (OSD.h:5-199; matrices NBLDPC.cpp:380-457, OSD.h:440-510).
+ * crc_len in {8, 16, 24} (anything else hangs the reference, OSD.h:472-499), crc_rate = crc_correctLen = number of CRC
+ * parity rows stacked on H.  fix_matrepr = 0 reproduces the reference's binary image (the block of 1/alpha is zero,
+ * GF.cpp:137), 1 uses the correct one. */
+typedef struct orc_osd orc_osd;
+orc_osd *orc_osd_create(const orc_code *c, int crc_len, int crc_rate, int fix_matrepr);
+void orc_osd_destroy(orc_osd *o);
+/* Decoding_OSD_bit.  sym [N]: in = decisions of the iterative decoder (ignored when flag), out = OSD decisions;
+ * sym_sum = LLR_Sym_sum [N][q-1] (ignored when flag: the channel LLRs rank the bits). */
+void orc_osd_run(orc_osd *o, int order, int flag, const double *L_ch, const double *sym_sum, int *sym);
+void orc_osd_last(const orc_osd *o, int *order, int *min_distance);
+/* orc_decode + the reference's "if (OSD_Order >= 0 && !decode_correct) Decoding_OSD_bit(...)" tail */
+int orc_decode_osd(const orc_code *c, int method, int max_iter, int p0, int p1, double factor, double offset,
+                   const double *L_ch, int *out_sym, double *L_post, int *iters,
+                   orc_osd *osd, int osd_order, double osd_alpha, int osd_flag);
+
 /* number of T-EMS configuration leaves visited in the last orc_decode call (tems_route_num, NBLDPC.cpp:1896) */
 double orc_last_tems_leaves(void);
 

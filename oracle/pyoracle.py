@@ -32,6 +32,14 @@ def lib():
         _lib.orc_demap_qam.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double, ip, C.c_int, dp]
         _lib.orc_gf_tables.argtypes = [C.c_int, C.c_int, ip, ip]
         _lib.orc_last_tems_leaves.restype = C.c_double
+        _lib.orc_osd_create.restype = C.c_void_p
+        _lib.orc_osd_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.orc_osd_destroy.argtypes = [C.c_void_p]
+        _lib.orc_osd_run.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp, ip]
+        _lib.orc_osd_last.argtypes = [C.c_void_p, ip, ip]
+        _lib.orc_decode_osd.restype = C.c_int
+        _lib.orc_decode_osd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                        dp, ip, dp, ip, C.c_void_p, C.c_int, C.c_double, C.c_int]
     return _lib
 
 
@@ -103,15 +111,48 @@ class OracleCode:
             lib().orc_code_destroy(self._h)
             self._h = None
 
-    def decode(self, method, max_iter, p0, p1, factor, offset, L_ch):
-        """L_ch [N][q-1] float64 -> (ret, iters, out_sym[N], L_post[N][q-1])"""
+    def decode(self, method, max_iter, p0, p1, factor, offset, L_ch, osd=None, osd_order=-1, osd_alpha=1.0, osd_flag=0):
+        """L_ch [N][q-1] float64 -> (ret, iters, out_sym[N], L_post[N][q-1]); osd = an OracleOsd of this code"""
         L_ch = np.ascontiguousarray(L_ch, np.float64).reshape(self.N, self.q - 1)
         out = np.zeros(self.N, np.int32)
         post = np.zeros_like(L_ch)
         it = C.c_int(0)
-        ret = lib().orc_decode(self._h, method, max_iter, p0, p1, float(factor), float(offset),
-                               _dp(L_ch), _ip(out), _dp(post), C.byref(it))
+        ret = lib().orc_decode_osd(self._h, method, max_iter, p0, p1, float(factor), float(offset),
+                                   _dp(L_ch), _ip(out), _dp(post), C.byref(it),
+                                   osd._h if osd is not None else None, osd_order, float(osd_alpha), osd_flag)
         return ret, it.value, out, post
+
+
+class OracleOsd:
+    """bit-level OSD post-processor of one code (OSD.h): CRC rows + binary image of H, built once"""
+
+    def __init__(self, oc, crc_len=8, crc_rate=0, fix_matrepr=0):
+        self.oc = oc
+        self._h = lib().orc_osd_create(oc._h, crc_len, crc_rate, fix_matrepr)
+        if not self._h:
+            raise ValueError("unsupported CRC configuration")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_osd_destroy(self._h)
+            self._h = None
+
+    def run(self, order, L_ch, sym=None, sym_sum=None):
+        """stand-alone call: sym/sym_sum None = the reference's flag 1 (method 6)"""
+        N, q1 = self.oc.N, self.oc.q - 1
+        L_ch = np.ascontiguousarray(L_ch, np.float64).reshape(N, q1)
+        flag = sym is None
+        out = np.zeros(N, np.int32) if flag else np.ascontiguousarray(sym, np.int32).copy()
+        ss = L_ch if flag else np.ascontiguousarray(sym_sum, np.float64).reshape(N, q1)
+        lib().orc_osd_run(self._h, order, int(flag), _dp(L_ch), _dp(ss), _ip(out))
+        return out
+
+    def last(self):
+        p = self.oc.q.bit_length() - 1
+        order = np.zeros(self.oc.N * p, np.int32)
+        dist = C.c_int(0)
+        lib().orc_osd_last(self._h, _ip(order), C.byref(dist))
+        return order, dist.value
 
 
 def demap_bpsk(q, N, y_re, sigma, punct=()):

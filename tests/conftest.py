@@ -48,7 +48,12 @@ def load_golden(name):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """fixtures of the iterative decoders (the OSD fixtures f3_* have their own tests)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("f3_"))
+
+
+def golden_osd_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("f3_"))
 
 
 def golden_lch(z, meta, frames=None):

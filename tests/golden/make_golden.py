@@ -45,6 +45,14 @@ CASES = {
     "x_qspa_gf64": dict(code="BDS.576.288.GF.64", GFq=64, method=1, snr=1.5, frames=3),
     "f2_bstems_gf256": dict(code="divsalar.UNBLDPC.512.256.GF.256", GFq=256, method=7, snr=2.75, frames=10, bs_nm=4, bs_nc=3, bs_offset=0.2),
     "f2_bstems_gf64_nm9": dict(code="BDS.576.288.GF.64", GFq=64, method=7, snr=2.0, frames=12, bs_nm=9, bs_nc=2, bs_factor=1.25, bs_offset=0.1),
+    # 8(f)#3: OSD post-processing of failed frames (low SNR so that most frames fail), CRC-aided rows, method 6 stand-alone
+    "f3_osd2_tems_gf16": dict(code="divsalar.UNBLDPC.128.64.GF.16", GFq=16, method=4, snr=1.0, frames=32, max_iter=5, osd_order=2, crc_correct=0),
+    "f3_osd1_crc_ems_gf16": dict(code="divsalar.UNBLDPC.128.64.GF.16", GFq=16, method=2, snr=1.0, frames=24, max_iter=4, osd_order=1,
+                                 osd_factor=0.5, crc=8, crc_correct=8, ems_nm=6, ems_nc=2),
+    "f3_osd3_qspa_hbit256": dict(code="H_bit_GF256", GFq=256, method=1, snr=1.5, frames=8, max_iter=3, osd_order=3, crc=16, crc_correct=4),
+    "f3_osd1_tems_gf256": dict(code="divsalar.UNBLDPC.512.256.GF.256", GFq=256, method=4, snr=1.5, frames=4, max_iter=4, osd_order=1,
+                               crc=24, crc_correct=24, osd_flag=1),
+    "f3_osd_alone_gf64": dict(code="BDS.576.288.GF.64", GFq=64, method=6, snr=3.0, frames=6, osd_order=1, crc=8, crc_correct=8),
     "f2_bstems_gf16": dict(code="divsalar.UNBLDPC.128.64.GF.16", GFq=16, method=7, snr=2.5, frames=24, bs_nm=3, bs_nc=3, bs_offset=0.0),
 }
 
@@ -96,7 +104,8 @@ def run_case(name, cfg):
     # --- pin the oracle against the reference, bit for bit ---
     d = dict(DEFAULTS); d.update(cfg)
     oc = po.OracleCode(code)
-    if method == 1: p0, p1, fac, ofs = 0, 0, 1.0, 0.0
+    osd = po.OracleOsd(oc, d["crc"], d["crc_correct"]) if d["osd_order"] >= 0 else None
+    if method in (1, 6): p0, p1, fac, ofs = 0, 0, 1.0, 0.0
     elif method == 2: p0, p1, fac, ofs = d["ems_nm"], d["ems_nc"], d["ems_factor"], d["ems_offset"]
     elif method == 7: p0, p1, fac, ofs = d["bs_nm"], d["bs_nc"], d["bs_factor"], d["bs_offset"]
     else: p0, p1, fac, ofs = d["tems_nr"], d["tems_nc"], d["tems_factor"], d["tems_offset"]
@@ -106,15 +115,20 @@ def run_case(name, cfg):
     for f in range(F):
         mine = po.demap_bpsk(q, N, rx[f, :, 0], sigma) if d["nqam"] == 2 else po.demap_qam(q, N, rx[f], cons, sigma)
         assert np.array_equal(mine, lch[f]), "oracle demapper differs from the reference"
-        r, it, out, post = oc.decode(method, max_iter, p0, p1, fac, ofs, lch[f])
+        if method == 6:                                           # stand-alone OSD (Decoding_OSD_bit with flag 1): returns 0
+            assert ret[f] == 0
+            assert np.array_equal(osd.run(d["osd_order"], lch[f]), dec[f]), (name, f)
+            continue
+        r, it, out, post = oc.decode(method, max_iter, p0, p1, fac, ofs, lch[f], osd, d["osd_order"], d["osd_factor"], d["osd_flag"])
         assert (r, it) == (ret[f], iters[f]), (name, f, r, it, ret[f], iters[f])
-        assert np.array_equal(out, dec[f]), (name, f)
+        assert np.array_equal(out, dec[f]), (name, f, np.flatnonzero(out != dec[f]))
         assert np.array_equal(post, lpost[f]), (name, f, np.abs(post - lpost[f]).max())
     rng = np.random.RandomState(12345)
     idx = np.sort(rng.choice(q1, min(q1, 32), replace=False)).astype(np.int32)
     meta = dict(name=name, code=cfg["code"], q=q, N=N, K=K, method=method, max_iter=max_iter, p0=p0, p1=p1,
                 factor=fac, offset=ofs, snr_db=d["snr"], sigma=sigma, seed=d["seed"], random_msg=d["random_msg"],
-                nqam=d["nqam"], constellation=d["constellation"], crc=d["crc"])
+                nqam=d["nqam"], constellation=d["constellation"], crc=d["crc"], crc_correct=d["crc_correct"],
+                osd_order=d["osd_order"], osd_factor=d["osd_factor"], osd_flag=d["osd_flag"])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), rx=rx, tx_code_sym=tx.astype(np.int16),
                         tx_msg_sym=msg.astype(np.int16), ret=ret.astype(np.int8), iters=iters.astype(np.int8),
                         dec_sym=dec.astype(np.int16), lpost_idx=idx, lpost_sample=lpost[:, :, idx],

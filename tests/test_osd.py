@@ -1,0 +1,99 @@
+"""bit-level OSD post-processing of failed frames (reference OSD.h).
+
+CPU: the oracle's restatement against the fixtures dumped from the compiled reference (decisions of failed frames after
+OSD, orders 1-3, CRC-aided rows, forgetting factor, OSD_flag, stand-alone method 6).  GPU: the CUDA path through the
+C ABI against the same fixtures and against the oracle on random inputs."""
+import numpy as np
+import pytest
+
+from conftest import get_code_dict, golden_lch, golden_osd_names, load_golden, load_product_code
+
+
+def _oracle(meta):
+    from oracle import pyoracle as po
+    oc = po.OracleCode(get_code_dict(meta["code"]))
+    return oc, po.OracleOsd(oc, meta["crc"], meta["crc_correct"])
+
+
+@pytest.mark.parametrize("name", golden_osd_names())
+def test_oracle_osd_matches_reference(name):
+    z, meta = load_golden(name)
+    if meta["q"] == 256 and meta["N"] > 16:
+        pytest.skip("minutes on a CPU; pinned when the fixture was made (tests/golden/make_golden.py)")
+    oc, osd = _oracle(meta)
+    lch = golden_lch(z, meta)
+    for f in range(len(z["ret"])):
+        if meta["method"] == 6:
+            assert np.array_equal(osd.run(meta["osd_order"], lch[f]), z["dec_sym"][f])
+            continue
+        r, it, out, _ = oc.decode(meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], lch[f],
+                                  osd, meta["osd_order"], meta["osd_factor"], meta["osd_flag"])
+        assert (r, it) == (z["ret"][f], z["iters"][f])
+        assert np.array_equal(out, z["dec_sym"][f]), f
+
+
+def test_osd_improves_on_the_iterative_decoder():
+    """sanity of the fixtures themselves: OSD touched exactly the failed frames and turned some of them into the
+    transmitted code word (26 -> 19 frame errors at this SNR)"""
+    z, meta = load_golden("f3_osd2_tems_gf16")
+    oc, _ = _oracle(meta)
+    lch = golden_lch(z, meta)
+    plain = np.stack([oc.decode(meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], l)[2] for l in lch])
+    failed = z["ret"] == 0
+    assert (plain[failed] != z["dec_sym"][failed]).any()
+    assert np.array_equal(plain[~failed], z["dec_sym"][~failed])
+    assert (z["dec_sym"] != z["tx_code_sym"]).any(axis=1).sum() < (plain != z["tx_code_sym"]).any(axis=1).sum()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("name", golden_osd_names())
+def test_gpu_osd_matches_reference(name, precision, code_files):
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    F = len(z["ret"])
+    lch = golden_lch(z, meta)
+    method = meta["method"] if meta["method"] != 6 else 1
+    dec = capi.Decoder(code, method, meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                       precision=precision, max_batch=F)
+    dec.enable_osd(meta["osd_order"], meta["osd_factor"], meta["osd_flag"], meta["crc"], meta["crc_correct"])
+    if meta["method"] == 6:
+        got = dec.osd(lch)
+        same = (got == z["dec_sym"]).all(axis=1)
+    else:
+        r = dec.decode(lch)
+        assert np.array_equal(r["converged"], z["ret"].astype(np.int32)) or precision == capi.PREC_F32
+        same = (r["sym"] == z["dec_sym"]).all(axis=1) & (r["converged"] == z["ret"])
+    if precision == capi.PREC_F64:
+        assert same.all(), np.flatnonzero(~same)
+    else:
+        assert same.mean() >= 0.75, same          # fp32 messages: a near-tie in the ranking or a distance may fall the other way
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("q,order,crc,rate,alpha,flag", [(16, 2, 8, 0, 1.0, 0), (32, 1, 8, 8, 0.5, 0), (64, 2, 16, 5, 1.0, 1), (16, 3, 8, 3, 0.7, 0)])
+def test_gpu_osd_random_codes_against_oracle(q, order, crc, rate, alpha, flag, tmp_path):
+    """random (some rank-deficient) codes: exercises the column rotation of the elimination and the candidate order"""
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    from test_warp_paths_gpu import _random_code
+    rng = np.random.default_rng(5000 + q + order)
+    code = _random_code(q, 10, rng, q != 32)
+    p = q.bit_length() - 1
+    N = code["N"]
+    F = 12
+    y = 1.0 + 1.0 * rng.standard_normal((F, N * p))
+    lch = np.stack([po.demap_bpsk(q, N, yy, 1.0) for yy in y])
+    path = tmp_path / "osd.txt"
+    path.write_text(po.code_text(code))
+    oc = po.OracleCode(code)
+    osd = po.OracleOsd(oc, crc, rate)
+    want = [oc.decode(4, 3, 2, 2, 1.0, 0.5, l, osd, order, alpha, flag) for l in lch]
+    dec = capi.Decoder(capi.Code.from_file(str(path)), 4, 3, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=F)
+    dec.enable_osd(order, alpha, flag, crc, rate)
+    r = dec.decode(lch)
+    assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
+    assert (r["converged"] == 0).any()
+    assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+    assert np.array_equal(dec.osd(lch), np.stack([osd.run(order, l) for l in lch]))
