@@ -50,10 +50,10 @@ bool CNBLDPC::Initial(CSimulation &sim) {
     EMS_Nm = sim.ems_nm; EMS_Nc = sim.ems_nc; EMS_Correction_Factor = sim.ems_factor; EMS_Correction_Offset = sim.ems_offset;
     TEMS_Nr = sim.tems_nr; TEMS_Nc = sim.tems_nc; TEMS_Factor = sim.tems_factor; TEMS_Offset = sim.tems_offset;
     basic_set_Nm = sim.bs_tems_nm; basic_set_Nc = sim.bs_tems_nc; basic_set_factor = sim.bs_tems_factor; basic_set_offset = sim.bs_tems_offset;   // NBLDPC.cpp:334-337
-    OSD_Order = sim.OSD_order;
+    OSD_Order = sim.OSD_order; OSD_Alpha = sim.OSD_factor; OSD_flag = sim.OSD_flag;     // NBLDPC.cpp:381-383
+    CRCLen = sim.crcLen; CRCrate = sim.crc_correctLen;                                  // NBLDPC.cpp:437-438
     precision_ = sim.precision;
     if (DecodeMethod == EMS_DECODE && EMS_Nm > GFq) { std::cerr << "EMS configuration error! EMS_Nm is too large!" << std::endl; exit(-1); }
-    if (OSD_Order >= 0) { std::cerr << "OSD post-processing is outside this decode path; run with OSD_order < 0" << std::endl; exit(-1); }
 
     post_.assign((size_t)CodeLen * (GFq - 1), 0.0);
     post_rows_.resize(CodeLen);
@@ -134,7 +134,13 @@ int CNBLDPC::ensure_decoder(int batch) {
     else if (DecodeMethod == T_EMS_DECODE) { cfg.p0 = TEMS_Nr; cfg.p1 = TEMS_Nc; cfg.factor = TEMS_Factor; cfg.offset = TEMS_Offset; }
     else if (DecodeMethod == BS_TEMS_DECODE) { cfg.p0 = basic_set_Nm; cfg.p1 = basic_set_Nc; cfg.factor = basic_set_factor; cfg.offset = basic_set_offset; }
     else { cfg.factor = 1; }
+    if (DecodeMethod == OSD_DECODE) cfg.method = BP_DECODE;     // method 6 runs OSD alone (nbl_osd_batch); the handle still needs a decoder
     if (nbl_decoder_create(&dec_, code_, &cfg, nullptr) != NBL_OK) die("decoder");
+    if (OSD_Order >= 0 || DecodeMethod == OSD_DECODE) {         // the reference's tail of every Decoding_* (NBLDPC.cpp:770-775, 921-925, 1135-1139)
+        nbl_osd_config oc{};
+        oc.order = OSD_Order < 0 ? 0 : OSD_Order; oc.factor = OSD_Alpha; oc.flag = OSD_flag; oc.crc_len = CRCLen; oc.crc_correct_len = CRCrate;
+        if (nbl_decoder_enable_osd(dec_, &oc) != NBL_OK) die("OSD");
+    }
     dec_batch_ = batch;
     return 0;
 }
@@ -149,6 +155,11 @@ int CNBLDPC::run_method(int method, double **L_ch, int *out) {
     lch_.resize((size_t)CodeLen * q1);
     for (int v = 0; v < CodeLen; ++v) std::copy(L_ch[v], L_ch[v] + q1, lch_.begin() + (size_t)v * q1);   // ragged -> dense
     int conv = 0, iters = 0;
+    if (method == OSD_DECODE) {                  // Decoding_OSD_bit(L_ch, out, rely, 1) returns 0 (OSD.h:198)
+        if (nbl_osd_batch(dec_, lch_.data(), 1, out) != NBL_OK) die("OSD");
+        lastIterations = 0;
+        return 0;
+    }
     if (nbl_decode_batch(dec_, lch_.data(), 1, out, &conv, &iters, post_.data()) != NBL_OK) die("decode");
     lastIterations = iters;
     return conv;
@@ -158,6 +169,12 @@ int CNBLDPC::Decoding_BP(double **L_ch, int *DecodeOutput) { return run_method(B
 int CNBLDPC::Decoding_EMS(double **L_ch, int *DecodeOutput, int *) { return run_method(EMS_DECODE, L_ch, DecodeOutput); }
 int CNBLDPC::Decoding_TEMS(double **L_ch, int *DecodeOutput, int *, int *) { return run_method(T_EMS_DECODE, L_ch, DecodeOutput); }
 int CNBLDPC::Decoding_BS_TEMS(double **L_ch, int *DecodeOutput, int *, int *) { return run_method(BS_TEMS_DECODE, L_ch, DecodeOutput); }
+// OSD.h:5: the stand-alone form (flag 1) only; with flag 0 the reference feeds it the state of the iterative decoder
+// that has just failed, which here happens on the device inside nbl_decode_batch
+int CNBLDPC::Decoding_OSD_bit(double **L_ch, int *DecodeOutput, int *, int flag) {
+    if (!flag) { std::cerr << "Decoding_OSD_bit with flag 0 runs inside the iterative decoders on this path" << std::endl; exit(-1); }
+    return run_method(OSD_DECODE, L_ch, DecodeOutput);
+}
 
 int CNBLDPC::Decoding(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, int *RelySeri_bit) {
     switch (DecodeMethod) {                      // NBLDPC.cpp:607-641
@@ -167,7 +184,7 @@ int CNBLDPC::Decoding(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, in
     case MinMax_DECODE: std::cout << "Min Max algorithm has not been developed" << std::endl; exit(-1);
     case T_MinMax_DECODE: std::cout << "Trellis Min Max algorithm has not been developed" << std::endl; exit(-1);
     case BS_TEMS_DECODE: return Decoding_BS_TEMS(L_ch, DecodeOutput, RelySeri_symbol, RelySeri_bit);
-    case OSD_DECODE: std::cout << "Decode method " << DecodeMethod << " is outside this decode path" << std::endl; exit(-1);
+    case OSD_DECODE: return Decoding_OSD_bit(L_ch, DecodeOutput, RelySeri_bit, 1);
     default: std::cout << "Decode Method is not specified!" << std::endl; exit(-1);
     }
     return 0;
@@ -176,6 +193,14 @@ int CNBLDPC::Decoding(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, in
 int CNBLDPC::DecodingBatch(int modulation, const double *y, int B, const double *constellation, double sigma,
                            int *DecodeOutput, int *converged, int *iterations) {
     ensure_decoder(B);
+    if (DecodeMethod == OSD_DECODE) {            // method 6: demap, then OSD alone on every frame; "not converged", as the reference returns
+        lch_.resize((size_t)B * CodeLen * (GFq - 1));
+        const int rc = modulation == 2 ? nbl_demap_bpsk(dec_, y, B, sigma, PuncturePosition, PunctureLen, lch_.data())
+                                       : nbl_demap_qam(dec_, y, B, constellation, sigma, PuncturePosition, PunctureLen, lch_.data());
+        if (rc != NBL_OK || nbl_osd_batch(dec_, lch_.data(), B, DecodeOutput) != NBL_OK) die("demap+OSD");
+        for (int f = 0; f < B; ++f) { converged[f] = 0; iterations[f] = 0; }
+        return 0;
+    }
     if (nbl_demap_decode_batch(dec_, modulation, y, B, constellation, sigma, PuncturePosition, PunctureLen, DecodeOutput, converged, iterations) != NBL_OK)
         die("demap+decode");
     return 0;

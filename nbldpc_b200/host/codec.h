@@ -30,7 +30,8 @@ public:
     int EMS_Nm = 0, EMS_Nc = 0; double EMS_Correction_Factor = 1, EMS_Correction_Offset = 0;
     int TEMS_Nr = 0, TEMS_Nc = 0; double TEMS_Factor = 1, TEMS_Offset = 0;
     int basic_set_Nm = 0, basic_set_Nc = 0; double basic_set_factor = 1, basic_set_offset = 0;   // NBLDPC.h:169-172
-    int OSD_Order = -1;
+    int OSD_Order = -1, OSD_flag = 0; double OSD_Alpha = 1;   // NBLDPC.h: OSD_Order / OSD_flag / OSD_Alpha
+    int CRCLen = 0, CRCrate = 0;                               // crcLen, crc_correctLen
     double tems_route_num = 0;                 // kept for source compatibility; the GPU search does not count leaves
     int lastIterations = 0;                    // iteration count of the last Decoding() call (not exposed by the reference)
 
@@ -42,6 +43,7 @@ public:
     int Decoding_EMS(double **L_ch, int *DecodeOutput, int *RelySeri_bit);
     int Decoding_BS_TEMS(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, int *RelySeri_bit);   // NBLDPC.h (BS_TEMS_DECODE)
     int Decoding_TEMS(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, int *RelySeri_bit);
+    int Decoding_OSD_bit(double **L_ch, int *DecodeOutput, int *ReliableSeri_BIT, int flag);   // OSD.h:5
     int DecideLLRVector(double *LLR);
 
     // batched drop-in: B frames of received samples (BPSK: [B][mod_len] real parts, QAM: [B][mod_len][2]) ->

@@ -102,3 +102,21 @@ def test_simulation_driver_reproduces_reference_fer_point(tmp_path):
     # the row the compiled reference prints for this profile (oracle/_ref/nbldpc_ref, 83 s on one CPU core):
     #   3  51  0  1.872226e-03  5.491864e-03  1.508876e-02  0.000000e+00
     assert last[:7] == ["3", "51", "0", "1.872226e-03", "5.491864e-03", "1.508876e-02", "0.000000e+00"], rows[-1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["f3_osd2_tems_gf16", "f3_osd1_crc_ems_gf16", "f3_osd_alone_gf64"])
+def test_harness_osd_matches_reference(name, tmp_path):
+    """profile keys OSD_order / OSD_factor / OSD_flag / crc_correctLen and decode method 6 through CNBLDPC::Decoding:
+    failed frames come back with the reference's OSD decision"""
+    z, meta = load_golden(name)
+    _workdir(tmp_path, meta, dict(osd_order=meta["osd_order"], osd_factor=meta["osd_factor"], osd_flag=meta["osd_flag"],
+                                  crc_correct=meta["crc_correct"]))
+    F = len(z["ret"])
+    _, recs = _run_dump(tmp_path, F, decode=True)
+    assert (z["ret"] == 0).any()
+    for f, r in enumerate(recs):
+        assert r["ret"] == int(z["ret"][f]), f
+        if meta["method"] != 6:
+            assert r["iters"] == int(z["iters"][f]), f
+        assert np.array_equal(r["dec"], z["dec_sym"][f]), f
