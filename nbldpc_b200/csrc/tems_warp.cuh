@@ -45,6 +45,9 @@ constexpr int TW_HOIST = 2;   // messages of a variable fetched ahead (its degre
 #define TW_MIN_CTAS_VALUE 5
 #endif
 constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident CTAs per SM the register allocation aims for (5 x 4 warps)
+#ifndef TW_MINB_VALUE
+#define TW_MINB_VALUE (TW_MIN_CTAS * 4 / TW_WARPS)
+#endif
 
 // A message-sized vector in shared memory is cut into 16-byte pieces; piece h of all 32 lane-blocks is contiguous:
 //   index(k, j) = (j / E16) * (32 * E16) + k * E16 + j % E16     (element VEC*k + j; E16 = elements per 16 bytes, or VEC
@@ -342,7 +345,7 @@ template <typename T, int VEC> __device__ __forceinline__ void ld_blk(const unsi
 // DC > 0: every check row has exactly DC edges (no degree guards in the unrolled stages); DC == 0: row degree from the
 // descriptor.  DV > 0: every variable has exactly DV <= TW_HOIST edges; DV == 0: variable degree from the descriptor.
 template <typename T, int Q, int DC, int DV>
-__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MIN_CTAS * 4 / TW_WARPS : 1) k_iterate_tems_warp(const IterParams<T> P) {
+__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MINB_VALUE : 1) k_iterate_tems_warp(const IterParams<T> P) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
     using S = TwSmem<T, Q>;
