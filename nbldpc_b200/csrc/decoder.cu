@@ -1017,6 +1017,12 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
     const size_t ydbl = (size_t)d->cfg.max_batch * ylen * (cfg->modulation == 2 ? 1 : 2);
     if ((rc = ensure_ystage(d, ydbl * sizeof(double)))) return rc;
     const bool rnd = cfg->n_codewords == 0 && cfg->random_msg != 0;
+    if (rnd && d->osd_on && d->osd.order >= 0 && d->osd_cfg.crc_correct_len > 0) {
+        // k_sim_message draws K free symbols; the CRC rows of the OSD matrix would then constrain bits that carry no CRC
+        nbl_set_error("nbl_simulate: random messages carry no CRC on the device; use OSD with crc_correct_len = 0, a codeword pool "
+                      "encoded with the CRC (host harness), or the all-zero code word");
+        return NBL_ERR_ARG;
+    }
     if (!d->d_tx) CK(cudaMalloc((void **)&d->d_tx, (size_t)d->cfg.max_batch * N));
     if (rnd) {
         if (!d->sim_enc && (rc = nbl_encoder_create(&d->sim_enc, d->code, d->cfg.device, d->stream))) return rc;

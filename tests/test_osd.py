@@ -97,3 +97,25 @@ def test_gpu_osd_random_codes_against_oracle(q, order, crc, rate, alpha, flag, t
     assert (r["converged"] == 0).any()
     assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
     assert np.array_equal(dec.osd(lch), np.stack([osd.run(order, l) for l in lch]))
+
+
+@pytest.mark.gpu
+def test_device_monte_carlo_with_osd(code_files):
+    """nbl_simulate with OSD enabled: the same frames (same seed) lose frame errors, never gain one on a frame that
+    converged, and the CRC-row variant is refused for device-drawn messages (they carry no CRC)"""
+    from nbldpc_b200 import capi
+    code = load_product_code(code_files, "divsalar.UNBLDPC.128.64.GF.16")
+    frames = 20000
+    dec = capi.Decoder(code, capi.METHOD_TEMS, 5, 2, 2, 1.0, 0.5, precision=capi.PREC_F32, max_batch=frames)
+    plain = dec.simulate(2.0, frames, seed=3, random_msg=1)
+    dec.enable_osd(1, 1.0, 0, 8, 0)
+    osd = dec.simulate(2.0, frames, seed=3, random_msg=1)
+    assert int(plain[0]) == int(osd[0]) == frames
+    assert int(osd[4]) == int(plain[4])                     # converged frames: untouched
+    assert 0 < int(osd[1]) < int(plain[1]), (plain, osd)    # frame errors: some failed frames are now the transmitted code word
+    dec.enable_osd(1, 1.0, 0, 8, 8)
+    with pytest.raises(Exception, match="no CRC"):
+        dec.simulate(2.0, 1000, seed=3, random_msg=1)
+    dec.enable_osd(-1)
+    again = dec.simulate(2.0, frames, seed=3, random_msg=1)
+    assert np.array_equal(again, plain)
