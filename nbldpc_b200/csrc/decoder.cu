@@ -57,6 +57,7 @@ template <typename T> struct IterParams {
 #include "ems_warp.cuh"
 #include "qspa_warp.cuh"
 #include "osd.cuh"
+#include "qspa_half.cuh"
 
 // channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
 template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
@@ -280,6 +281,8 @@ struct nbl_decoder {
     bool qspa_warp_path = false; // QSPA, dc <= 4, q >= 32: one warp per check row (qspa_warp.cuh)
     bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
+    bool qspa_half_path = false; // QSPA over GF(16), dc <= 8, dv <= 4: four lanes per check row, eight rows per warp (qspa_half.cuh)
+    int *d_rowdesc8 = nullptr;   // its row descriptors [M][QH_MAXDC][QH_DSC]
     // OSD post-processing of failed frames (osd.cuh); off until nbl_decoder_enable_osd
     bool osd_on = false;
     nbl_osd_config osd_cfg{};
@@ -332,7 +335,7 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
     cudaSetDevice(d->cfg.device);
     void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_rowdesc, d->d_pfwd, d->d_pinv, d->d_pfwd_sw, d->d_pinv_sw, d->d_lch, d->d_v2c,
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
-                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg, d->d_osd_H0, d->d_osd_sum, d->d_osd_status};
+                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg, d->d_osd_H0, d->d_osd_sum, d->d_osd_status, d->d_rowdesc8};
     if (d->sim_enc) nbl_encoder_destroy(d->sim_enc);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : d->it_ev) if (e) cudaEventDestroy(e);
@@ -410,6 +413,18 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
             for (size_t i = 0; i < pf.size(); ++i) { pfs[i] = (uint8_t)swz(pf[i]); pis[i] = (uint8_t)swz(pi[i]); }
             if ((rc = upload(&d->d_pfwd_sw, pfs)) || (rc = upload(&d->d_pinv_sw, pis))) return fail(rc);
         }
+    }
+    if (q == 16 && cfg->method == NBL_METHOD_QSPA && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV && !getenv("NBLDPC_FORCE_GENERIC")) {
+        std::vector<int> rd((size_t)code->M * QH_MAXDC * QH_DSC, 0);
+        for (int r = 0; r < code->M; ++r)
+            for (int e = code->chk_ptr[r]; e < code->chk_ptr[r + 1]; ++e) {
+                int *slot = &rd[((size_t)r * QH_MAXDC + (e - code->chk_ptr[r])) * QH_DSC];
+                const int v = code->chk_var[e];
+                slot[0] = v; slot[1] = code->var_ptr[v + 1] - code->var_ptr[v];
+                for (int s = code->var_ptr[v]; s < code->var_ptr[v + 1]; ++s) slot[2 + s - code->var_ptr[v]] = code->var_edge[s];
+            }
+        if ((rc = upload(&d->d_rowdesc8, rd))) return fail(rc);
+        d->qspa_half_path = true;
     }
     d->g = DevGraph{q, code->p, N, code->M, E, code->max_dv, code->max_dc, d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_pfwd, d->d_pinv, d->d_rowdesc};
     const size_t B = cfg->max_batch;
@@ -550,6 +565,14 @@ template <typename T, int Q> static int launch_iterate_qspa_warp(nbl_decoder *d,
     }
 }
 template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const IterParams<T> &P) {
+    if constexpr (Q == 16) {
+        if (d->qspa_half_path) {
+            const long long rows = (long long)P.B * P.g.M, per_cta = QH_ROWS * QH_WARPS;
+            k_iterate_qspa_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, QhSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
+            CK(cudaGetLastError());
+            return NBL_OK;
+        }
+    }
     if (d->warp_path) return launch_iterate_warp<T, Q>(d, P);
     if (d->ems_warp_path) return launch_iterate_ems_warp<T, Q>(d, P);
     if (d->qspa_warp_path) return launch_iterate_qspa_warp<T, Q>(d, P);

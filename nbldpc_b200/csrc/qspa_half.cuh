@@ -1,0 +1,262 @@
+// Fused iteration kernel for QSPA over GF(16): FOUR LANES per (frame, check row), four field elements per lane, eight
+// check rows per warp.
+//
+// GF(16) vectors are 16 values, so the warp kernels' "q / 32 elements per lane" does not apply and the group kernel runs
+// them as 16-thread groups -- correctly, but its ncu capture on BASELINE configs[0] (profiles/r01_cfg1_v1_ncu_key.txt)
+// shows ~1 400 warp instructions per check row and the long-scoreboard stall on top: every message load waits on a chain
+// of index loads (chk_var -> var_ptr -> var_edge -> message), decisions go through shared-memory scratch.  A first
+// register-only form with one lane per element (16 lanes per row) still needed ~1 050 instructions per row
+// (profiles/r01_cfg1_v3_ncu_key.txt): with one element per lane every decision is four shuffle stages plus a vote, every
+// transform four shuffle stages, every address is computed sixteen times.  Hence four elements per lane:
+//   * a message vector is one 16-byte load per lane; half of the butterfly stages of the 16-point Walsh-Hadamard
+//     transform and of every arg-max are in-lane, the other half two shuffles;
+//   * a row descriptor (8 edges x {variable, degree, up to 4 edge ids}) makes every address known after ONE load; the
+//     descriptor of edge d + 2 and the messages of edge d + 1 are in flight while edge d is computed;
+//   * the permutations x -> h x / h^-1 x go through a small shared-memory slab per warp (one 16-byte store, four
+//     indexed loads).
+// All shuffles and votes are WARP-wide (full mask): offsets 1 and 2 stay inside a row's four lanes, so the eight rows of a
+// warp run ONE instruction stream; whatever differs between them (row degree, the damping trigger, a finished frame) is
+// predicated, never branched on, unless the branch is warp-uniform.
+// Same arithmetic as the other QSPA kernels -- steps A-C of NBLDPC.cpp:676-744, c2v_d = ln WHT(prod_{l != d} WHT(P_l)) --
+// with the butterflies of group_wht_reg (cn_qspa.cuh) in the same stage and operand order: bit-identical results.
+// Serves check degrees <= 8 and variable degrees <= 4 (all GF(16) codes of the reference: d_c = 5, d_v = 2, 3).
+#pragma once
+#include "cn_qspa.cuh"
+
+namespace nbl {
+
+constexpr int QH_MAXDC = 8;     // edges per row in the descriptor
+constexpr int QH_MAXDV = 4;     // messages of a variable held in registers
+constexpr int QH_DSC = 8;       // ints per edge: variable, degree, edge ids (file order = summation order)
+constexpr int QH_ROWS = 8;      // check rows per warp
+constexpr int QH_WARPS = 4;     // warps per CTA
+constexpr unsigned QH_FULL = 0xffffffffu;
+
+template <typename T> struct QhSmem {
+    // per warp: the row's current vector in natural order, for the two gathers of an edge
+    static constexpr size_t v_bytes = (size_t)QH_ROWS * 16 * sizeof(T);
+    static constexpr size_t r_bytes = (size_t)QH_ROWS * 16 * sizeof(double);
+    static constexpr size_t bytes_per_warp = v_bytes + r_bytes;
+    static constexpr size_t bytes = bytes_per_warp * QH_WARPS;
+};
+
+template <typename T> __device__ __forceinline__ void qh_load4(const T *p, T (&v)[4]) {
+    if constexpr (sizeof(T) == 4) { const float4 w = *reinterpret_cast<const float4 *>(p); v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w; }
+    else {
+        const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+template <typename T> __device__ __forceinline__ void qh_store4(T *p, const T (&v)[4]) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]); }
+}
+
+// DecideLLRVector (NBLDPC.cpp:1542-1562): arg-max over the non-zero symbols if the maximum is positive, else 0; ties: lowest
+template <typename T> __device__ __forceinline__ int qh_decide(const T (&v)[4], int x0) {
+    T key[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) key[j] = (x0 + j > 0 && v[j] > T(0)) ? v[j] : T(0);
+    T m = key[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) m = key[j] > m ? key[j] : m;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) { const T t = __shfl_xor_sync(QH_FULL, m, o); m = t > m ? t : m; }
+    int cand = 99;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) if (key[j] == m) cand = x0 + j;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) cand = min(cand, __shfl_xor_sync(QH_FULL, cand, o));
+    return m > T(0) ? cand : 0;
+}
+
+// 16-point WHT, element 4 * l4 + j in v[j] of lane l4 of the row: stages bit = 1, 2 in-lane, bit = 4, 8 by shuffle
+__device__ __forceinline__ void qh_wht(double (&v)[4], int l4) {
+#pragma unroll
+    for (int bit = 1; bit < 4; bit <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (!(j & bit)) { const double a = v[j], b = v[j | bit]; v[j] = a + b; v[j | bit] = a - b; }
+    }
+#pragma unroll
+    for (int lb = 1; lb <= 2; lb <<= 1) {
+        const bool up = l4 & lb;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double other = __shfl_xor_sync(QH_FULL, v[j], lb); v[j] = up ? (other - v[j]) : (v[j] + other); }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_iterate_qspa_half(const IterParams<T> P, const int *__restrict__ desc) {
+    constexpr int Q = 16;
+    extern __shared__ __align__(16) unsigned char qh_raw[];
+    const DevGraph &g = P.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l4 = lane & 3, rw = lane >> 2, x0 = 4 * l4;            // my lane of the row, the row's slot in the warp, first element
+    T *sV = reinterpret_cast<T *>(qh_raw + QhSmem<T>::bytes_per_warp * warp) + rw * 16;
+    double *sR = reinterpret_cast<double *>(qh_raw + QhSmem<T>::bytes_per_warp * warp + QhSmem<T>::v_bytes) + rw * 16;
+    const long long nrows = (long long)P.B * g.M;
+    long long w = ((long long)blockIdx.x * QH_WARPS + warp) * QH_ROWS + rw;
+    bool active = w < nrows;
+    if (!active) w = nrows - 1;                                     // the lanes stay for the warp-wide shuffles; they store nothing
+    const int f = (int)(w / g.M), row = (int)(w % g.M);
+    if (P.early_stop && P.done[f]) active = false;
+    if (!__any_sync(QH_FULL, active)) return;                       // warp-uniform
+
+    const int *rd = desc + (size_t)row * (QH_MAXDC * QH_DSC);
+    const int e0 = g.chk_ptr[row];
+    const int dcn = active ? g.chk_ptr[row + 1] - e0 : 0;
+    const int dmax = __reduce_max_sync(QH_FULL, dcn);               // the longest of the warp's rows
+    const T *lchf = P.lch + (size_t)f * g.N * Q + x0;
+    const T *cinf = P.c2v_in + (size_t)f * g.E * Q + x0;
+    T *v2cf = P.v2c + (size_t)f * g.E * Q + x0;
+    uint8_t *vdecf = P.vdec + (size_t)f * g.E;
+
+    // software pipeline over the edges: descriptor of edge d + 2 and messages of edge d + 1 are in flight during edge d
+    int4 da[2]; int2 db[2];                                         // {variable, degree, edge ids 0..1}, {edge ids 2..3}
+    T lc[2][4], mm[2][QH_MAXDV][4]; int meta[2];                    // meta: own slot | degree << 4 | old decision + 1 << 8 | variable << 17
+    auto fetch_desc = [&](int d, int slot) {
+        da[slot] = make_int4(0, 0, 0, 0); db[slot] = make_int2(0, 0);
+        if (d < dcn) { da[slot] = *reinterpret_cast<const int4 *>(rd + QH_DSC * d); db[slot] = *reinterpret_cast<const int2 *>(rd + QH_DSC * d + 4); }
+    };
+    auto fetch_msgs = [&](int d, int slot) {                        // slot of the descriptor == slot of the messages (d & 1)
+        const int ej[QH_MAXDV] = {da[slot].z, da[slot].w, db[slot].x, db[slot].y};
+        const int nv = da[slot].y;
+        int own = QH_MAXDV, bef = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lc[slot][i] = T(0);
+#pragma unroll
+        for (int j = 0; j < QH_MAXDV; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mm[slot][j][i] = T(0);
+        if (d < dcn) {
+            qh_load4<T>(lchf + (size_t)da[slot].x * Q, lc[slot]);
+#pragma unroll
+            for (int j = 0; j < QH_MAXDV; ++j) {
+                if (!P.first && j < nv) qh_load4<T>(cinf + (size_t)ej[j] * Q, mm[slot][j]);
+                if (j < nv && ej[j] == e0 + d) own = j;
+            }
+            bef = P.first ? 0 : (int)vdecf[e0 + d] + 1;
+        }
+        meta[slot] = own | (nv << 4) | (bef << 8) | (da[slot].x << 17);
+    };
+    T V[QH_MAXDC][4];
+    unsigned tf[QH_MAXDC], ti[QH_MAXDC];                            // my four bytes of the rows h * x and h^-1 * x
+    unsigned sdw = 0u;                                              // nibble d: decide(v2c_d)
+    int syn = 0;
+    fetch_desc(0, 0);
+    fetch_desc(1, 1);
+    fetch_msgs(0, 0);
+    // ---- steps A-C (NBLDPC.cpp:676-744): posterior, decisions, syndrome, damped v2c ------------------------------------------
+#pragma unroll
+    for (int d = 0; d < QH_MAXDC; ++d) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) V[d][i] = T(0);
+        tf[d] = 0u; ti[d] = 0u;
+        if (d < dmax) {                                             // warp-uniform
+            const int slot = d & 1;
+            if (d + 1 < QH_MAXDC) fetch_msgs(d + 1, slot ^ 1);      // needs descriptor d + 1 (requested one step ago)
+            const bool live = d < dcn;
+            const int e = e0 + d, own = meta[slot] & 15, nv = (meta[slot] >> 4) & 15, bef = (meta[slot] >> 8) & 511, col = meta[slot] >> 17;
+            if (live) {
+                tf[d] = *reinterpret_cast<const unsigned *>(g.pfwd + (size_t)e * Q + x0);
+                ti[d] = *reinterpret_cast<const unsigned *>(g.pinv + (size_t)e * Q + x0);
+            }
+            T post[4], mine[4], vnew[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { post[i] = lc[slot][i]; mine[i] = T(0); }
+#pragma unroll
+            for (int j = 0; j < QH_MAXDV; ++j)
+                if (j < nv) {                                       // iteration 1: + 0, exact
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { post[i] = post[i] + mm[slot][j][i]; if (j == own) mine[i] = mm[slot][j][i]; }
+                }
+            if (d + 2 < QH_MAXDC) fetch_desc(d + 2, slot);          // this slot's descriptor and messages are consumed
+#pragma unroll
+            for (int i = 0; i < 4; ++i) vnew[i] = post[i] - mine[i];
+            const int dpost = qh_decide<T>(post, x0);
+            int dfin = qh_decide<T>(vnew, x0);
+            const bool need = live && !P.first && P.w_old != T(0) && dfin != bef - 1;
+            if (__any_sync(QH_FULL, need)) {                        // warp-uniform
+                T vd[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vd[i] = vnew[i];
+                if (need) {
+                    T vold[4];
+                    qh_load4<T>(v2cf + (size_t)e * Q, vold);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vd[i] = P.w_old * vold[i] + P.w_new * vnew[i];    // -fmad=false
+                }
+                const int d2 = qh_decide<T>(vd, x0);
+                if (need) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vnew[i] = vd[i];
+                    dfin = d2;
+                }
+            }
+            if (live) {
+                qh_store4<T>(v2cf + (size_t)e * Q, vnew);
+                if (l4 == 0) { vdecf[e] = (uint8_t)dfin; P.dec[(size_t)f * g.N + col] = (uint8_t)dpost; }
+            }
+            // h * decision: byte dpost & 3 of the word of lane dpost >> 2 of this row
+            const unsigned hw = __shfl_sync(QH_FULL, tf[d], (lane & ~3) + (dpost >> 2));
+            if (live) syn ^= (int)((hw >> (8 * (dpost & 3))) & 255u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) V[d][i] = vnew[i];
+            sdw |= (unsigned)dfin << (4 * d);
+        }
+    }
+    if (active && l4 == 0 && syn != 0) P.flag[f] = 1;
+    // ---- check node: distributions in the syndrome domain, maximum normalised to 1, transformed ------------------------------
+    double F[QH_MAXDC][4];
+#pragma unroll
+    for (int d = 0; d < QH_MAXDC; ++d) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) F[d][i] = 1.0;
+        if (d < dmax) {
+            qh_store4<T>(sV + x0, V[d]);
+            __syncwarp();
+            const double vmax = (double)sV[(sdw >> (4 * d)) & 15u];
+            double t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = qspa_exp<T>((double)sV[(ti[d] >> (8 * i)) & 255u] - vmax);   // P[s] = p[h^-1 s]
+            __syncwarp();
+            qh_wht(t, l4);
+            if (d < dcn) {                                          // edges another row has and this one lacks: factor 1
+#pragma unroll
+                for (int i = 0; i < 4; ++i) F[d][i] = t[i];
+            }
+        }
+    }
+    T *coutf = P.c2v_out + (size_t)f * g.E * Q + x0;
+#pragma unroll
+    for (int d = 0; d < QH_MAXDC; ++d) {
+        if (d < dmax) {
+            double r[4] = {1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+            for (int l = 0; l < QH_MAXDC; ++l)
+                if (l != d) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r[i] *= F[l][i];    // * 1.0 is exact
+                }
+            qh_wht(r, l4);
+            qh_store4<double>(sR + x0, r);
+            __syncwarp();
+            // floor at the fp64 noise of the transform (see cn_qspa.cuh), log, un-permute
+            const double tot = sR[0];
+            const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
+            const double lt = qspa_log<T>(tot > fl ? tot : fl);
+            T out[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double a = sR[(tf[d] >> (8 * i)) & 255u];
+                out[i] = (T)(qspa_log<T>(a > fl ? a : fl) - lt);
+            }
+            __syncwarp();
+            if (l4 == 0) out[0] = T(0);
+            if (d < dcn) qh_store4<T>(coutf + (size_t)(e0 + d) * Q, out);
+        }
+    }
+}
+
+}  // namespace nbl

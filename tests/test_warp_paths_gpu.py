@@ -180,10 +180,10 @@ def test_ems_warp_kernel_random_codes(q, regular, tmp_path):
     _check_ems(code, tmp_path, lch[:4], 8, 3, 1.0, 0.5, env={"NBLDPC_WARP_GENERIC": "1"})
 
 
-@pytest.mark.parametrize("q", [32, 64, 128])
+@pytest.mark.parametrize("q", [16, 32, 64, 128])
 @pytest.mark.parametrize("regular", [True, False])
 def test_qspa_warp_kernel_random_codes(q, regular, tmp_path):
-    """the QSPA warp kernel (qspa_warp.cuh) against the oracle's log-domain box-plus: decisions and iteration counts
+    """the QSPA warp kernel (qspa_warp.cuh; q = 16: the half-warp kernel, qspa_half.cuh) against the oracle's log-domain box-plus: decisions and iteration counts
     identical, posteriors to 1e-6 on the part above the transform's noise floor"""
     from nbldpc_b200 import capi
     from oracle import pyoracle as po
@@ -204,6 +204,29 @@ def test_qspa_warp_kernel_random_codes(q, regular, tmp_path):
     sel = ref > -25.0
     err = np.abs(r["post"] - ref)[sel] / np.maximum(np.abs(ref[sel]), 1.0)
     assert err.max() < 1e-6, err.max()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("name", ["cfg1_qspa_gf16", "cfg1_qspa_gf16_allzero"])
+def test_qspa_half_warp_and_group_kernels_are_bit_identical(name, precision, code_files):
+    """GF(16): the half-warp kernel (registers and shuffles only) and the group kernel agree bit for bit, posteriors included"""
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)
+    outs = []
+    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
+        os.environ.update(env)
+        try:
+            dec = capi.Decoder(code, 1, meta["max_iter"], precision=precision, max_batch=len(lch))
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        outs.append(dec.decode(lch, want_post=True))
+    for k in ("sym", "converged", "iterations", "post"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    if precision == capi.PREC_F64:
+        assert np.array_equal(outs[0]["sym"], z["dec_sym"].astype(np.int32))
 
 
 @pytest.mark.parametrize("precision", [0, 1])
