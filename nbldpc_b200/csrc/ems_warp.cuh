@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
     // ---- check node, one output edge at a time (NBLDPC.cpp:883-916) ------------------------------------------------------
     T *coutf = P.c2v_out + (size_t)f * g.E * Q + VEC * lane;
     const int no = dcn - 1;                                         // inputs taking part
-    const int combos = 1 << (lg * no);
 #pragma unroll
     for (int d = 0; d < TW_DC; ++d) {
         if (DC || d < dcn) {
