@@ -6,7 +6,7 @@
 
 Our arm.  One process per GPU (torchrun for N > 1).  A STEP is one pass of the hot path over one batch of
 `--frames` synthetic frames:
-  value : device Monte-Carlo step (nbl_simulate_async): random messages (Philox) -> device encoder -> AWGN -> soft demapper
+  value : device Monte-Carlo step (nbl_simulate_async): random messages (Philox) + CRC-8 -> device encoder -> AWGN -> soft demapper
           -> 10 fixed T-EMS iterations (early stop OFF, every frame pays all 10) -> error counters in HBM.
           Nothing crosses PCIe inside the timed region.  N > 1: frames are sharded by global frame index
           (weak scaling), no data-path collective; the 8 x u64 counter vector is all-reduced (NCCL) once at the
@@ -209,7 +209,7 @@ def main_ours(args):
 
     def sim_step(d, step):
         first = (step * world + rank) * B                      # disjoint global frame indices per rank and step
-        d.simulate_async(EBN0_DB, B, counters, seed=args.seed, first_frame=first, random_msg=1)   # every frame its own code word
+        d.simulate_async(EBN0_DB, B, counters, seed=args.seed, first_frame=first, random_msg=1, crc_len=8)   # every frame its own message + CRC-8 (the reference profile's crcLen)
 
     def timed(fn, steps, warmup, after=None):
         for i in range(warmup):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NBL_ABI_VERSION 2
+#define NBL_ABI_VERSION 3
 
 typedef enum {
     NBL_OK = 0,
@@ -189,9 +189,10 @@ int nbl_encode_batch(nbl_encoder *enc, const int *msg, int B, int *code_sym);
 #define NBL_CNT_ERR_SYMS 2
 #define NBL_CNT_ERR_BITS 3
 #define NBL_CNT_CONVERGED 4   /* decoder returned 1                                         */
-#define NBL_CNT_UNDETECTED 5  /* converged to a wrong codeword                              */
+#define NBL_CNT_UNDETECTED 5  /* crc_len == 0: converged to a wrong codeword; crc_len > 0: the reference's U_errFrame --
+                                 message in error AND its CRC check passes (Comm.cpp:462-469)  */
 #define NBL_CNT_ITERATIONS 6  /* sum of iteration counts                                    */
-#define NBL_CNT_RESERVED 7
+#define NBL_CNT_CRC_OK 7      /* crc_len > 0: frames whose decoded message passes the CRC check */
 #define NBL_NUM_COUNTERS 8
 
 typedef struct {
@@ -207,6 +208,10 @@ typedef struct {
     int random_msg;             /* with n_codewords == 0: 1 = every frame draws its own K message symbols on the
                                    device (Philox keyed by (seed, frame index)) and encodes them there
                                    (the reference's randomMsg = 1, Comm.cpp:214-249 + CNBLDPC::Encode); 0 = all-zero */
+    int crc_len;                /* crcLen 0, 8, 16 or 24: with random_msg the last crc_len message bits are the CRC of the
+                                   others (CComm::CRCEncode, Comm.cpp:506-560), and the decoded message of every frame
+                                   is CRC-checked for NBL_CNT_UNDETECTED / NBL_CNT_CRC_OK (CComm::CrcCheck, :562-630;
+                                   like the reference: CRC24A on encode but CRC24B on check)                  */
 } nbl_sim_config;
 
 /* counters: host uint64[NBL_NUM_COUNTERS], ACCUMULATED into (caller zeroes). */

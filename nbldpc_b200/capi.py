@@ -41,7 +41,7 @@ class OsdConfig(C.Structure):
 class SimConfig(C.Structure):
     _fields_ = [("ebn0_db", C.c_double), ("modulation", C.c_int), ("constellation", C.c_void_p), ("seed", C.c_uint64),
                 ("first_frame", C.c_uint64), ("frames", C.c_uint64), ("codewords", C.c_void_p), ("n_codewords", C.c_int),
-                ("random_msg", C.c_int)]
+                ("random_msg", C.c_int), ("crc_len", C.c_int)]
 
 
 def lib_path():
@@ -288,18 +288,18 @@ class Decoder:
         _check(lib().nbl_demap_decode_batch(self._h, modulation, _ptr(y), B, _ptr(constellation), float(sigma), None, 0,
                                             _ptr(out_sym), _ptr(converged), _ptr(iterations)))
 
-    def simulate(self, ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, counters=None, random_msg=0):
+    def simulate(self, ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, counters=None, random_msg=0, crc_len=0):
         cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
         cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
-        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg))
+        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg), int(crc_len))
         cnt = counters if counters is not None else np.zeros(NUM_COUNTERS, np.uint64)
         _check(lib().nbl_simulate(self._h, C.byref(cfg), _ptr(cnt)))
         return cnt
 
-    def simulate_async(self, ebn0_db, frames, dev_counters, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, random_msg=0):
+    def simulate_async(self, ebn0_db, frames, dev_counters, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, random_msg=0, crc_len=0):
         cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
         cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
-        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg))
+        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg), int(crc_len))
         _check(lib().nbl_simulate_async(self._h, C.byref(cfg), _ptr(dev_counters)))
 
     def sync(self):

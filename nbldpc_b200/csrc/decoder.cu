@@ -958,6 +958,47 @@ __global__ void k_sim_message(int B, int K, int q, uint64_t seed, uint64_t first
         if (4 * j + h < K) msg[(size_t)f * K + 4 * j + h] = (uint8_t)(r[h] & (uint32_t)(q - 1));
 }
 
+// CRC generator taps as bit masks of the shift register (Comm.cpp:513-531): bit j set <=> G[j] = 1, j = 0..crc_len-1
+__device__ __host__ inline unsigned crc_taps(int crc_len, int type24) {
+    if (crc_len == 8) return 0x9Bu;                                 // x^8 + x^7 + x^4 + x^3 + x + 1
+    if (crc_len == 16) return 0x1021u;                              // x^16 + x^12 + x^5 + 1
+    if (crc_len == 24) return type24 ? 0x800063u : 0x864CFBu;       // CRC24B / CRC24A
+    return 0u;
+}
+// bit b of message symbol s is message bit s * p + b (LSB first, Comm.cpp:234-249)
+__device__ inline int msg_bit(const uint8_t *m, int p, int i) { return (m[i / p] >> (i % p)) & 1; }
+
+// CComm::CRCEncode (Comm.cpp:506-560): the last crc_len message bits become the CRC of the first K p - crc_len
+__global__ void k_sim_crc(int B, int K, int p, int crc_len, uint8_t *__restrict__ msg) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+    uint8_t *m = msg + (size_t)f * K;
+    const int n = K * p - crc_len;
+    const unsigned taps = crc_taps(crc_len, 0), top = 1u << (crc_len - 1), mask = (top << 1) - 1u;
+    unsigned reg = 0;
+    for (int i = 0; i < n; ++i) {
+        const unsigned fb = ((reg & top) ? 1u : 0u) ^ (unsigned)msg_bit(m, p, i);
+        reg = ((reg << 1) & mask & ~1u) ^ (fb ? (taps & ~1u) : 0u) | fb;          // reg[j] = reg[j-1] ^ (G[j] & fb), reg[0] = fb
+    }
+    for (int i = 0; i < crc_len; ++i) {
+        const int bit = (reg >> (crc_len - 1 - i)) & 1, pos = n + i;
+        m[pos / p] = (uint8_t)((m[pos / p] & ~(1u << (pos % p))) | ((unsigned)bit << (pos % p)));
+    }
+}
+
+// CComm::CrcCheck (Comm.cpp:562-630) on the K p decoded message bits
+__device__ inline bool crc_check(const int *sym, int K, int p, int crc_len) {
+    const unsigned taps = crc_taps(crc_len, 1), top = 1u << (crc_len - 1), mask = (top << 1) - 1u;
+    unsigned reg = 0; int ones = 0;
+    for (int i = 0; i < K * p; ++i) {
+        const unsigned in = (unsigned)((sym[i / p] >> (i % p)) & 1);
+        const unsigned fb = (reg & top) ? 1u : 0u;
+        reg = ((reg << 1) & mask & ~1u) ^ (fb ? (taps & ~1u) : 0u) | (fb ^ in);
+        ones += (int)in;
+    }
+    return reg == 0 && ones != 0;                                   // an all-zero sequence never passes (Comm.cpp:618-628)
+}
+
 // received samples of B frames.  BPSK: y[f][N*p] = (1 - 2 bit) + sigma n  (0 -> +1, 1 -> -1, BPSK.txt; bit b of
 // symbol s is sample s*p+b, Comm.cpp:272-279).  QAM: y[f][N][2] = constellation[symbol] + sigma (n_re, n_im).
 __global__ void k_sim_channel(int B, int N, int p, int modulation, uint64_t seed, uint64_t first_frame, double sigma,
@@ -986,7 +1027,7 @@ __global__ void k_sim_channel(int B, int N, int p, int modulation, uint64_t seed
 }
 
 // CComm::Err (Comm.cpp:446-503) per frame on the first K symbols, accumulated into uint64 counters
-__global__ void k_sim_count(int B, int N, int K, const uint8_t *__restrict__ tx,
+__global__ void k_sim_count(int B, int N, int K, int p, int crc_len, const uint8_t *__restrict__ tx,
                             const int *__restrict__ out_sym, const int *__restrict__ conv, const int *__restrict__ iters,
                             unsigned long long *counters) {
     __shared__ unsigned long long acc[NBL_NUM_COUNTERS];
@@ -1003,7 +1044,11 @@ __global__ void k_sim_count(int B, int N, int K, const uint8_t *__restrict__ tx,
         atomicAdd(&acc[NBL_CNT_FRAMES], 1ULL);
         if (es) { atomicAdd(&acc[NBL_CNT_ERR_FRAMES], 1ULL); atomicAdd(&acc[NBL_CNT_ERR_SYMS], (unsigned long long)es); atomicAdd(&acc[NBL_CNT_ERR_BITS], (unsigned long long)eb); }
         if (conv[f]) atomicAdd(&acc[NBL_CNT_CONVERGED], 1ULL);
-        if (conv[f] && es) atomicAdd(&acc[NBL_CNT_UNDETECTED], 1ULL);
+        if (crc_len > 0) {
+            const bool ok = crc_check(out_sym + (size_t)f * N, K, p, crc_len);
+            if (ok) atomicAdd(&acc[NBL_CNT_CRC_OK], 1ULL);
+            if (ok && es) atomicAdd(&acc[NBL_CNT_UNDETECTED], 1ULL);
+        } else if (conv[f] && es) atomicAdd(&acc[NBL_CNT_UNDETECTED], 1ULL);
         atomicAdd(&acc[NBL_CNT_ITERATIONS], (unsigned long long)iters[f]);
     }
     __syncthreads();
@@ -1040,10 +1085,12 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
     const size_t ydbl = (size_t)d->cfg.max_batch * ylen * (cfg->modulation == 2 ? 1 : 2);
     if ((rc = ensure_ystage(d, ydbl * sizeof(double)))) return rc;
     const bool rnd = cfg->n_codewords == 0 && cfg->random_msg != 0;
-    if (rnd && d->osd_on && d->osd.order >= 0 && d->osd_cfg.crc_correct_len > 0) {
-        // k_sim_message draws K free symbols; the CRC rows of the OSD matrix would then constrain bits that carry no CRC
-        nbl_set_error("nbl_simulate: random messages carry no CRC on the device; use OSD with crc_correct_len = 0, a codeword pool "
-                      "encoded with the CRC (host harness), or the all-zero code word");
+    if (cfg->crc_len != 0 && cfg->crc_len != 8 && cfg->crc_len != 16 && cfg->crc_len != 24) { nbl_set_error("nbl_simulate: crc_len must be 0, 8, 16 or 24"); return NBL_ERR_ARG; }
+    if (cfg->crc_len >= K * p) { nbl_set_error("nbl_simulate: crc_len does not fit into the message"); return NBL_ERR_ARG; }
+    if (rnd && d->osd_on && d->osd.order >= 0 && d->osd_cfg.crc_correct_len > 0 && cfg->crc_len != d->osd_cfg.crc_len) {
+        // the CRC rows of the OSD matrix constrain the last message bits: the messages must carry that CRC
+        nbl_set_error("nbl_simulate: OSD with CRC rows needs messages with the same CRC: set nbl_sim_config.crc_len = nbl_osd_config.crc_len "
+                      "(or use crc_correct_len = 0)");
         return NBL_ERR_ARG;
     }
     if (!d->d_tx) CK(cudaMalloc((void **)&d->d_tx, (size_t)d->cfg.max_batch * N));
@@ -1060,6 +1107,11 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
             const long long nm = (long long)B * ((K + 3) / 4);
             k_sim_message<<<(unsigned)((nm + 255) / 256), 256, 0, d->stream>>>(B, K, q, cfg->seed, cfg->first_frame + done, d->d_msg);
             CK(cudaGetLastError());
+            if (cfg->crc_len > 0) {
+                k_sim_crc<<<(B + 127) / 128, 128, 0, d->stream>>>(B, K, p, cfg->crc_len, d->d_msg);
+                CK(cudaGetLastError());
+                launches += 1;
+            }
             if ((rc = nbl_encoder_launch_u8(d->sim_enc, d->d_msg, B, d->d_tx, d->stream))) return rc;
             launches += 1;
         } else {
@@ -1072,7 +1124,7 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
         if ((rc = demap_common(d, cfg->modulation, d->d_ystage, B, d->d_cons, sigma, nullptr, 0, true, nullptr))) return rc;
         rc = d->cfg.precision == NBL_PREC_F64 ? run_decode<double>(d, B, nullptr) : run_decode<float>(d, B, nullptr);
         if (rc) return rc;
-        k_sim_count<<<(B + 127) / 128, 128, 0, d->stream>>>(B, N, K, d->d_tx, d->d_out, d->d_conv, d->d_iters, dev_counters);
+        k_sim_count<<<(B + 127) / 128, 128, 0, d->stream>>>(B, N, K, p, cfg->crc_len, d->d_tx, d->d_out, d->d_conv, d->d_iters, dev_counters);
         CK(cudaGetLastError());
         launches += d->last_launches + 4;
         done += B;

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(capi.lib_path())
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert capi.lib().nbl_abi_version() == 2
+    assert capi.lib().nbl_abi_version() == 3
 
 
 def test_gf_tables_match_oracle_and_reference_files():

@@ -102,7 +102,7 @@ def test_gpu_osd_random_codes_against_oracle(q, order, crc, rate, alpha, flag, t
 @pytest.mark.gpu
 def test_device_monte_carlo_with_osd(code_files):
     """nbl_simulate with OSD enabled: the same frames (same seed) lose frame errors, never gain one on a frame that
-    converged, and the CRC-row variant is refused for device-drawn messages (they carry no CRC)"""
+    converged; the CRC-row variant is refused unless the device-drawn messages carry that CRC (crc_len)"""
     from nbldpc_b200 import capi
     code = load_product_code(code_files, "divsalar.UNBLDPC.128.64.GF.16")
     frames = 20000
@@ -114,8 +114,39 @@ def test_device_monte_carlo_with_osd(code_files):
     assert int(osd[4]) == int(plain[4])                     # converged frames: untouched
     assert 0 < int(osd[1]) < int(plain[1]), (plain, osd)    # frame errors: some failed frames are now the transmitted code word
     dec.enable_osd(1, 1.0, 0, 8, 8)
-    with pytest.raises(Exception, match="no CRC"):
+    with pytest.raises(Exception, match="same CRC"):
         dec.simulate(2.0, 1000, seed=3, random_msg=1)
+    crc_rows = dec.simulate(2.0, frames, seed=3, random_msg=1, crc_len=8)     # messages now carry the CRC the rows check
     dec.enable_osd(-1)
+    crc_plain = dec.simulate(2.0, frames, seed=3, random_msg=1, crc_len=8)
+    assert 0 < int(crc_rows[1]) < int(crc_plain[1])
     again = dec.simulate(2.0, frames, seed=3, random_msg=1)
     assert np.array_equal(again, plain)
+
+
+@pytest.mark.gpu
+def test_device_monte_carlo_crc(code_files):
+    """crc_len in nbl_simulate: CComm::CRCEncode on the device-drawn messages, CComm::CrcCheck on every decoded message.
+    Pinned to the reference from both sides: code words the REFERENCE transmitted (golden fixture, CRC-8 inside) pass the
+    device check, and so do the device's own messages; with errors, the identity
+    CRC passes == error-free frames + undetected frames holds and undetected frames are a ~2^-8 fraction."""
+    from nbldpc_b200 import capi
+    z, meta = load_golden("cfg1_qspa_gf16")
+    assert meta["crc"] == 8
+    code = load_product_code(code_files, meta["code"])
+    dec = capi.Decoder(code, capi.METHOD_QSPA, 10, precision=capi.PREC_F32, max_batch=20000)
+    pool = z["tx_code_sym"].astype(np.int32)
+    c = dec.simulate(9.0, 4800, seed=5, codewords=pool, crc_len=8)
+    assert int(c[1]) == 0 and int(c[7]) == 4800, c
+    c = dec.simulate(9.0, 4800, seed=5, random_msg=1, crc_len=8)
+    assert int(c[1]) == 0 and int(c[7]) == 4800, c
+    c = dec.simulate(9.0, 4800, seed=5, random_msg=1, crc_len=0)
+    assert int(c[7]) == 0
+    c = dec.simulate(1.0, 20000, seed=5, random_msg=1, crc_len=8)
+    frames, err, und, ok = int(c[0]), int(c[1]), int(c[5]), int(c[7])
+    assert err > 5000 and ok == frames - err + und, c
+    assert und < err / 40, c                                  # about err / 256
+    for crc in (16, 24):
+        c = dec.simulate(9.0, 2000, seed=5, random_msg=1, crc_len=crc)
+        assert int(c[1]) == 0
+        assert int(c[7]) == (2000 if crc == 16 else 0)        # crcLen 24: CRC24A on encode, CRC24B on check (SURVEY Q8), as the reference
