@@ -333,34 +333,45 @@ __device__ void cn_tems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, in
 // The subset enumeration is tiny (2^n_m leaves) and its running sum is formed by add / subtract exactly in the
 // reference's order, so one thread walks it with the same recursion; everything around it is data parallel.
 template <typename T, int Q> struct BsWalk {
+    // BasicSet_TEMS_ConstructConf (NBLDPC.cpp:2102-2147) without the recursion: element `lvl` of the basic set is first
+    // included (if its column is free and the deviation budget allows), then excluded; the running sum is added to on the
+    // way down and subtracted from on the way back exactly as the reference does, so its rounding residue is the same.
+    // st[lvl]: 0 = not visited yet, 1 = inside the "included" subtree, 2 = inside the "excluded" subtree.
     TemsSmem<T, Q> &S;
     int nm, nc, dcn;
-    unsigned col_sel; int diff, sum_sym; T sum;
-    uint8_t cand[16];
-    __device__ void walk(int begin) {
-        if (begin >= nm) {
-            if (sum < S.dW[sum_sym]) {
-                S.dW[sum_sym] = sum;
-                for (int d = 0; d < dcn; ++d) S.eta[d * Q + sum_sym] = cand[d];
+    __device__ void walk() {
+        unsigned col_sel = 0; int diff = 0, sum_sym = 0; T sum = T(0);
+        uint8_t cand[16], st[17];
+        for (int d = 0; d < 16; ++d) cand[d] = 0;
+        int lvl = 0;
+        st[0] = 0;
+        while (lvl >= 0) {
+            if (lvl == nm) {                                        // a leaf: strict '<' keeps the first of equal costs
+                if (sum < S.dW[sum_sym]) {
+                    S.dW[sum_sym] = sum;
+                    for (int d = 0; d < dcn; ++d) S.eta[d * Q + sum_sym] = cand[d];
+                }
+                --lvl;
+                continue;
             }
-            return;
-        }
-        const int col = S.pb[begin], bq = S.lb[begin];
-        const T bL = S.lc[begin];
-        if (!((col_sel >> col) & 1)) {
-            diff += 1;
-            if (diff <= nc) {
-                col_sel |= 1u << col;
-                sum_sym ^= bq; sum = sum + bL; cand[col] = (uint8_t)bq;
-                walk(begin + 1);
+            const int col = S.pb[lvl], bq = S.lb[lvl];
+            const T bL = S.lc[lvl];
+            if (st[lvl] == 0) {
+                if (!((col_sel >> col) & 1)) {
+                    if (diff + 1 <= nc) {                           // include first
+                        diff += 1; col_sel |= 1u << col;
+                        sum_sym ^= bq; sum = sum + bL; cand[col] = (uint8_t)bq;
+                        st[lvl] = 1;
+                    } else { cand[col] = 0; st[lvl] = 2; }          // budget spent: excluded subtree only
+                } else st[lvl] = 2;                                 // column already deviates: this element cannot be added
+                ++lvl; st[lvl] = 0;
+            } else if (st[lvl] == 1) {                              // back from the included subtree: undo, then exclude
                 sum_sym ^= bq; sum = sum - bL; col_sel &= ~(1u << col);
                 diff -= 1; cand[col] = 0;
-                walk(begin + 1);
-            } else {
-                diff -= 1; cand[col] = 0;
-                walk(begin + 1);
-            }
-        } else walk(begin + 1);
+                st[lvl] = 2;
+                ++lvl; st[lvl] = 0;
+            } else --lvl;
+        }
     }
 };
 
@@ -418,8 +429,8 @@ __device__ void cn_bstems(TemsSmem<T, Q> &S, const DevGraph &g, int gid, int x, 
     }
     Grp<Q>::sync(gid);
     if (x == 0) {
-        BsWalk<T, Q> wk{S, found, nc, dcn, 0u, 0, 0, T(0), {0}};
-        wk.walk(0);
+        BsWalk<T, Q> wk{S, found, nc, dcn};
+        wk.walk();
     }
     Grp<Q>::sync(gid);                                              // deltaW / Eta complete; V is free from here on
     T *Tout = S.V;
