@@ -277,7 +277,7 @@ struct nbl_decoder {
     int it_recorded = 0;
     float last_ms = 0; int last_launches = 0;
     size_t smem_iter = 0;
-    bool warp_path = false;      // T-EMS n_c <= 2, dc <= 4, q >= 32: one warp per check row (tems_warp.cuh)
+    bool warp_path = false;      // T-EMS n_c <= 2 or BS-TEMS, dc <= 4, q >= 32: one warp per check row (tems_warp.cuh)
     bool qspa_warp_path = false; // QSPA, dc <= 4, q >= 32: one warp per check row (qspa_warp.cuh)
     bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
@@ -446,6 +446,8 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_BITEXACT) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
     const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || cfg->tie_mode == NBL_TIES_BITEXACT || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
     d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
+    // BS-TEMS on the same kernel (its search replaced by the basic-set walk): no tie modes, the walk is the reference's own
+    if (cfg->method == NBL_METHOD_BSTEMS && desc_ok && q >= 32 && cfg->offset >= 0.0 && !getenv("NBLDPC_FORCE_GENERIC")) d->warp_path = true;
     {
         const bool pow2 = cfg->p0 >= 1 && (cfg->p0 & (cfg->p0 - 1)) == 0;
         long long combos = 1;
@@ -511,8 +513,8 @@ template <typename T, int Q, int METHOD> static int launch_iterate_tqm(nbl_decod
     CK(cudaGetLastError());
     return NBL_OK;
 }
-template <typename T, int Q, int DC, int DV> static int launch_iterate_warp_dc(nbl_decoder *d, const IterParams<T> &P) {
-    auto kern = k_iterate_tems_warp<T, Q, DC, DV>;
+template <typename T, int Q, int DC, int DV, int BS = 0> static int launch_iterate_warp_dc(nbl_decoder *d, const IterParams<T> &P) {
+    auto kern = k_iterate_tems_warp<T, Q, DC, DV, BS>;
     constexpr size_t smem = TwSmem<T, Q>::bytes;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // grid: x = group of TW_WARPS check rows (fastest, so that the rows of a frame -- which share messages -- run together),
@@ -524,6 +526,8 @@ template <typename T, int Q, int DC, int DV> static int launch_iterate_warp_dc(n
 }
 template <typename T, int Q> static int launch_iterate_warp(nbl_decoder *d, const IterParams<T> &P) {
     if constexpr (Q >= 32) {
+        if (d->cfg.method == NBL_METHOD_BSTEMS)
+            return d->warp_regular ? launch_iterate_warp_dc<T, Q, TW_DC, TW_HOIST, 1>(d, P) : launch_iterate_warp_dc<T, Q, 0, 0, 1>(d, P);
         return d->warp_regular ? launch_iterate_warp_dc<T, Q, TW_DC, TW_HOIST>(d, P) : launch_iterate_warp_dc<T, Q, 0, 0>(d, P);
     } else {
         nbl_set_error("internal: warp path needs q >= 32");

@@ -344,8 +344,10 @@ template <typename T, int VEC> __device__ __forceinline__ void ld_blk(const unsi
 
 // DC > 0: every check row has exactly DC edges (no degree guards in the unrolled stages); DC == 0: row degree from the
 // descriptor.  DV > 0: every variable has exactly DV <= TW_HOIST edges; DV == 0: variable degree from the descriptor.
-template <typename T, int Q, int DC, int DV>
-__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MINB_VALUE : 1) k_iterate_tems_warp(const IterParams<T> P) {
+// BS == 1: BS-TEMS (decode method 7) -- same variable-node step, delta domain, column order, fill-in and output stage; the
+// pair search is replaced by the basic-set construction and the walk over its subsets (see the BS block below).
+template <typename T, int Q, int DC, int DV, int BS = 0>
+__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_MINB_VALUE) : 1) k_iterate_tems_warp(const IterParams<T> P) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
     using S = TwSmem<T, Q>;
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MINB_VALUE 
         const T second_ok = P.p0 >= 2 ? T(0) : INF;                 // n_r = 1: only the cheapest column may deviate
 #pragma unroll
         for (int c = 0; c < TW_DC; ++c) {
-            if (DC || c < dcn) {                                    // D_c[x]: cheapest allowed column of x other than c
+            if (!BS && (DC || c < dcn)) {                           // D_c[x]: cheapest allowed column of x other than c
                 T dcv[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
@@ -524,100 +526,212 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? TW_MINB_VALUE 
         }
     }
     __syncwarp();
-    // ---- pair search: best[s] = min_a m0(a) + D_{c0(a)}[s ^ a] ----------------------------------------------------------
-    T best[VEC]; int tag[VEC];
-#pragma unroll
-    for (int r = 0; r < VEC; ++r) { best[r] = INF; tag[r] = 0; }
-    if (P.p1 >= 2) {
-#pragma unroll 1
-        for (int bh = 0; bh < 32; ++bh) {
-            // one eta-block: best = min(best, candidates of the block); tag the block where it got smaller
-            T cost[VEC]; unsigned cls;
-            ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);   // warp-uniform operands of the block's entries
-#if TW_UNIFORM_CLS
-            cls = __reduce_or_sync(0xffffffffu, cls);               // same value, but now provably uniform: uniform branches below
-#endif
-            const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
-            T nb[VEC];
-            if constexpr (VEC >= 2) {
-                constexpr int NP2 = VEC / 2;
-                Pair2<T> pc[TW_DC][NP2];
-#pragma unroll
-                for (int c = 0; c < TW_DC; ++c) ld_pairs<VEC>(Dk + c * VB, pc[c]);
-                entry_pair<T, VEC, 0>(cls, cost, pc, best, nb);
-                if constexpr (VEC > 2) entry_pair<T, VEC, 2>(cls, cost, pc, best, nb);
-                if constexpr (VEC > 4) { entry_pair<T, VEC, 4>(cls, cost, pc, best, nb); entry_pair<T, VEC, 6>(cls, cost, pc, best, nb); }
-            } else {
-                const T p = *reinterpret_cast<const T *>(Dk + (cls & 3) * VB);
-                nb[0] = fmin(best[0], p + cost[0]);
-            }
-#pragma unroll
-            for (int r = 0; r < VEC; ++r) { if (nb[r] < best[r]) tag[r] = bh; best[r] = nb[r]; }
-        }
-    }
-    // ---- deltaW and the recorded path of each owned s --------------------------------------------------------------------
-    // single deviation: (s, c0(s));  pair: a in column ca, b = s ^ a in column cb, costs ua = m0(a), ub = D_ca[b]
-    unsigned path[VEC];   // swz(a) | swz(b) << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
-    T va[VEC], vb[VEC];                                             // dw - ua, dw - ub of pair paths
     const unsigned long long c01w = ld_bytes<VEC>(c01 + x0);
-    {
-        T m0[VEC];
-        ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0);
-        if (lane == 0) m0[0] = T(0);
+    T *Tout = R1;
+    if constexpr (!BS) {
+        // ---- pair search: best[s] = min_a m0(a) + D_{c0(a)}[s ^ a] ----------------------------------------------------------
+        T best[VEC]; int tag[VEC];
+#pragma unroll
+        for (int r = 0; r < VEC; ++r) { best[r] = INF; tag[r] = 0; }
+        if (P.p1 >= 2) {
+#pragma unroll 1
+            for (int bh = 0; bh < 32; ++bh) {
+                // one eta-block: best = min(best, candidates of the block); tag the block where it got smaller
+                T cost[VEC]; unsigned cls;
+                ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);   // warp-uniform operands of the block's entries
+#if TW_UNIFORM_CLS
+                cls = __reduce_or_sync(0xffffffffu, cls);               // same value, but now provably uniform: uniform branches below
+#endif
+                const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
+                T nb[VEC];
+                if constexpr (VEC >= 2) {
+                    constexpr int NP2 = VEC / 2;
+                    Pair2<T> pc[TW_DC][NP2];
+#pragma unroll
+                    for (int c = 0; c < TW_DC; ++c) ld_pairs<VEC>(Dk + c * VB, pc[c]);
+                    entry_pair<T, VEC, 0>(cls, cost, pc, best, nb);
+                    if constexpr (VEC > 2) entry_pair<T, VEC, 2>(cls, cost, pc, best, nb);
+                    if constexpr (VEC > 4) { entry_pair<T, VEC, 4>(cls, cost, pc, best, nb); entry_pair<T, VEC, 6>(cls, cost, pc, best, nb); }
+                } else {
+                    const T p = *reinterpret_cast<const T *>(Dk + (cls & 3) * VB);
+                    nb[0] = fmin(best[0], p + cost[0]);
+                }
+#pragma unroll
+                for (int r = 0; r < VEC; ++r) { if (nb[r] < best[r]) tag[r] = bh; best[r] = nb[r]; }
+            }
+        }
+        // ---- deltaW and the recorded path of each owned s --------------------------------------------------------------------
+        // single deviation: (s, c0(s));  pair: a in column ca, b = s ^ a in column cb, costs ua = m0(a), ub = D_ca[b]
+        unsigned path[VEC];   // swz(a) | swz(b) << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
+        T va[VEC], vb[VEC];                                             // dw - ua, dw - ub of pair paths
+        {
+            T m0[VEC];
+            ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0);
+            if (lane == 0) m0[0] = T(0);
+#pragma unroll
+            for (int r = 0; r < VEC; ++r) {
+                const int s = x0 + r;
+                va[r] = T(0); vb[r] = T(0);
+                path[r] = s == 0 ? 0u : (0x100000u << (byte_of(c01w, r) & 15));
+                const bool pair = best[r] < m0[r];                      // never for s == 0 (m0 = 0)
+                if (!pair) best[r] = m0[r];                             // from here on best = deltaW
+                else {
+                    // recover the pair from the winning block: the first entry in search order that attains the minimum
+                    const int bh = tag[r], k = lane ^ bh;
+                    T cost[VEC]; unsigned cls;
+                    ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);
+                    const unsigned char *Dk = slab + k * (PL::E16 * (int)sizeof(T));
+                    int bl0 = 0; T ub = T(0), ua = T(0);
+#pragma unroll
+                    for (int bl = VEC - 1; bl >= 0; --bl) {             // descending: the smallest matching eta remains
+                        constexpr int E16 = PL::E16;
+                        const int j = r ^ bl;
+                        const int cofs = (int)((cls >> (2 * bl)) & 3u) * VB;
+                        const T dv = *reinterpret_cast<const T *>(Dk + cofs + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
+                        if (dv + cost[bl] == best[r]) { bl0 = bl; ub = dv; ua = cost[bl]; }
+                    }
+                    const int aa = VEC * bh + bl0, bb = s ^ aa;
+                    const int ca = (cls >> (2 * bl0)) & 3, kb = c01[bb];
+                    const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
+                    va[r] = best[r] - ua; vb[r] = best[r] - ub;
+                    const unsigned sa = (unsigned)PL::index(bh, bl0), sb = (unsigned)PL::index(lane, r) ^ sa;   // the layout is linear
+                    path[r] = sa | (sb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
+                }
+            }
+        }
+        __syncwarp();                                                  // everyone is done with D
+        // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
+#pragma unroll
+        for (int d = 0; d < TW_DC; ++d) {
+            if (DC || d < dcn) {
+                T tv[VEC];
+#pragma unroll
+                for (int r = 0; r < VEC; ++r) tv[r] = (path[r] & (0x100000u << d)) ? INF : best[r];
+                st_split<T, VEC>(Tout + d * Q, lane, tv);
+            }
+        }
+        __syncwarp();
+        // ... then the entries of two-deviation paths, which land on another index (values are >= 0: ordered like their bits)
 #pragma unroll
         for (int r = 0; r < VEC; ++r) {
-            const int s = x0 + r;
-            va[r] = T(0); vb[r] = T(0);
-            path[r] = s == 0 ? 0u : (0x100000u << (byte_of(c01w, r) & 15));
-            const bool pair = best[r] < m0[r];                      // never for s == 0 (m0 = 0)
-            if (!pair) best[r] = m0[r];                             // from here on best = deltaW
-            else {
-                // recover the pair from the winning block: the first entry in search order that attains the minimum
-                const int bh = tag[r], k = lane ^ bh;
-                T cost[VEC]; unsigned cls;
-                ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);
-                const unsigned char *Dk = slab + k * (PL::E16 * (int)sizeof(T));
-                int bl0 = 0; T ub = T(0), ua = T(0);
-#pragma unroll
-                for (int bl = VEC - 1; bl >= 0; --bl) {             // descending: the smallest matching eta remains
-                    constexpr int E16 = PL::E16;
-                    const int j = r ^ bl;
-                    const int cofs = (int)((cls >> (2 * bl)) & 3u) * VB;
-                    const T dv = *reinterpret_cast<const T *>(Dk + cofs + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
-                    if (dv + cost[bl] == best[r]) { bl0 = bl; ub = dv; ua = cost[bl]; }
-                }
-                const int aa = VEC * bh + bl0, bb = s ^ aa;
-                const int ca = (cls >> (2 * bl0)) & 3, kb = c01[bb];
-                const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
-                va[r] = best[r] - ua; vb[r] = best[r] - ub;
-                const unsigned sa = (unsigned)PL::index(bh, bl0), sb = (unsigned)PL::index(lane, r) ^ sa;   // the layout is linear
-                path[r] = sa | (sb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
+            if (path[r] >> 24) {
+                const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 3, cb = (path[r] >> 18) & 3;
+                atomic_min_nonneg(Tout + ca * Q + b, va[r]);
+                atomic_min_nonneg(Tout + cb * Q + a, vb[r]);
             }
         }
-    }
-    __syncwarp();                                                  // everyone is done with D
-    // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
-    T *Tout = R1;
+        __syncwarp();
+    } else {
+        // ---- BS-TEMS (Decoding_BS_TEMS, NBLDPC.cpp:1145-1396).  As the reference runs it the T-EMS stage only leaves the
+        //      all-zero configuration (TEMS_Nr is never set in this mode); every other syndrome is reached by a subset of the
+        //      BASIC SET or takes the fill-in value.
+        // (a) Construct_BasicSet (:2023-2101): the n_m cheapest eta != 0 by m0(eta), lowest eta among equals; when
+        //     n_m <= log2 q chosen greedily so that they stay linearly independent over GF(2) (a span flag per eta).
+        //     Element k of the set lives on lane k: eta, its cheapest column, its cost.
+        const int nm = P.p0, nc = P.p1;
+        T rc[VEC];                                                  // m0 of my etas, +inf at eta = 0
+        ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), rc);
+        unsigned avail = (1u << VEC) - 1u, span = 0u;
+        int found = 0, my_bq = 0, my_col = 0; T my_bL = T(0);
+        for (int k = 0; k < nm; ++k) {
+            T lm = INF; int lj = 0;
 #pragma unroll
-    for (int d = 0; d < TW_DC; ++d) {
-        if (DC || d < dcn) {
-            T tv[VEC];
+            for (int j = VEC - 1; j >= 0; --j) if (((avail >> j) & 1u) && rc[j] <= lm) { lm = rc[j]; lj = j; }
+            if (!(lm < INF)) lj = 0;
+            T wm = lm;
 #pragma unroll
-            for (int r = 0; r < VEC; ++r) tv[r] = (path[r] & (0x100000u << d)) ? INF : best[r];
-            st_split<T, VEC>(Tout + d * Q, lane, tv);
+            for (int o = 16; o; o >>= 1) wm = fmin(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+            if (!(wm < INF)) break;                                 // nothing left (n_m > number of candidates); warp-uniform
+            const int src = __ffs(__ballot_sync(0xffffffffu, lm == wm)) - 1;
+            const int w = VEC * src + __shfl_sync(0xffffffffu, lj, src);
+            const int wcol = c01[w] & 15;
+            found = k + 1;
+            if (lane == k) { my_bq = w; my_col = wcol; my_bL = wm; }
+            if (nm > g.p) { if (lane == src) avail &= ~(1u << lj); }
+            else {                                                  // span of the chosen elements: in[x] = in[x] | in[x ^ w] | (x == w)
+                const unsigned other = __shfl_sync(0xffffffffu, span, lane ^ (w / VEC));
+                unsigned moved = 0u;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) moved |= ((other >> (j ^ (w % VEC))) & 1u) << j;
+                span |= moved | (lane == src ? (1u << lj) : 0u);
+                avail &= ~span;
+            }
         }
-    }
-    __syncwarp();
-    // ... then the entries of two-deviation paths, which land on another index (values are >= 0: ordered like their bits)
+        // (b) BasicSet_TEMS_ConstructConf (:2102-2147): one lane walks the subsets (<= n_c elements, no column twice) with the
+        //     reference's include-first order and its add / subtract running sum; deltaW and the recorded subset per syndrome
+        //     go through the (now unused) D area: dWs[eta], sets[eta] = index + 1 of the basic element per column.
+        T *dWs = R1;
+        unsigned *sets = reinterpret_cast<unsigned *>(R1 + Q);
+        int *bsq = reinterpret_cast<int *>(sets + Q); int *bsc = bsq + 16; T *bsl = reinterpret_cast<T *>(bsc + 16);
+        {
+            T dinit[VEC];
 #pragma unroll
-    for (int r = 0; r < VEC; ++r) {
-        if (path[r] >> 24) {
-            const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 3, cb = (path[r] >> 18) & 3;
-            atomic_min_nonneg(Tout + ca * Q + b, va[r]);
-            atomic_min_nonneg(Tout + cb * Q + a, vb[r]);
+            for (int j = 0; j < VEC; ++j) { dinit[j] = (x0 + j == 0) ? T(0) : INF; sets[x0 + j] = 0u; }
+            st_vec<T, VEC>(dWs + x0, dinit);
+            if (lane < found) { bsq[lane] = my_bq; bsc[lane] = my_col; bsl[lane] = my_bL; }
         }
+        __syncwarp();
+        if (lane == 0) {
+            unsigned col_sel = 0u, cand = 0u; int diff = 0, sym = 0, lvl = 0; T sum = T(0);
+            uint8_t st[17];                                         // 0 = not visited, 1 = inside "included", 2 = inside "excluded"
+            st[0] = 0;
+            while (lvl >= 0) {
+                if (lvl == found) {                                 // a leaf: strict '<' keeps the first of equal costs
+                    if (sum < dWs[sym]) { dWs[sym] = sum; sets[sym] = cand; }
+                    --lvl;
+                    continue;
+                }
+                const int col = bsc[lvl], bq = bsq[lvl];
+                const T bL = bsl[lvl];
+                if (st[lvl] == 0) {
+                    if (!((col_sel >> col) & 1u)) {
+                        if (diff + 1 <= nc) {
+                            diff += 1; col_sel |= 1u << col;
+                            sym ^= bq; sum = sum + bL; cand |= (unsigned)(lvl + 1) << (8 * col);
+                            st[lvl] = 1;
+                        } else st[lvl] = 2;
+                    } else st[lvl] = 2;
+                    ++lvl; st[lvl] = 0;
+                } else if (st[lvl] == 1) {
+                    sym ^= bq; sum = sum - bL; col_sel &= ~(1u << col); cand &= ~(255u << (8 * col));
+                    diff -= 1;
+                    st[lvl] = 2;
+                    ++lvl; st[lvl] = 0;
+                } else --lvl;
+            }
+        }
+        __syncwarp();
+        const int my_bq_sw = PL::swz(my_bq);
+        T dw[VEC]; unsigned et[VEC];
+        ld_vec<T, VEC>(dWs + x0, dw);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) et[j] = sets[x0 + j];
+        __syncwarp();                                               // the D area becomes the output trellis
+        // (c) output trellis (NBLDPC.cpp:1364-1374): Tout[d][eta ^ eta_d] = min(deltaW[eta] - dU[d][eta_d]) over the reached eta
+        {
+            T inf_v[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) inf_v[j] = INF;
+#pragma unroll
+            for (int d = 0; d < TW_DC; ++d) if (DC || d < dcn) st_split<T, VEC>(Tout + d * Q, lane, inf_v);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < VEC; ++r) {
+#pragma unroll
+            for (int d = 0; d < TW_DC; ++d) {
+                const int k1 = (int)((et[r] >> (8 * d)) & 255u);    // basic element deviating in column d, + 1
+                const int ksrc = k1 ? k1 - 1 : 0;
+                const int dev_sw = __shfl_sync(0xffffffffu, my_bq_sw, ksrc);
+                const T du = __shfl_sync(0xffffffffu, my_bL, ksrc);
+                if ((DC || d < dcn) && dw[r] < INF) {               // the layout is linear over XOR: swz(s ^ dev) = swz(s) ^ swz(dev)
+                    const int t_sw = PL::index(lane, r) ^ (k1 ? dev_sw : 0);
+                    atomic_min_any(Tout + d * Q + t_sw, k1 ? dw[r] - du : dw[r] - T(0));   // the running sum's residue can make this negative
+                }
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     // ---- fill-in (NBLDPC.cpp:1095-1102): indices no path landed on take the smallest dU of the other columns -------------
     {
         T m0[VEC], m1[VEC];

@@ -248,3 +248,30 @@ def test_qspa_warp_and_group_kernels_are_bit_identical(precision, code_files):
         outs.append(dec.decode(lch, want_post=True))
     for k in ("sym", "converged", "iterations", "post"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("name", ["f2_bstems_gf256", "f2_bstems_gf64_nm9"])
+def test_bstems_warp_and_group_kernels_agree(name, precision, code_files):
+    """BS-TEMS on the warp kernel (tems_warp.cuh, BS = 1: basic-set rounds + one lane walking the subsets) and on the group
+    kernel (cn_bstems): same decisions, iteration counts and posteriors (both form every sum in the reference's order)"""
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)
+    outs = []
+    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
+        os.environ.update(env)
+        try:
+            dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                               precision=precision, max_batch=len(lch))
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        outs.append(dec.decode(lch, want_post=True))
+    for k in ("sym", "converged", "iterations"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert np.abs(outs[0]["post"] - outs[1]["post"]).max() < (1e-9 if precision == capi.PREC_F64 else 1e-3)
+    if precision == capi.PREC_F64:
+        assert np.array_equal(outs[0]["sym"], z["dec_sym"].astype(np.int32))
+        assert np.array_equal(outs[0]["iterations"], z["iters"].astype(np.int32))
