@@ -27,6 +27,8 @@
 //     h x ^ (syn ^ beta)  need no data-dependent table row, an address is  base ^ (byte ^ key) << 2  (one shift, one LOP3),
 //     and the scalar look-ups beta = h * decide(.) are two shuffles out of registers;
 //   * the search loop does one eta-block per trip so that its body stays inside the instruction cache.
+// BS-TEMS (decode method 7) runs on the same kernel with BS = 1: everything around the search is shared, the search itself
+// is replaced by the basic-set construction and the walk over its subsets (see the BS block in the kernel).
 #pragma once
 #include "dev_common.cuh"
 #include <type_traits>
