@@ -217,7 +217,9 @@ typedef struct {
 /* counters: host uint64[NBL_NUM_COUNTERS], ACCUMULATED into (caller zeroes). */
 int nbl_simulate(nbl_decoder *dec, const nbl_sim_config *cfg, uint64_t *counters);
 /* same, but leaves the sums in a device-resident uint64[8] (for an in-place NCCL all-reduce) and
- * does not synchronise; dev_counters is accumulated into. */
+ * does not synchronise; dev_counters is accumulated into.  All work is queued on the decoder's stream
+ * (nbl_decoder_stream): zero, reduce or read the counters on THAT stream, or after nbl_decoder_sync -- a decoder created
+ * with stream == NULL owns a non-blocking stream that the legacy default stream does not wait for. */
 int nbl_simulate_async(nbl_decoder *dec, const nbl_sim_config *cfg, uint64_t *dev_counters);
 
 /* timing hook: milliseconds the GPU spent in the decode kernels of the last nbl_decode_batch /

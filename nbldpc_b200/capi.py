@@ -297,6 +297,9 @@ class Decoder:
         return cnt
 
     def simulate_async(self, ebn0_db, frames, dev_counters, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, random_msg=0, crc_len=0):
+        """queues the whole call on the decoder's stream and returns; dev_counters (device int64/uint64[8]) is accumulated
+        into.  Touch the counters on the same stream (create the Decoder with stream=torch's current stream, as bench.py
+        does) or after sync() -- a private decoder stream is not ordered with torch's default stream."""
         cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
         cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
         cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg), int(crc_len))
