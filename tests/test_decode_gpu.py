@@ -149,3 +149,20 @@ def test_tems_bitexact_mode_reproduces_reference_posteriors_bit_for_bit(name, co
     assert np.array_equal(r["iterations"], z["iters"][:F].astype(np.int32))
     assert np.array_equal(r["sym"], z["dec_sym"][:F].astype(np.int32))
     assert np.array_equal(r["post"][:, :, z["lpost_idx"]], z["lpost_sample"][:F])
+
+
+def test_fp32_fer_matches_the_reference_anchor_points(code_files):
+    """The fp32 fast path at the operating points for which BASELINE.md holds FER figures of the reference itself:
+    H_bit_GF256, T-EMS 2/2/0.5, 3 dB, random messages: 54 / 2001 = 2.70e-2 (the reference's sample is small: +-3 sigma
+    = +-1.1e-2); BDS (576,288) GF(64), EMS 8/3/0.5, 2 dB: 3.25e-2.  200 k device frames each (sigma ~ 4e-4)."""
+    from nbldpc_b200 import capi
+    code = load_product_code(code_files, "H_bit_GF256")
+    dec = capi.Decoder(code, capi.METHOD_TEMS, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F32, max_batch=50000)
+    c = dec.simulate(3.0, 200000, seed=21, random_msg=1, crc_len=8)
+    fer = int(c[1]) / int(c[0])
+    assert 1.6e-2 < fer < 3.8e-2, fer
+    code = load_product_code(code_files, "BDS.576.288.GF.64")
+    dec = capi.Decoder(code, capi.METHOD_EMS, 10, 8, 3, 1.0, 0.5, precision=capi.PREC_F32, max_batch=50000)
+    c = dec.simulate(2.0, 200000, seed=21, random_msg=1, crc_len=8)
+    fer = int(c[1]) / int(c[0])
+    assert 2.6e-2 < fer < 3.9e-2, fer
