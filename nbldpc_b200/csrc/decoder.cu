@@ -58,6 +58,7 @@ template <typename T> struct IterParams {
 #include "qspa_warp.cuh"
 #include "osd.cuh"
 #include "qspa_half.cuh"
+#include "tems_half.cuh"
 
 // channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
 template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
@@ -281,6 +282,7 @@ struct nbl_decoder {
     bool qspa_warp_path = false; // QSPA, dc <= 4, q >= 32: one warp per check row (qspa_warp.cuh)
     bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
+    bool tems_half_path = false; // T-EMS n_c <= 2 over GF(16), dc <= 8, dv <= 4, not the reference tie order (tems_half.cuh)
     bool qspa_half_path = false; // QSPA over GF(16), dc <= 8, dv <= 4: four lanes per check row, eight rows per warp (qspa_half.cuh)
     int *d_rowdesc8 = nullptr;   // its row descriptors [M][QH_MAXDC][QH_DSC]
     // OSD post-processing of failed frames (osd.cuh); off until nbl_decoder_enable_osd
@@ -414,7 +416,8 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
             if ((rc = upload(&d->d_pfwd_sw, pfs)) || (rc = upload(&d->d_pinv_sw, pis))) return fail(rc);
         }
     }
-    if (q == 16 && cfg->method == NBL_METHOD_QSPA && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV && !getenv("NBLDPC_FORCE_GENERIC")) {
+    if (q == 16 && (cfg->method == NBL_METHOD_QSPA || cfg->method == NBL_METHOD_TEMS) && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV &&
+        !getenv("NBLDPC_FORCE_GENERIC")) {
         std::vector<int> rd((size_t)code->M * QH_MAXDC * QH_DSC, 0);
         for (int r = 0; r < code->M; ++r)
             for (int e = code->chk_ptr[r]; e < code->chk_ptr[r + 1]; ++e) {
@@ -424,7 +427,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
                 for (int s = code->var_ptr[v]; s < code->var_ptr[v + 1]; ++s) slot[2 + s - code->var_ptr[v]] = code->var_edge[s];
             }
         if ((rc = upload(&d->d_rowdesc8, rd))) return fail(rc);
-        d->qspa_half_path = true;
+        d->qspa_half_path = cfg->method == NBL_METHOD_QSPA;
     }
     d->g = DevGraph{q, code->p, N, code->M, E, code->max_dv, code->max_dc, d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_pfwd, d->d_pinv, d->d_rowdesc};
     const size_t B = cfg->max_batch;
@@ -446,6 +449,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_BITEXACT) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
     const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || cfg->tie_mode == NBL_TIES_BITEXACT || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
     d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
+    d->tems_half_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && q == 16 && d->d_rowdesc8 != nullptr && !ref_ties;
     // BS-TEMS on the same kernel (its search replaced by the basic-set walk): no tie modes, the walk is the reference's own
     if (cfg->method == NBL_METHOD_BSTEMS && desc_ok && q >= 32 && cfg->offset >= 0.0 && !getenv("NBLDPC_FORCE_GENERIC")) d->warp_path = true;
     {
@@ -570,6 +574,12 @@ template <typename T, int Q> static int launch_iterate_qspa_warp(nbl_decoder *d,
 }
 template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const IterParams<T> &P) {
     if constexpr (Q == 16) {
+        if (d->tems_half_path) {
+            const long long rows = (long long)P.B * P.g.M, per_cta = QH_ROWS * QH_WARPS;
+            k_iterate_tems_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, ThSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
+            CK(cudaGetLastError());
+            return NBL_OK;
+        }
         if (d->qspa_half_path) {
             const long long rows = (long long)P.B * P.g.M, per_cta = QH_ROWS * QH_WARPS;
             k_iterate_qspa_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, QhSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);

@@ -86,32 +86,46 @@ __device__ __forceinline__ void qh_wht(double (&v)[4], int l4) {
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_iterate_qspa_half(const IterParams<T> P, const int *__restrict__ desc) {
-    constexpr int Q = 16;
-    extern __shared__ __align__(16) unsigned char qh_raw[];
-    const DevGraph &g = P.g;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l4 = lane & 3, rw = lane >> 2, x0 = 4 * l4;            // my lane of the row, the row's slot in the warp, first element
-    T *sV = reinterpret_cast<T *>(qh_raw + QhSmem<T>::bytes_per_warp * warp) + rw * 16;
-    double *sR = reinterpret_cast<double *>(qh_raw + QhSmem<T>::bytes_per_warp * warp + QhSmem<T>::v_bytes) + rw * 16;
-    const long long nrows = (long long)P.B * g.M;
-    long long w = ((long long)blockIdx.x * QH_WARPS + warp) * QH_ROWS + rw;
-    bool active = w < nrows;
-    if (!active) w = nrows - 1;                                     // the lanes stay for the warp-wide shuffles; they store nothing
-    const int f = (int)(w / g.M), row = (int)(w % g.M);
-    if (P.early_stop && P.done[f]) active = false;
-    if (!__any_sync(QH_FULL, active)) return;                       // warp-uniform
+// What the two GF(16) kernels (QSPA here, T-EMS in tems_half.cuh) share: the row a lane works on, and steps A-C.
+template <typename T> struct QhRow {
+    int lane, l4, rw, x0;              // lane, my lane of the row (0..3), the row's slot in the warp (0..7), first element
+    bool active;                       // the row exists and its frame is still decoding
+    int f, row, e0, dcn, dmax;         // frame, check row, first edge, row degree (0 if inactive), longest row of the warp
+};
 
-    const int *rd = desc + (size_t)row * (QH_MAXDC * QH_DSC);
-    const int e0 = g.chk_ptr[row];
-    const int dcn = active ? g.chk_ptr[row + 1] - e0 : 0;
-    const int dmax = __reduce_max_sync(QH_FULL, dcn);               // the longest of the warp's rows
+// false: nothing to do for the whole warp
+template <typename T> __device__ __forceinline__ bool qh_setup(const IterParams<T> &P, QhRow<T> &R) {
+    const DevGraph &g = P.g;
+    R.lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    R.l4 = R.lane & 3; R.rw = R.lane >> 2; R.x0 = 4 * R.l4;
+    const long long nrows = (long long)P.B * g.M;
+    long long w = ((long long)blockIdx.x * QH_WARPS + warp) * QH_ROWS + R.rw;
+    R.active = w < nrows;
+    if (!R.active) w = nrows - 1;                                   // the lanes stay for the warp-wide shuffles; they store nothing
+    R.f = (int)(w / g.M); R.row = (int)(w % g.M);
+    if (P.early_stop && P.done[R.f]) R.active = false;
+    if (!__any_sync(QH_FULL, R.active)) return false;               // warp-uniform
+    R.e0 = g.chk_ptr[R.row];
+    R.dcn = R.active ? g.chk_ptr[R.row + 1] - R.e0 : 0;
+    R.dmax = __reduce_max_sync(QH_FULL, R.dcn);                     // the longest of the warp's rows
+    return true;
+}
+
+// steps A-C (NBLDPC.cpp:676-744 / 977-1052): posterior, decisions, syndrome, damped v2c of the row's edges.
+// Out: V[d] = v2c of edge d (my four elements), tf / ti = my four bytes of the rows h * x and h^-1 * x, sdw nibble d =
+// decide(v2c_d).  Sets P.flag[f] when the row's syndrome is not zero.
+template <typename T>
+__device__ __forceinline__ void qh_vn_phase(const IterParams<T> &P, const int *__restrict__ desc, const QhRow<T> &R,
+                                            T (&V)[QH_MAXDC][4], unsigned (&tf)[QH_MAXDC], unsigned (&ti)[QH_MAXDC], unsigned &sdw) {
+    constexpr int Q = 16;
+    const DevGraph &g = P.g;
+    const int lane = R.lane, l4 = R.l4, x0 = R.x0, f = R.f, e0 = R.e0, dcn = R.dcn, dmax = R.dmax;
+    const int *rd = desc + (size_t)R.row * (QH_MAXDC * QH_DSC);
     const T *lchf = P.lch + (size_t)f * g.N * Q + x0;
     const T *cinf = P.c2v_in + (size_t)f * g.E * Q + x0;
     T *v2cf = P.v2c + (size_t)f * g.E * Q + x0;
     uint8_t *vdecf = P.vdec + (size_t)f * g.E;
-
     // software pipeline over the edges: descriptor of edge d + 2 and messages of edge d + 1 are in flight during edge d
     int4 da[2]; int2 db[2];                                         // {variable, degree, edge ids 0..1}, {edge ids 2..3}
     T lc[2][4], mm[2][QH_MAXDV][4]; int meta[2];                    // meta: own slot | degree << 4 | old decision + 1 << 8 | variable << 17
@@ -140,9 +154,7 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_itera
         }
         meta[slot] = own | (nv << 4) | (bef << 8) | (da[slot].x << 17);
     };
-    T V[QH_MAXDC][4];
-    unsigned tf[QH_MAXDC], ti[QH_MAXDC];                            // my four bytes of the rows h * x and h^-1 * x
-    unsigned sdw = 0u;                                              // nibble d: decide(v2c_d)
+    sdw = 0u;
     int syn = 0;
     fetch_desc(0, 0);
     fetch_desc(1, 1);
@@ -206,7 +218,23 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_itera
             sdw |= (unsigned)dfin << (4 * d);
         }
     }
-    if (active && l4 == 0 && syn != 0) P.flag[f] = 1;
+    if (R.active && l4 == 0 && syn != 0) P.flag[f] = 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_iterate_qspa_half(const IterParams<T> P, const int *__restrict__ desc) {
+    constexpr int Q = 16;
+    extern __shared__ __align__(16) unsigned char qh_raw[];
+    const DevGraph &g = P.g;
+    QhRow<T> R;
+    if (!qh_setup<T>(P, R)) return;
+    const int warp = threadIdx.x >> 5, l4 = R.l4, x0 = R.x0, f = R.f, e0 = R.e0, dcn = R.dcn, dmax = R.dmax;
+    T *sV = reinterpret_cast<T *>(qh_raw + QhSmem<T>::bytes_per_warp * warp) + R.rw * 16;
+    double *sR = reinterpret_cast<double *>(qh_raw + QhSmem<T>::bytes_per_warp * warp + QhSmem<T>::v_bytes) + R.rw * 16;
+    T V[QH_MAXDC][4];
+    unsigned tf[QH_MAXDC], ti[QH_MAXDC];                            // my four bytes of the rows h * x and h^-1 * x
+    unsigned sdw;                                                   // nibble d: decide(v2c_d)
+    qh_vn_phase<T>(P, desc, R, V, tf, ti, sdw);
     // ---- check node: distributions in the syndrome domain, maximum normalised to 1, transformed ------------------------------
     double F[QH_MAXDC][4];
 #pragma unroll

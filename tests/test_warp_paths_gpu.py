@@ -275,3 +275,38 @@ def test_bstems_warp_and_group_kernels_agree(name, precision, code_files):
     if precision == capi.PREC_F64:
         assert np.array_equal(outs[0]["sym"], z["dec_sym"].astype(np.int32))
         assert np.array_equal(outs[0]["iterations"], z["iters"].astype(np.int32))
+
+
+@pytest.mark.parametrize("regular", [True, False])
+@pytest.mark.parametrize("p0,p1,factor,offset", [(2, 2, 1.0, 0.5), (1, 2, 1.0, 0.5), (3, 2, 0.8, 0.25), (2, 1, 1.0, 0.5), (2, 2, 1.5, 0.0)])
+def test_tems_gf16_kernel_random_codes(regular, p0, p1, factor, offset, tmp_path):
+    """T-EMS over GF(16) on the four-lanes-per-row kernel (tems_half.cuh; tie mode FAST) against the oracle: random regular
+    and irregular codes (check degrees up to 5-6), n_r = 1 / 2 / 3, n_c = 1 / 2, scaling factor, zero offset"""
+    rng = np.random.default_rng(1600 + regular + 10 * p0 + p1)
+    code = _random_code(16, 12, rng, regular)
+    lch = _frames(code, 16, 0.70, rng)
+    r = _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset)
+    assert len(set(r["iterations"].tolist())) > 1
+
+
+def test_tems_gf16_kernel_on_the_reference_code(code_files):
+    """the (128,64) GF(16) code of the reference (d_c = 5, d_v = 2 and 3), frames of the QSPA fixture decoded with T-EMS:
+    the GF(16) kernel and the group kernel give the same decisions and iteration counts in fp64 and agree in fp32"""
+    from nbldpc_b200 import capi
+    z, meta = load_golden("cfg1_qspa_gf16")
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)
+    for precision, tol in ((capi.PREC_F64, 1e-8), (capi.PREC_F32, 1e-3)):
+        outs = []
+        for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
+            os.environ.update(env)
+            try:
+                dec = capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=precision, max_batch=len(lch), tie_mode=1)
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+            outs.append(dec.decode(lch, want_post=True))
+        same = (outs[0]["sym"] == outs[1]["sym"]).all(axis=1) & (outs[0]["iterations"] == outs[1]["iterations"])
+        assert same.all() if precision == capi.PREC_F64 else same.mean() > 0.9
+        d = np.abs(outs[0]["post"] - outs[1]["post"])[same]
+        assert (d / np.maximum(np.abs(outs[1]["post"][same]), 1.0)).max() < tol
