@@ -284,7 +284,7 @@ def main_ours(args):
             traffic, traffic_src = t["bytes_per_frame_iteration"] * B, t["capture"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": bytes_iter * B,
-                    "kernel": "k_iterate_tems_warp<float,256,4,2>", "kernel_ms": k_ms, "launches_timed": len(it_ms),
+                    "kernel": "k_iterate_tems_warp<float,256,4,2>", "kernel_family": dec.kernel(), "kernel_ms": k_ms, "launches_timed": len(it_ms),
                     "peak_source": peak_src,
                     "alu": {"note": "T-EMS check node is FP32-issue bound (SURVEY 8d): reference leaf count x 2 lane-ops",
                             "achieved_tlaneops": ops_iter * B / (k_ms * 1e-3) / 1e12, "peak_tlaneops": alu_peak / 1e12,

@@ -121,6 +121,11 @@ typedef struct {
 /* stream: a cudaStream_t (as void*) to launch on, or NULL for a private non-blocking stream */
 int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const nbl_decoder_config *cfg, void *stream);
 void nbl_decoder_destroy(nbl_decoder *dec);
+/* which iteration kernel this decoder launches (static string): "tems_warp", "bstems_warp", "ems_warp", "qspa_warp"
+ * (one warp per check row, q >= 32, d_c <= 4), "tems_gf16", "qspa_gf16" (four lanes per row), or "group" (the generic
+ * q-threads-per-row kernel: any code, any parameters, several times slower).  For logs and tests: a configuration that
+ * silently moved to "group" is a performance regression, not an error. */
+const char *nbl_decoder_kernel(const nbl_decoder *dec);
 
 /* Bit-level ordered-statistics post-processing of the frames the iterative decoder fails on -- replaces
  * CNBLDPC::Decoding_OSD_bit (OSD.h:5-199) and the "if (OSD_Order >= 0 && !decode_correct)" tail of every Decoding_*

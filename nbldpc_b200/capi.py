@@ -69,6 +69,8 @@ def lib():
         L.nbl_decoder_create.argtypes = [C.POINTER(vp), vp, C.POINTER(DecoderConfig), vp]
         L.nbl_decoder_destroy.argtypes = [vp]
         L.nbl_decoder_destroy.restype = None
+        L.nbl_decoder_kernel.argtypes = [vp]
+        L.nbl_decoder_kernel.restype = C.c_char_p
         L.nbl_decoder_stream.argtypes = [vp]
         L.nbl_decoder_stream.restype = vp
         L.nbl_decoder_sync.argtypes = [vp]
@@ -235,6 +237,10 @@ class Decoder:
         if want_post:
             out["post"] = post
         return out
+
+    def kernel(self):
+        """name of the iteration kernel this decoder launches ("tems_warp", ..., "group")"""
+        return lib().nbl_decoder_kernel(self._h).decode()
 
     def enable_osd(self, order, factor=1.0, flag=0, crc_len=8, crc_correct_len=0, fix_matrepr=0):
         """OSD post-processing of failed frames in every later decode call (profile keys OSD_order, OSD_factor, OSD_flag,

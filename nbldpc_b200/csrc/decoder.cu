@@ -465,6 +465,16 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     return NBL_OK;
 }
 
+extern "C" const char *nbl_decoder_kernel(const nbl_decoder *d) {
+    if (!d) return "";
+    if (d->tems_half_path) return "tems_gf16";
+    if (d->qspa_half_path) return "qspa_gf16";
+    if (d->warp_path) return d->cfg.method == NBL_METHOD_BSTEMS ? "bstems_warp" : "tems_warp";
+    if (d->ems_warp_path) return "ems_warp";
+    if (d->qspa_warp_path) return "qspa_warp";
+    return "group";
+}
+
 extern "C" void *nbl_decoder_stream(nbl_decoder *d) { return d ? (void *)d->stream : nullptr; }
 extern "C" int nbl_decoder_sync(nbl_decoder *d) {
     if (!d) { nbl_set_error("null decoder"); return NBL_ERR_ARG; }

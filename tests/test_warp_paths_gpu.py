@@ -310,3 +310,21 @@ def test_tems_gf16_kernel_on_the_reference_code(code_files):
         assert same.all() if precision == capi.PREC_F64 else same.mean() > 0.9
         d = np.abs(outs[0]["post"] - outs[1]["post"])[same]
         assert (d / np.maximum(np.abs(outs[1]["post"][same]), 1.0)).max() < tol
+
+
+def test_baseline_configurations_run_on_their_fast_kernels(code_files):
+    """every BASELINE configuration (and the other decoders on the reference's codes) selects the kernel built for it; the
+    parity modes and the parameters outside a fast kernel's range fall back to the group kernel"""
+    from nbldpc_b200 import capi
+    G16, G64, G256 = "divsalar.UNBLDPC.128.64.GF.16", "BDS.576.288.GF.64", "divsalar.UNBLDPC.512.256.GF.256"
+    want = [(G16, 1, 0, 0, 0.0, "qspa_gf16"), (G64, 2, 8, 3, 0.5, "ems_warp"), (G256, 4, 2, 2, 0.5, "tems_warp"),
+            ("divsalar.CNBLDPC.512.256.GF.256", 1, 0, 0, 0.0, "qspa_warp"), ("H_bit_GF256", 4, 2, 2, 0.5, "tems_warp"),
+            (G256, 7, 4, 3, 0.2, "bstems_warp"), (G16, 4, 2, 2, 0.5, "tems_gf16"), (G64, 4, 2, 2, 0.5, "tems_warp"),
+            (G256, 4, 2, 3, 0.5, "group"), (G16, 2, 8, 3, 0.5, "group"), (G64, 2, 6, 3, 0.5, "group")]
+    for name, method, p0, p1, off, kern in want:
+        code = load_product_code(code_files, name)
+        dec = capi.Decoder(code, method, 10, p0, p1, 1.0, off, precision=capi.PREC_F32, max_batch=4)
+        assert dec.kernel() == kern, (name, method, p0, p1, dec.kernel())
+    code = load_product_code(code_files, G256)
+    assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4).kernel() == "group"          # reference tie order
+    assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4, tie_mode=1).kernel() == "tems_warp"
