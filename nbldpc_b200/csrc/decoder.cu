@@ -59,6 +59,7 @@ template <typename T> struct IterParams {
 #include "osd.cuh"
 #include "qspa_half.cuh"
 #include "tems_half.cuh"
+#include "ems_half.cuh"
 
 // channel LLRs: double [B][N][q-1] -> T [B][N][Q] with a zero in slot 0
 template <typename T> __global__ void k_convert_lch(const double *__restrict__ src, T *__restrict__ dst, size_t nvec, int q) {
@@ -282,6 +283,7 @@ struct nbl_decoder {
     bool qspa_warp_path = false; // QSPA, dc <= 4, q >= 32: one warp per check row (qspa_warp.cuh)
     bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
+    bool ems_half_path = false;  // EMS over GF(16), dc <= 8, dv <= 4, n_m <= 16, n_c <= 3 (ems_half.cuh)
     bool tems_half_path = false; // T-EMS n_c <= 2 over GF(16), dc <= 8, dv <= 4, not the reference tie order (tems_half.cuh)
     bool qspa_half_path = false; // QSPA over GF(16), dc <= 8, dv <= 4: four lanes per check row, eight rows per warp (qspa_half.cuh)
     int *d_rowdesc8 = nullptr;   // its row descriptors [M][QH_MAXDC][QH_DSC]
@@ -416,7 +418,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
             if ((rc = upload(&d->d_pfwd_sw, pfs)) || (rc = upload(&d->d_pinv_sw, pis))) return fail(rc);
         }
     }
-    if (q == 16 && (cfg->method == NBL_METHOD_QSPA || cfg->method == NBL_METHOD_TEMS) && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV &&
+    if (q == 16 && (cfg->method == NBL_METHOD_QSPA || cfg->method == NBL_METHOD_TEMS || cfg->method == NBL_METHOD_EMS) && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV &&
         !getenv("NBLDPC_FORCE_GENERIC")) {
         std::vector<int> rd((size_t)code->M * QH_MAXDC * QH_DSC, 0);
         for (int r = 0; r < code->M; ++r)
@@ -450,6 +452,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || cfg->tie_mode == NBL_TIES_BITEXACT || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
     d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
     d->tems_half_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && q == 16 && d->d_rowdesc8 != nullptr && !ref_ties;
+    d->ems_half_path = cfg->method == NBL_METHOD_EMS && q == 16 && d->d_rowdesc8 != nullptr && cfg->p0 <= EH_MAXNM && cfg->p1 + 1 <= EH_MAXNJ;
     // BS-TEMS on the same kernel (its search replaced by the basic-set walk): no tie modes, the walk is the reference's own
     if (cfg->method == NBL_METHOD_BSTEMS && desc_ok && q >= 32 && cfg->offset >= 0.0 && !getenv("NBLDPC_FORCE_GENERIC")) d->warp_path = true;
     {
@@ -468,6 +471,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
 extern "C" const char *nbl_decoder_kernel(const nbl_decoder *d) {
     if (!d) return "";
     if (d->tems_half_path) return "tems_gf16";
+    if (d->ems_half_path) return "ems_gf16";
     if (d->qspa_half_path) return "qspa_gf16";
     if (d->warp_path) return d->cfg.method == NBL_METHOD_BSTEMS ? "bstems_warp" : "tems_warp";
     if (d->ems_warp_path) return "ems_warp";
@@ -587,6 +591,13 @@ template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const 
         if (d->tems_half_path) {
             const long long rows = (long long)P.B * P.g.M, per_cta = QH_ROWS * QH_WARPS;
             k_iterate_tems_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, ThSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
+            CK(cudaGetLastError());
+            return NBL_OK;
+        }
+        if (d->ems_half_path) {
+            const long long rows = (long long)P.B * P.g.M, per_cta = QH_ROWS * QH_WARPS;
+            CK(cudaFuncSetAttribute(k_iterate_ems_half<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EhSmem<T>::bytes));
+            k_iterate_ems_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, EhSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
             CK(cudaGetLastError());
             return NBL_OK;
         }

@@ -320,7 +320,7 @@ def test_baseline_configurations_run_on_their_fast_kernels(code_files):
     want = [(G16, 1, 0, 0, 0.0, "qspa_gf16"), (G64, 2, 8, 3, 0.5, "ems_warp"), (G256, 4, 2, 2, 0.5, "tems_warp"),
             ("divsalar.CNBLDPC.512.256.GF.256", 1, 0, 0, 0.0, "qspa_warp"), ("H_bit_GF256", 4, 2, 2, 0.5, "tems_warp"),
             (G256, 7, 4, 3, 0.2, "bstems_warp"), (G16, 4, 2, 2, 0.5, "tems_gf16"), (G64, 4, 2, 2, 0.5, "tems_warp"),
-            (G256, 4, 2, 3, 0.5, "group"), (G16, 2, 8, 3, 0.5, "group"), (G64, 2, 6, 3, 0.5, "group")]
+            (G256, 4, 2, 3, 0.5, "group"), (G16, 2, 8, 3, 0.5, "ems_gf16"), (G16, 7, 4, 3, 0.2, "group"), (G64, 2, 6, 3, 0.5, "group")]
     for name, method, p0, p1, off, kern in want:
         code = load_product_code(code_files, name)
         dec = capi.Decoder(code, method, 10, p0, p1, 1.0, off, precision=capi.PREC_F32, max_batch=4)
@@ -328,3 +328,38 @@ def test_baseline_configurations_run_on_their_fast_kernels(code_files):
     code = load_product_code(code_files, G256)
     assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4).kernel() == "group"          # reference tie order
     assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4, tie_mode=1).kernel() == "tems_warp"
+
+
+@pytest.mark.parametrize("regular", [True, False])
+@pytest.mark.parametrize("nm,nc,factor,offset", [(8, 3, 1.0, 0.5), (6, 2, 1.0, 0.2), (16, 1, 1.25, 0.0), (4, 3, 1.0, 0.5)])
+def test_ems_gf16_kernel_random_codes(regular, nm, nc, factor, offset, tmp_path):
+    """EMS over GF(16) on the four-lanes-per-row kernel (ems_half.cuh) against the oracle: random regular and irregular
+    codes, n_m a power of two or not, n_c = 1..3"""
+    rng = np.random.default_rng(1700 + regular + nm + nc)
+    code = _random_code(16, 12, rng, regular)
+    lch = _frames(code, 12, 0.70, rng)
+    _check_ems(code, tmp_path, lch, nm, nc, factor, offset)
+
+
+def test_ems_gf16_kernel_on_the_reference_code(code_files):
+    """the golden EMS frames on the (128,64) GF(16) code (d_c = 5): reference decisions in fp64 on the GF(16) kernel, and
+    the group kernel gives the same posteriors"""
+    from nbldpc_b200 import capi
+    z, meta = load_golden("x_ems_gf16_dc5")
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)
+    outs = []
+    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
+        os.environ.update(env)
+        try:
+            dec = capi.Decoder(code, 2, meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], precision=capi.PREC_F64,
+                               max_batch=len(lch))
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        outs.append((dec.kernel(), dec.decode(lch, want_post=True)))
+    assert [k for k, _ in outs] == ["ems_gf16", "group"]
+    for k in ("sym", "converged", "iterations", "post"):
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+    assert np.array_equal(outs[0][1]["sym"], z["dec_sym"].astype(np.int32))
+    assert np.array_equal(outs[0][1]["iterations"], z["iters"].astype(np.int32))
