@@ -185,6 +185,7 @@ def main_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the decode path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's own banner / debug lines: not on stdout, which carries the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     code_path = "/tmp/nbldpc_bench_code_%d.txt" % rank
