@@ -175,24 +175,23 @@ __global__ void k_syndrome(DevGraph g, int B, int early_stop, const uint8_t *__r
     if (syn) flag[f] = 1;
 }
 
-// per frame: latch the result at the first zero syndrome (or at max_iter), as the reference returns it
+// per frame: latch the result at the first zero syndrome (or at max_iter), as the reference returns it.  One warp per frame.
 __global__ void k_finalize(int B, int N, int iter, int max_iter, int *flag, uint8_t *done, int *iters, int *conv,
                            const uint8_t *__restrict__ dec, int *out_sym, uint8_t *newly) {
-    const int f = blockIdx.x;
-    __shared__ int latch;
-    if (threadIdx.x == 0) {
-        int l = 0;
+    const int f = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (f >= B) return;
+    int l = 0;
+    if (lane == 0) {
         if (!done[f]) {
             const bool ok = flag[f] == 0;
             flag[f] = 0;
             if (ok || iter == max_iter) { done[f] = 1; conv[f] = ok ? 1 : 0; iters[f] = ok ? iter : max_iter; l = 1; }
         }
         newly[f] = (uint8_t)l;
-        latch = l;
     }
-    __syncthreads();
-    if (latch)
-        for (int i = threadIdx.x; i < N; i += blockDim.x) out_sym[(size_t)f * N + i] = dec[(size_t)f * N + i];
+    l = __shfl_sync(0xffffffffu, l, 0);
+    if (l)
+        for (int i = lane; i < N; i += 32) out_sym[(size_t)f * N + i] = dec[(size_t)f * N + i];
 }
 
 // ---- soft demapper (CComm::Demodulate, Comm.cpp:340-407); fp64 in the reference's operation order -----
@@ -681,7 +680,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
             CK(cudaGetLastError());
             d->last_launches += 2;
         }
-        k_finalize<<<B, 64, 0, d->stream>>>(B, d->g.N, it, c.max_iter, d->d_flag, d->d_done, d->d_iters, d->d_conv, d->d_dec, d->d_out, d->d_newly);
+        k_finalize<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, d->stream>>>(B, d->g.N, it, c.max_iter, d->d_flag, d->d_done, d->d_iters, d->d_conv, d->d_dec, d->d_out, d->d_newly);
         CK(cudaGetLastError());
         d->last_launches += 1;
         if (post_dev) {
