@@ -150,3 +150,24 @@ def test_device_monte_carlo_crc(code_files):
         c = dec.simulate(9.0, 2000, seed=5, random_msg=1, crc_len=crc)
         assert int(c[1]) == 0
         assert int(c[7]) == (2000 if crc == 16 else 0)        # crcLen 24: CRC24A on encode, CRC24B on check, as the reference
+
+
+@pytest.mark.gpu
+def test_gpu_osd_order2_on_the_headline_code(code_files):
+    """(512,256) GF(256), OSD order 2 with CRC-16 rows: 32 897 candidates per frame unranked from a linear index on the GPU
+    against the oracle's nested loops (a few seconds per frame on the CPU)"""
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    z, meta = load_golden("f3_osd1_tems_gf256")
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)[:3]
+    oc = po.OracleCode(get_code_dict(meta["code"]))
+    osd = po.OracleOsd(oc, 16, 9)
+    want = [oc.decode(4, 3, 2, 2, 1.0, 0.5, l, osd, 2, 0.8, 0) for l in lch]
+    assert all(w[0] == 0 for w in want)
+    dec = capi.Decoder(code, 4, 3, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=len(lch))
+    dec.enable_osd(2, 0.8, 0, 16, 9)
+    r = dec.decode(lch)
+    assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))
+    plain = capi.Decoder(code, 4, 3, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=len(lch)).decode(lch)
+    assert (plain["sym"] != r["sym"]).any()
