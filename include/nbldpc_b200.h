@@ -122,7 +122,7 @@ typedef struct {
 int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const nbl_decoder_config *cfg, void *stream);
 void nbl_decoder_destroy(nbl_decoder *dec);
 /* which iteration kernel this decoder launches (static string): "tems_warp", "bstems_warp", "ems_warp", "qspa_warp"
- * (one warp per check row, q >= 32, d_c <= 4), "tems_gf16", "ems_gf16", "qspa_gf16" (four lanes per row), or "group" (the generic
+ * (one warp per check row, q >= 32, d_c <= 4), "tems_gf16", "bstems_gf16", "ems_gf16", "qspa_gf16" (four lanes per row), or "group" (the generic
  * q-threads-per-row kernel: any code, any parameters, several times slower).  For logs and tests: a configuration that
  * silently moved to "group" is a performance regression, not an error. */
 const char *nbl_decoder_kernel(const nbl_decoder *dec);

@@ -417,7 +417,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
             if ((rc = upload(&d->d_pfwd_sw, pfs)) || (rc = upload(&d->d_pinv_sw, pis))) return fail(rc);
         }
     }
-    if (q == 16 && (cfg->method == NBL_METHOD_QSPA || cfg->method == NBL_METHOD_TEMS || cfg->method == NBL_METHOD_EMS) && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV &&
+    if (q == 16 && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV &&
         !getenv("NBLDPC_FORCE_GENERIC")) {
         std::vector<int> rd((size_t)code->M * QH_MAXDC * QH_DSC, 0);
         for (int r = 0; r < code->M; ++r)
@@ -451,6 +451,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || cfg->tie_mode == NBL_TIES_BITEXACT || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
     d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
     d->tems_half_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && q == 16 && d->d_rowdesc8 != nullptr && !ref_ties;
+    if (cfg->method == NBL_METHOD_BSTEMS && q == 16 && d->d_rowdesc8 != nullptr) d->tems_half_path = true;      // the same kernel with BS = 1
     d->ems_half_path = cfg->method == NBL_METHOD_EMS && q == 16 && d->d_rowdesc8 != nullptr && cfg->p0 <= EH_MAXNM && cfg->p1 + 1 <= EH_MAXNJ;
     // BS-TEMS on the same kernel (its search replaced by the basic-set walk): no tie modes, the walk is the reference's own
     if (cfg->method == NBL_METHOD_BSTEMS && desc_ok && q >= 32 && cfg->offset >= 0.0 && !getenv("NBLDPC_FORCE_GENERIC")) d->warp_path = true;
@@ -469,7 +470,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
 
 extern "C" const char *nbl_decoder_kernel(const nbl_decoder *d) {
     if (!d) return "";
-    if (d->tems_half_path) return "tems_gf16";
+    if (d->tems_half_path) return d->cfg.method == NBL_METHOD_BSTEMS ? "bstems_gf16" : "tems_gf16";
     if (d->ems_half_path) return "ems_gf16";
     if (d->qspa_half_path) return "qspa_gf16";
     if (d->warp_path) return d->cfg.method == NBL_METHOD_BSTEMS ? "bstems_warp" : "tems_warp";
@@ -589,7 +590,13 @@ template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const 
     if constexpr (Q == 16) {
         if (d->tems_half_path) {
             const long long rows = (long long)P.B * P.g.M, per_cta = QH_ROWS * QH_WARPS;
-            k_iterate_tems_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, ThSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
+            if (d->cfg.method == NBL_METHOD_BSTEMS) {
+                CK(cudaFuncSetAttribute(k_iterate_tems_half<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThSmem<T>::bytes));
+                k_iterate_tems_half<T, 1><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, ThSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
+            } else {
+                CK(cudaFuncSetAttribute(k_iterate_tems_half<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThSmem<T>::bytes));
+                k_iterate_tems_half<T, 0><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, ThSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
+            }
             CK(cudaGetLastError());
             return NBL_OK;
         }

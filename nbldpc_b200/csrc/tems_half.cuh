@@ -20,13 +20,16 @@ namespace nbl {
 
 template <typename T> struct ThSmem {
     // per row: V [16] (gather buffer), D_c [8][16] (later the output trellis), m0 [16], m1 [16], c0 | c1 << 4 [16] bytes
-    static constexpr size_t row_elems = 16 + 8 * 16 + 16 + 16;
-    static constexpr size_t row_bytes = row_elems * sizeof(T) + 16;
+    //          BS-TEMS: deltaW [16], basic-set costs [16]; recorded subsets [16] x 8 bytes; basic-set eta / column [16] bytes each
+    static constexpr size_t row_elems = 16 + 8 * 16 + 16 + 16 + 16 + 16;
+    static constexpr size_t row_bytes = row_elems * sizeof(T) + 16 + 16 * 8 + 32;
     static constexpr size_t bytes_per_warp = row_bytes * QH_ROWS;
     static constexpr size_t bytes = bytes_per_warp * QH_WARPS;
 };
 
-template <typename T>
+// BS == 1: BS-TEMS (decode method 7): the pair search is replaced by the basic-set construction and the walk over its
+// subsets, as in tems_warp.cuh; here lane 0 of every row walks its own row, eight rows of a warp at a time.
+template <typename T, int BS = 0>
 __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_iterate_tems_half(const IterParams<T> P, const int *__restrict__ desc) {
     constexpr int Q = 16;
     extern __shared__ __align__(16) unsigned char th_raw[];
@@ -38,7 +41,10 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_itera
     T *sV = reinterpret_cast<T *>(th_raw + ThSmem<T>::bytes_per_warp * warp + ThSmem<T>::row_bytes * R.rw);
     T *sD = sV + 16;                                                // [8][16]
     T *sM0 = sD + 8 * 16, *sM1 = sM0 + 16;
-    uint8_t *sC = reinterpret_cast<uint8_t *>(sM1 + 16);            // [16]
+    T *sDW = sM1 + 16, *sBL = sDW + 16;                             // BS-TEMS: deltaW [16], costs of the basic set [16]
+    uint8_t *sC = reinterpret_cast<uint8_t *>(sBL + 16);            // [16]
+    unsigned long long *sSet = reinterpret_cast<unsigned long long *>(sC + 16);   // [16] byte d: basic element + 1 deviating in column d
+    uint8_t *sBQ = reinterpret_cast<uint8_t *>(sSet + 16), *sBC = sBQ + 16;       // basic set: eta, column
     T V[QH_MAXDC][4];
     unsigned tf[QH_MAXDC], ti[QH_MAXDC];                            // my four bytes of the rows h * x and h^-1 * x
     unsigned sdw;                                                   // nibble d: decide(v2c_d)
@@ -111,65 +117,157 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_itera
         }
     }
     __syncwarp();
-    // ---- pair search: best[s] = min over a != 0 of m0(a) + D_{c0(a)}[s ^ a]; the first (smallest) a that attains it ---------------
-    T best[4]; int arg[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { best[i] = INF; arg[i] = 0; }
-    if (P.p1 >= 2) {
-#pragma unroll 1
-        for (int a = 1; a < Q; ++a) {
-            const T ma = sM0[a];
-            const T *Da = sD + (sC[a] & 15) * 16;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const T cand = ma + Da[(x0 + i) ^ a];
-                if (cand < best[i]) { best[i] = cand; arg[i] = a; }
-            }
-        }
-    }
-    // ---- deltaW and the recorded path of each owned s ---------------------------------------------------------------------------
-    T dw[4], va[4], vb[4]; int pa[4], pb[4], pca[4], pcb[4]; bool pair[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int s = x0 + i;
-        const T single = (s == 0) ? T(0) : m0[i];
-        pair[i] = best[i] < single;                                 // never for s == 0
-        dw[i] = pair[i] ? best[i] : single;
-        pa[i] = arg[i]; pb[i] = s ^ arg[i];
-        pca[i] = pcb[i] = 0; va[i] = vb[i] = T(0);
-        if (pair[i]) {
-            const int ca = sC[pa[i]] & 15, kb = sC[pb[i]];
-            const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
-            pca[i] = ca; pcb[i] = cb;
-            va[i] = dw[i] - sM0[pa[i]];                             // dU[ca][a]
-            vb[i] = dw[i] - sD[ca * 16 + pb[i]];                    // dU[cb][b]
-        }
-    }
-    __syncwarp();                                                  // everyone is done with D
-    // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first, then the entries of pair paths -----------------------
     T *Tout = sD;
+    if constexpr (!BS) {
+        // ---- pair search: best[s] = min over a != 0 of m0(a) + D_{c0(a)}[s ^ a]; the first (smallest) a that attains it ---------------
+        T best[4]; int arg[4];
 #pragma unroll
-    for (int d = 0; d < QH_MAXDC; ++d) {
-        if (d < dmax) {
-            T tv[4];
+        for (int i = 0; i < 4; ++i) { best[i] = INF; arg[i] = 0; }
+        if (P.p1 >= 2) {
+#pragma unroll 1
+            for (int a = 1; a < Q; ++a) {
+                const T ma = sM0[a];
+                const T *Da = sD + (sC[a] & 15) * 16;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int s = x0 + i;
-                const bool uses = s != 0 && (pair[i] ? (pca[i] == d || pcb[i] == d) : (k0[i] == d));
-                tv[i] = uses ? INF : dw[i];
+                for (int i = 0; i < 4; ++i) {
+                    const T cand = ma + Da[(x0 + i) ^ a];
+                    if (cand < best[i]) { best[i] = cand; arg[i] = a; }
+                }
             }
-            qh_store4<T>(Tout + d * 16 + x0, tv);
         }
-    }
-    __syncwarp();
+        // ---- deltaW and the recorded path of each owned s ---------------------------------------------------------------------------
+        T dw[4], va[4], vb[4]; int pa[4], pb[4], pca[4], pcb[4]; bool pair[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (pair[i]) {                                              // (values are >= 0: ordered like their bits)
-            atomic_min_nonneg(Tout + pca[i] * 16 + pb[i], va[i]);
-            atomic_min_nonneg(Tout + pcb[i] * 16 + pa[i], vb[i]);
+        for (int i = 0; i < 4; ++i) {
+            const int s = x0 + i;
+            const T single = (s == 0) ? T(0) : m0[i];
+            pair[i] = best[i] < single;                                 // never for s == 0
+            dw[i] = pair[i] ? best[i] : single;
+            pa[i] = arg[i]; pb[i] = s ^ arg[i];
+            pca[i] = pcb[i] = 0; va[i] = vb[i] = T(0);
+            if (pair[i]) {
+                const int ca = sC[pa[i]] & 15, kb = sC[pb[i]];
+                const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
+                pca[i] = ca; pcb[i] = cb;
+                va[i] = dw[i] - sM0[pa[i]];                             // dU[ca][a]
+                vb[i] = dw[i] - sD[ca * 16 + pb[i]];                    // dU[cb][b]
+            }
         }
+        __syncwarp();                                                  // everyone is done with D
+        // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first, then the entries of pair paths -----------------------
+#pragma unroll
+        for (int d = 0; d < QH_MAXDC; ++d) {
+            if (d < dmax) {
+                T tv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int s = x0 + i;
+                    const bool uses = s != 0 && (pair[i] ? (pca[i] == d || pcb[i] == d) : (k0[i] == d));
+                    tv[i] = uses ? INF : dw[i];
+                }
+                qh_store4<T>(Tout + d * 16 + x0, tv);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (pair[i]) {                                              // (values are >= 0: ordered like their bits)
+                atomic_min_nonneg(Tout + pca[i] * 16 + pb[i], va[i]);
+                atomic_min_nonneg(Tout + pcb[i] * 16 + pa[i], vb[i]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- BS-TEMS (Decoding_BS_TEMS, NBLDPC.cpp:1145-1396): the all-zero configuration plus the subsets of the basic set ----------
+        // (a) Construct_BasicSet (:2023-2101): the n_m cheapest eta != 0 by m0, lowest eta among equals; for n_m <= log2 q
+        //     greedily linearly independent over GF(2) (span = 16-bit mask of the row, the same in its four lanes)
+        const int nm = P.p0, nc = P.p1;
+        T rc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rc[i] = (x0 + i == 0) ? INF : m0[i];
+        unsigned avail = 15u, span = 0u;
+        int found = 0;
+#pragma unroll 1
+        for (int k = 0; k < nm; ++k) {                              // warp-uniform trip count; a row that ran out keeps found
+            T lm = INF; int lx = 99;
+#pragma unroll
+            for (int i = 3; i >= 0; --i) if (((avail >> i) & 1u) && rc[i] <= lm && rc[i] < INF) { lm = rc[i]; lx = x0 + i; }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const T om = __shfl_xor_sync(QH_FULL, lm, o);
+                const int ox = __shfl_xor_sync(QH_FULL, lx, o);
+                if (om < lm || (om == lm && ox < lx)) { lm = om; lx = ox; }
+            }
+            if (lx < 16 && found == k) {                            // (found == k: the row has not run out before)
+                const int w = lx;
+                if (l4 == 0) { sBQ[k] = (uint8_t)w; sBC[k] = (uint8_t)(sC[w] & 15); sBL[k] = lm; }
+                found = k + 1;
+                if (nm > g.p) { if ((w >> 2) == l4) avail &= ~(1u << (w & 3)); }
+                else {
+                    unsigned moved = 0u;
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) moved |= ((span >> (x ^ w)) & 1u) << x;
+                    span |= moved | (1u << w);
+                    avail &= ~((span >> x0) & 15u);
+                }
+            }
+        }
+        // (b) BasicSet_TEMS_ConstructConf (:2102-2147): lane 0 of the row walks the subsets (<= n_c elements, no column twice),
+        //     include first, with the reference's add / subtract running sum
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sDW[x0 + i] = (x0 + i == 0) ? T(0) : INF; sSet[x0 + i] = 0ull; }
+        __syncwarp();
+        if (l4 == 0 && dcn > 0) {
+            unsigned col_sel = 0u; unsigned long long cand = 0ull; int diff = 0, sym = 0, lvl = 0; T sum = T(0);
+            uint8_t st[17];
+            st[0] = 0;
+            while (lvl >= 0) {
+                if (lvl == found) {
+                    if (sum < sDW[sym]) { sDW[sym] = sum; sSet[sym] = cand; }
+                    --lvl;
+                    continue;
+                }
+                const int col = sBC[lvl], bq = sBQ[lvl];
+                const T bL = sBL[lvl];
+                if (st[lvl] == 0) {
+                    if (!((col_sel >> col) & 1u) && diff + 1 <= nc) {
+                        diff += 1; col_sel |= 1u << col;
+                        sym ^= bq; sum = sum + bL; cand |= (unsigned long long)(lvl + 1) << (8 * col);
+                        st[lvl] = 1;
+                    } else st[lvl] = 2;
+                    ++lvl; st[lvl] = 0;
+                } else if (st[lvl] == 1) {
+                    sym ^= bq; sum = sum - bL; col_sel &= ~(1u << col); cand &= ~(255ull << (8 * col));
+                    diff -= 1;
+                    st[lvl] = 2;
+                    ++lvl; st[lvl] = 0;
+                } else --lvl;
+            }
+        }
+        __syncwarp();
+        // (c) output trellis: Tout[d][eta ^ eta_d] = min(deltaW[eta] - dU[d][eta_d]) over the reached eta
+        T dw[4]; unsigned long long et[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dw[i] = sDW[x0 + i]; et[i] = sSet[x0 + i]; }
+        {
+            T inf_v[4] = {INF, INF, INF, INF};
+#pragma unroll
+            for (int d = 0; d < QH_MAXDC; ++d) if (d < dmax) qh_store4<T>(Tout + d * 16 + x0, inf_v);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (dw[i] < INF) {
+                for (int d = 0; d < dcn; ++d) {
+                    const int k1 = (int)((et[i] >> (8 * d)) & 255ull);
+                    const int dev = k1 ? sBQ[k1 - 1] : 0;
+                    const T du = k1 ? sBL[k1 - 1] : T(0);
+                    atomic_min_any(Tout + d * 16 + ((x0 + i) ^ dev), dw[i] - du);      // the running sum's residue can make this negative
+                }
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     // ---- fill-in (:1095-1102), normal domain, un-permute, correct (:1105-1128) -----------------------------------------------------
     T *coutf = P.c2v_out + (size_t)f * g.E * Q + x0;
 #pragma unroll

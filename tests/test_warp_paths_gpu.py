@@ -251,7 +251,7 @@ def test_qspa_warp_and_group_kernels_are_bit_identical(precision, code_files):
 
 
 @pytest.mark.parametrize("precision", [0, 1])
-@pytest.mark.parametrize("name", ["f2_bstems_gf256", "f2_bstems_gf64_nm9"])
+@pytest.mark.parametrize("name", ["f2_bstems_gf256", "f2_bstems_gf64_nm9", "f2_bstems_gf16"])
 def test_bstems_warp_and_group_kernels_agree(name, precision, code_files):
     """BS-TEMS on the warp kernel (tems_warp.cuh, BS = 1: basic-set rounds + one lane walking the subsets) and on the group
     kernel (cn_bstems): same decisions, iteration counts and posteriors (both form every sum in the reference's order)"""
@@ -320,7 +320,7 @@ def test_baseline_configurations_run_on_their_fast_kernels(code_files):
     want = [(G16, 1, 0, 0, 0.0, "qspa_gf16"), (G64, 2, 8, 3, 0.5, "ems_warp"), (G256, 4, 2, 2, 0.5, "tems_warp"),
             ("divsalar.CNBLDPC.512.256.GF.256", 1, 0, 0, 0.0, "qspa_warp"), ("H_bit_GF256", 4, 2, 2, 0.5, "tems_warp"),
             (G256, 7, 4, 3, 0.2, "bstems_warp"), (G16, 4, 2, 2, 0.5, "tems_gf16"), (G64, 4, 2, 2, 0.5, "tems_warp"),
-            (G256, 4, 2, 3, 0.5, "group"), (G16, 2, 8, 3, 0.5, "ems_gf16"), (G16, 7, 4, 3, 0.2, "group"), (G64, 2, 6, 3, 0.5, "group")]
+            (G256, 4, 2, 3, 0.5, "group"), (G16, 2, 8, 3, 0.5, "ems_gf16"), (G16, 7, 4, 3, 0.2, "bstems_gf16"), (G64, 2, 6, 3, 0.5, "group")]
     for name, method, p0, p1, off, kern in want:
         code = load_product_code(code_files, name)
         dec = capi.Decoder(code, method, 10, p0, p1, 1.0, off, precision=capi.PREC_F32, max_batch=4)
