@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NBL_ABI_VERSION 3
+#define NBL_ABI_VERSION 4
 
 typedef enum {
     NBL_OK = 0,
@@ -47,6 +47,13 @@ typedef enum {
 #define NBL_TIES_FAST 1
 #define NBL_TIES_REFERENCE 2
 #define NBL_TIES_BITEXACT 3
+
+/* nbl_decoder_config.kernel: which iteration kernel family serves the decoder.  AUTO picks the fastest one the code and
+ * the parameters allow (what nbl_decoder_kernel reports); the other two exist for A/B measurements and for the tests that
+ * compare the kernels with each other -- results are identical by construction.                                          */
+#define NBL_KERNEL_AUTO 0
+#define NBL_KERNEL_GROUP 1        /* the generic q-threads-per-row kernel (any code, any parameters)                    */
+#define NBL_KERNEL_WARP_GENERIC 2 /* the warp-per-row kernels in their degree-generic instantiation (degree guards kept) */
 
 typedef struct nbl_code nbl_code;       /* GF(q) tables + parity-check graph, resident on one device */
 typedef struct nbl_decoder nbl_decoder; /* message workspace for up to max_batch frames + a stream    */
@@ -116,6 +123,7 @@ typedef struct {
                         after two iterations, because outputs are copies and sums of inputs.  This mode replays
                         that search sequentially (one thread per check row) and so reproduces the reference's
                         messages bit for bit in fp64 for any n_c; orders of magnitude slower                 */
+    int kernel;      /* NBL_KERNEL_* (0 = AUTO).  Nothing in the library reads the environment.              */
 } nbl_decoder_config;
 
 /* stream: a cudaStream_t (as void*) to launch on, or NULL for a private non-blocking stream */
@@ -217,6 +225,10 @@ typedef struct {
                                    others (CComm::CRCEncode, Comm.cpp:506-560), and the decoded message of every frame
                                    is CRC-checked for NBL_CNT_UNDETECTED / NBL_CNT_CRC_OK (CComm::CrcCheck, :562-630;
                                    like the reference: CRC24A on encode but CRC24B on check)                  */
+    const int *punct_sym;       /* host [n_punct] punctured symbol positions (nbl_code_puncture_set; the reference's
+                                   PunctureVarDegree rule, NBLDPC.cpp:163-177): not transmitted, all-zero LLRs at the decoder,
+                                   sigma from R = K / (N - n_punct) as Comm.cpp:98.  NULL / 0: nothing punctured          */
+    int n_punct;
 } nbl_sim_config;
 
 /* counters: host uint64[NBL_NUM_COUNTERS], ACCUMULATED into (caller zeroes). */
@@ -226,6 +238,37 @@ int nbl_simulate(nbl_decoder *dec, const nbl_sim_config *cfg, uint64_t *counters
  * (nbl_decoder_stream): zero, reduce or read the counters on THAT stream, or after nbl_decoder_sync -- a decoder created
  * with stream == NULL owns a non-blocking stream that the legacy default stream does not wait for. */
 int nbl_simulate_async(nbl_decoder *dec, const nbl_sim_config *cfg, uint64_t *dev_counters);
+
+/* ---- multi-GPU: frames shard by global frame index (nbl_sim_config.first_frame); the only collective of the path is the
+ *      sum of the 8 x u64 counter vectors.  Replaces the reference's serial merge of its workers' counters
+ *      (main.cpp:46-51 parallel_for + Comm.cpp:484-493 CComm::Err adding into CSimulation), so that every rank applies the
+ *      stop rule (Simulation.cpp:373-376) to the same totals.  NCCL is bound at run time; world == 1 needs none. ---- */
+typedef struct nbl_comm nbl_comm;
+/* one process driving n_devices GPUs (devices == NULL: 0..n-1): ncclCommInitAll */
+int nbl_comm_create(nbl_comm **out, int n_devices, const int *devices);
+/* one process per GPU: rank 0 calls nbl_comm_unique_id and hands the 128 bytes to the other ranks by its own means
+ * (file, MPI, torch.distributed broadcast); every rank then calls nbl_comm_create_rank (ncclCommInitRank) */
+int nbl_comm_unique_id(void *id128);
+int nbl_comm_create_rank(nbl_comm **out, int world, int rank, const void *id128, int device);
+void nbl_comm_destroy(nbl_comm *comm);
+int nbl_comm_size(const nbl_comm *comm);        /* ranks in the communicator */
+int nbl_comm_local_ranks(const nbl_comm *comm); /* ranks this process holds: n_devices, or 1 */
+int nbl_comm_rank(const nbl_comm *comm, int local_index);   /* global rank of local rank i (-1: out of range) */
+int nbl_comm_device(const nbl_comm *comm, int local_index); /* its CUDA device */
+/* In-place sum over all ranks of dev_counters (device uint64[NBL_NUM_COUNTERS], as filled by nbl_simulate_async), queued on
+ * each decoder's stream behind the simulation it just ran: decoders[i] / dev_counters[i] belong to local rank i
+ * (nbl_comm_local_ranks entries; the decoder must live on that rank's device).  Asynchronous: read the result after
+ * nbl_decoder_sync or on the same stream.  One ncclAllReduce(sum, uint64 x 8) per rank, grouped. */
+int nbl_allreduce_counters(nbl_comm *comm, nbl_decoder *const *decoders, uint64_t *const *dev_counters);
+
+/* One round of a sharded Monte-Carlo run = one pass of the reference's frame loop main.cpp:43-55 (its `parallel` workers, then
+ * the merge of their counters): local rank i (global rank r_i) simulates frames_per_rank frames starting at
+ * cfg->first_frame + (round_index * world + r_i) * frames_per_rank on decoders[i] (cfg->frames is ignored), the per-rank counter
+ * vectors are summed with nbl_allreduce_counters, and the round's total is ADDED to totals (host uint64[8]) on every rank.
+ * Synchronous.  The union of the frames of rounds 0..R-1 does not depend on the number of ranks when
+ * world * frames_per_rank is kept constant, hence neither do the totals. */
+int nbl_simulate_sharded(nbl_comm *comm, nbl_decoder *const *decoders, const nbl_sim_config *cfg, uint64_t frames_per_rank,
+                         uint64_t round_index, uint64_t *totals);
 
 /* timing hook: milliseconds the GPU spent in the decode kernels of the last nbl_decode_batch /
  * nbl_demap_decode_batch / nbl_simulate call on this decoder (CUDA events on the decoder's stream),

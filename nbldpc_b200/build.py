@@ -6,10 +6,10 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libnbldpc_b200.so")
-SOURCES = ["decoder.cu", "encoder.cu", "code.cpp"]
+SOURCES = ["decoder.cu", "encoder.cu", "code.cpp", "comm.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               # parity mode must not contract a*b+c (e.g. 0.25*old + 0.75*new, NBLDPC.cpp:1046)
-              "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl"]
 
 
 def _stale():

@@ -13,8 +13,9 @@ from . import build as _build
 METHOD_QSPA, METHOD_EMS, METHOD_TEMS, METHOD_BSTEMS = 1, 2, 4, 7
 PREC_F32, PREC_F64 = 0, 1
 TIES_AUTO, TIES_FAST, TIES_REFERENCE, TIES_BITEXACT = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GROUP, KERNEL_WARP_GENERIC = 0, 1, 2
 NUM_COUNTERS = 8
-COUNTER_NAMES = ["frames", "err_frames", "err_syms", "err_bits", "converged", "undetected", "iterations", "reserved"]
+COUNTER_NAMES = ["frames", "err_frames", "err_syms", "err_bits", "converged", "undetected", "iterations", "crc_ok"]
 
 _lib = None
 
@@ -30,7 +31,7 @@ class CodeInfo(C.Structure):
 class DecoderConfig(C.Structure):
     _fields_ = [("method", C.c_int), ("max_iter", C.c_int), ("p0", C.c_int), ("p1", C.c_int), ("factor", C.c_double),
                 ("offset", C.c_double), ("precision", C.c_int), ("early_stop", C.c_int), ("max_batch", C.c_int),
-                ("device", C.c_int), ("tie_mode", C.c_int)]
+                ("device", C.c_int), ("tie_mode", C.c_int), ("kernel", C.c_int)]
 
 
 class OsdConfig(C.Structure):
@@ -41,7 +42,7 @@ class OsdConfig(C.Structure):
 class SimConfig(C.Structure):
     _fields_ = [("ebn0_db", C.c_double), ("modulation", C.c_int), ("constellation", C.c_void_p), ("seed", C.c_uint64),
                 ("first_frame", C.c_uint64), ("frames", C.c_uint64), ("codewords", C.c_void_p), ("n_codewords", C.c_int),
-                ("random_msg", C.c_int), ("crc_len", C.c_int)]
+                ("random_msg", C.c_int), ("crc_len", C.c_int), ("punct_sym", C.c_void_p), ("n_punct", C.c_int)]
 
 
 def lib_path():
@@ -84,6 +85,17 @@ def lib():
         L.nbl_simulate_async.argtypes = [vp, C.POINTER(SimConfig), vp]
         L.nbl_decoder_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.nbl_decoder_iter_timing.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.nbl_comm_create.argtypes = [C.POINTER(vp), C.c_int, ip]
+        L.nbl_comm_unique_id.argtypes = [vp]
+        L.nbl_comm_create_rank.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, C.c_int]
+        L.nbl_comm_destroy.argtypes = [vp]
+        L.nbl_comm_destroy.restype = None
+        L.nbl_comm_size.argtypes = [vp]
+        L.nbl_comm_local_ranks.argtypes = [vp]
+        L.nbl_comm_rank.argtypes = [vp, C.c_int]
+        L.nbl_comm_device.argtypes = [vp, C.c_int]
+        L.nbl_allreduce_counters.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        L.nbl_simulate_sharded.argtypes = [vp, C.POINTER(vp), C.POINTER(SimConfig), C.c_uint64, C.c_uint64, vp]
         L.nbl_encoder_create.argtypes = [C.POINTER(vp), vp, C.c_int, vp]
         L.nbl_encoder_destroy.argtypes = [vp]
         L.nbl_encoder_destroy.restype = None
@@ -215,11 +227,83 @@ class Encoder:
         return out
 
 
+def sim_config(ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, random_msg=0, crc_len=0, punct=None):
+    """nbl_sim_config + the arrays it points into (keep them alive for the duration of the call)"""
+    cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
+    cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
+    ps = np.ascontiguousarray(punct, np.int32) if punct is not None and len(punct) else None
+    cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0],
+                    int(random_msg), int(crc_len), _ptr(ps), 0 if ps is None else len(ps))
+    return cfg, (cs, cw, ps)
+
+
+class Comm:
+    """nbl_comm: the ranks whose Monte-Carlo counters are summed (NCCL).  Comm(n) = one process driving GPUs 0..n-1;
+    Comm.from_rank(world, rank, id128, device) = one process per GPU (id128 from Comm.unique_id() on rank 0)."""
+
+    def __init__(self, n_devices=1, devices=None, _handle=None):
+        if _handle is not None:
+            self._h = _handle
+            return
+        h = C.c_void_p()
+        dv = np.ascontiguousarray(devices, np.int32) if devices is not None else None
+        _check(lib().nbl_comm_create(C.byref(h), n_devices, _ip(dv)))
+        self._h = h
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, np.uint8)
+        _check(lib().nbl_comm_unique_id(_ptr(buf)))
+        return buf
+
+    @classmethod
+    def from_rank(cls, world, rank, id128, device):
+        h = C.c_void_p()
+        ident = np.ascontiguousarray(id128, np.uint8) if id128 is not None else None
+        _check(lib().nbl_comm_create_rank(C.byref(h), world, rank, _ptr(ident), device))
+        return cls(_handle=h)
+
+    size = property(lambda self: lib().nbl_comm_size(self._h))
+    local_ranks = property(lambda self: lib().nbl_comm_local_ranks(self._h))
+
+    def rank(self, i=0):
+        return lib().nbl_comm_rank(self._h, i)
+
+    def device(self, i=0):
+        return lib().nbl_comm_device(self._h, i)
+
+    def allreduce_counters(self, decoders, dev_counters):
+        """in-place sum over all ranks of each local rank's device uint64[8] (queued on the decoders' streams)"""
+        n = len(decoders)
+        hs = (C.c_void_p * n)(*[d._h for d in decoders])
+        ps = (C.c_void_p * n)(*[_ptr(c) for c in dev_counters])
+        _check(lib().nbl_allreduce_counters(self._h, hs, ps))
+
+    def simulate_sharded(self, decoders, frames_per_rank, round_index, totals, **sim):
+        """one round (nbl_simulate_sharded): totals (numpy uint64[8]) += the round's counters summed over all ranks"""
+        n = len(decoders)
+        hs = (C.c_void_p * n)(*[d._h for d in decoders])
+        cfg, keep = sim_config(frames=0, **sim)
+        _check(lib().nbl_simulate_sharded(self._h, hs, C.byref(cfg), frames_per_rank, round_index, _ptr(totals)))
+        return totals
+
+    def close(self):
+        if self._h:
+            lib().nbl_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Decoder:
     def __init__(self, code, method, max_iter=10, p0=0, p1=0, factor=1.0, offset=0.0, precision=PREC_F32, early_stop=1,
-                 max_batch=1, device=0, stream=None, tie_mode=TIES_AUTO):
+                 max_batch=1, device=0, stream=None, tie_mode=TIES_AUTO, kernel=KERNEL_AUTO):
         self.code = code
-        self.cfg = DecoderConfig(method, max_iter, p0, p1, factor, offset, precision, early_stop, max_batch, device, tie_mode)
+        self.cfg = DecoderConfig(method, max_iter, p0, p1, factor, offset, precision, early_stop, max_batch, device, tie_mode, kernel)
         h = C.c_void_p()
         _check(lib().nbl_decoder_create(C.byref(h), code._h, C.byref(self.cfg), stream))
         self._h = h
@@ -294,21 +378,17 @@ class Decoder:
         _check(lib().nbl_demap_decode_batch(self._h, modulation, _ptr(y), B, _ptr(constellation), float(sigma), None, 0,
                                             _ptr(out_sym), _ptr(converged), _ptr(iterations)))
 
-    def simulate(self, ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, counters=None, random_msg=0, crc_len=0):
-        cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
-        cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
-        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg), int(crc_len))
+    def simulate(self, ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, counters=None, random_msg=0, crc_len=0, punct=None):
+        cfg, keep = sim_config(ebn0_db, frames, seed, first_frame, modulation, constellation, codewords, random_msg, crc_len, punct)
         cnt = counters if counters is not None else np.zeros(NUM_COUNTERS, np.uint64)
         _check(lib().nbl_simulate(self._h, C.byref(cfg), _ptr(cnt)))
         return cnt
 
-    def simulate_async(self, ebn0_db, frames, dev_counters, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, random_msg=0, crc_len=0):
+    def simulate_async(self, ebn0_db, frames, dev_counters, seed=1, first_frame=0, modulation=2, constellation=None, codewords=None, random_msg=0, crc_len=0, punct=None):
         """queues the whole call on the decoder's stream and returns; dev_counters (device int64/uint64[8]) is accumulated
         into.  Touch the counters on the same stream (create the Decoder with stream=torch's current stream, as bench.py
         does) or after sync() -- a private decoder stream is not ordered with torch's default stream."""
-        cs = np.ascontiguousarray(constellation, np.float64) if constellation is not None else None
-        cw = np.ascontiguousarray(codewords, np.int32) if codewords is not None else None
-        cfg = SimConfig(float(ebn0_db), modulation, _ptr(cs), seed, first_frame, frames, _ptr(cw), 0 if cw is None else cw.shape[0], int(random_msg), int(crc_len))
+        cfg, keep = sim_config(ebn0_db, frames, seed, first_frame, modulation, constellation, codewords, random_msg, crc_len, punct)
         _check(lib().nbl_simulate_async(self._h, C.byref(cfg), _ptr(dev_counters)))
 
     def sync(self):

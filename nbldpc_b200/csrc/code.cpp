@@ -25,6 +25,9 @@ static bool valid_q(int q) { return q >= 4 && q <= 256 && (q & (q - 1)) == 0; }
 extern "C" int nbl_gf_tables(int q, int prim_poly, int *mul, int *inv) {
     if (!(q >= 2 && q <= 512 && (q & (q - 1)) == 0) || !mul || !inv) { nbl_set_error("nbl_gf_tables: bad q"); return NBL_ERR_ARG; }
     if (!prim_poly) prim_poly = nbl_default_poly(q);
+    // degree exactly log2 q: bit q set and nothing above it -- otherwise the reduction below would leave v >= q and index
+    // past the tables (a polynomial can come from an untrusted Arith.Table header)
+    if (!(prim_poly & q) || (prim_poly & ~(2 * q - 1)) || prim_poly < 0) { nbl_set_error("nbl_gf_tables: the polynomial must have degree log2(q)"); return NBL_ERR_ARG; }
     // powers of x: antilog/log tables, then products by index addition
     std::vector<int> alog(2 * q), lg(q, -1);
     int v = 1;
@@ -103,6 +106,19 @@ static int init_field(nbl_code *c, int q, int prim_poly) {
 extern "C" int nbl_code_create(nbl_code **out, int q, int prim_poly, int N, int M, const int *chk_ptr, const int *chk_var,
                                const int *chk_coef, const int *var_ptr, const int *var_chk, const int *var_coef) {
     if (!out || !chk_ptr || !chk_var || !chk_coef || N <= 0 || M <= 0) { nbl_set_error("nbl_code_create: bad argument"); return NBL_ERR_ARG; }
+    if (var_ptr && (!var_chk || !var_coef)) { nbl_set_error("nbl_code_create: var_ptr without var_chk / var_coef"); return NBL_ERR_ARG; }
+    if (chk_ptr[0] != 0) { nbl_set_error("nbl_code_create: chk_ptr must start at 0"); return NBL_ERR_ARG; }
+    for (int r = 0; r < M; ++r) if (chk_ptr[r + 1] < chk_ptr[r]) { nbl_set_error("nbl_code_create: chk_ptr must be non-decreasing"); return NBL_ERR_ARG; }
+    {   // a (row, variable) pair may appear once: two edges between the same nodes would alias one message slot
+        std::vector<int> seen(N, -1);
+        for (int r = 0; r < M; ++r)
+            for (int e = chk_ptr[r]; e < chk_ptr[r + 1]; ++e) {
+                const int v = chk_var[e];
+                if (v < 0 || v >= N) { nbl_set_error("nbl_code_create: variable index out of range"); return NBL_ERR_ARG; }
+                if (seen[v] == r) { nbl_set_error("nbl_code_create: duplicate edge (same check row and variable twice)"); return NBL_ERR_ARG; }
+                seen[v] = r;
+            }
+    }
     nbl_code *c = new nbl_code;
     int rc = init_field(c, q, prim_poly);
     if (rc) { delete c; return rc; }
@@ -114,6 +130,9 @@ extern "C" int nbl_code_create(nbl_code **out, int q, int prim_poly, int N, int 
     for (int e = 0; e < E; ++e) if (chk_var[e] < 0 || chk_var[e] >= N) { nbl_set_error("nbl_code_create: variable index out of range"); delete c; return NBL_ERR_ARG; }
     if (var_ptr) {
         c->var_ptr.assign(var_ptr, var_ptr + N + 1);
+        bool mono = var_ptr[0] == 0;
+        for (int v = 0; v < N; ++v) mono = mono && var_ptr[v + 1] >= var_ptr[v];
+        if (!mono) { nbl_set_error("nbl_code_create: var_ptr must start at 0 and be non-decreasing"); delete c; return NBL_ERR_ARG; }
         if (var_ptr[N] != E) { nbl_set_error("nbl_code_create: edge counts differ"); delete c; return NBL_ERR_ARG; }
         c->var_chk.assign(var_chk, var_chk + E);
         c->var_coef.assign(var_coef, var_coef + E);
@@ -172,6 +191,9 @@ extern "C" int nbl_code_load_hbit(nbl_code **out, const char *path, int q, int p
     for (auto &r : B) if (r.size() != B[0].size()) { nbl_set_error("H_bit file: ragged rows"); return NBL_ERR_IO; }
     int p = 0; while ((1 << p) < q) ++p;
     if (!prim_poly) prim_poly = nbl_default_poly(q);
+    // degree exactly log2 q: bit q set and nothing above it -- otherwise the reduction below would leave v >= q and index
+    // past the tables (a polynomial can come from an untrusted Arith.Table header)
+    if (!(prim_poly & q) || (prim_poly & ~(2 * q - 1)) || prim_poly < 0) { nbl_set_error("nbl_gf_tables: the polynomial must have degree log2(q)"); return NBL_ERR_ARG; }
     // Orientation from the shape: more rows than columns = transposed image B[p*sym+l][p*chk+k];
     // otherwise H_bin[p*chk+k][p*sym+l].  Either way block(sym,chk)[l][k] = bit k of g*x^l.
     bool transposed = B.size() > B[0].size();

@@ -14,6 +14,7 @@
 #include "internal.h"
 #include "enc_internal.h"
 #include "dev_common.cuh"
+#include "iter_params.cuh"
 #include "cn_tems.cuh"
 #include "cn_ems.cuh"
 #include "cn_qspa.cuh"
@@ -38,20 +39,6 @@ using namespace nbl;
 // ======================================================================================================
 // kernels
 // ======================================================================================================
-template <typename T> struct IterParams {
-    DevGraph g;
-    int B, iter, first, early_stop, method, p0, p1;
-    int bitexact;                       // T-EMS tie mode BITEXACT: the sequential replay of the reference's search
-    T factor, offset, w_old, w_new;
-    const T *lch;
-    T *v2c;
-    const T *c2v_in;
-    T *c2v_out;
-    uint8_t *vdec, *dec;
-    int *flag;
-    const uint8_t *done;
-    const uint8_t *pfwd_sw, *pinv_sw;   // warp fast path: the permutation tables with values as split-layout indices
-};
 
 #include "tems_warp.cuh"
 #include "ems_warp.cuh"
@@ -359,6 +346,8 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     if (cfg->method == NBL_METHOD_TEMS && cfg->tie_mode == NBL_TIES_BITEXACT && code->max_dc > 16) {
         nbl_set_error("tie mode BITEXACT needs check degree <= 16"); return NBL_ERR_ARG;
     }
+    if (code->q < 16 || code->q > 256) { nbl_set_error("nbl_decoder_create: the decode kernels cover 16 <= q <= 256 (GF(4) and GF(8) tables load, but no decoder is built for them)"); return NBL_ERR_ARG; }
+    if (cfg->kernel < NBL_KERNEL_AUTO || cfg->kernel > NBL_KERNEL_WARP_GENERIC) { nbl_set_error("nbl_decoder_create: bad kernel selector"); return NBL_ERR_ARG; }
     if (cfg->max_iter < 1 || cfg->max_batch < 1) { nbl_set_error("nbl_decoder_create: max_iter and max_batch must be >= 1"); return NBL_ERR_ARG; }
     if (cfg->method == NBL_METHOD_EMS && (cfg->p0 < 1 || cfg->p0 > code->q || cfg->p1 < 1)) {
         nbl_set_error("EMS configuration error! EMS_Nm is too large!"); return NBL_ERR_ARG;   // NBLDPC.cpp:282-286
@@ -394,7 +383,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
         all_full = all_full && deg == TW_DC;
     }
     for (int v = 0; v < code->N; ++v) all_full = all_full && code->var_ptr[v + 1] - code->var_ptr[v] == TW_HOIST;
-    d->warp_regular = all_full && !getenv("NBLDPC_WARP_GENERIC");
+    d->warp_regular = all_full && cfg->kernel != NBL_KERNEL_WARP_GENERIC;
     if (desc_ok) {
         std::vector<int> rd((size_t)code->M * 32, 0);
         for (int r = 0; r < code->M; ++r) {
@@ -417,8 +406,8 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
             if ((rc = upload(&d->d_pfwd_sw, pfs)) || (rc = upload(&d->d_pinv_sw, pis))) return fail(rc);
         }
     }
-    if (q == 16 && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV &&
-        !getenv("NBLDPC_FORCE_GENERIC")) {
+    const bool fast_ok = cfg->kernel != NBL_KERNEL_GROUP;           // NBL_KERNEL_GROUP: every configuration on the generic kernel
+    if (q == 16 && code->max_dc <= QH_MAXDC && code->max_dv <= QH_MAXDV && N < (1 << 15) && fast_ok) {      // the GF(16) kernels pack the variable index into 15 bits
         std::vector<int> rd((size_t)code->M * QH_MAXDC * QH_DSC, 0);
         for (int r = 0; r < code->M; ++r)
             for (int e = code->chk_ptr[r]; e < code->chk_ptr[r + 1]; ++e) {
@@ -449,19 +438,19 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     d->smem_iter = smem_for(d, q);
     if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_BITEXACT) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
     const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || cfg->tie_mode == NBL_TIES_BITEXACT || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
-    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && !getenv("NBLDPC_FORCE_GENERIC");
+    d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && fast_ok;
     d->tems_half_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && q == 16 && d->d_rowdesc8 != nullptr && !ref_ties;
     if (cfg->method == NBL_METHOD_BSTEMS && q == 16 && d->d_rowdesc8 != nullptr) d->tems_half_path = true;      // the same kernel with BS = 1
     d->ems_half_path = cfg->method == NBL_METHOD_EMS && q == 16 && d->d_rowdesc8 != nullptr && cfg->p0 <= EH_MAXNM && cfg->p1 + 1 <= EH_MAXNJ;
     // BS-TEMS on the same kernel (its search replaced by the basic-set walk): no tie modes, the walk is the reference's own
-    if (cfg->method == NBL_METHOD_BSTEMS && desc_ok && q >= 32 && cfg->offset >= 0.0 && !getenv("NBLDPC_FORCE_GENERIC")) d->warp_path = true;
+    if (cfg->method == NBL_METHOD_BSTEMS && desc_ok && q >= 32 && cfg->offset >= 0.0 && fast_ok) d->warp_path = true;
     {
         const bool pow2 = cfg->p0 >= 1 && (cfg->p0 & (cfg->p0 - 1)) == 0;
         long long combos = 1;
         for (int i = 0; i + 1 < code->max_dc; ++i) combos *= cfg->p0;
-        d->qspa_warp_path = cfg->method == NBL_METHOD_QSPA && desc_ok && q >= 32 && !getenv("NBLDPC_FORCE_GENERIC");
+        d->qspa_warp_path = cfg->method == NBL_METHOD_QSPA && desc_ok && q >= 32 && fast_ok;
         d->ems_warp_path = cfg->method == NBL_METHOD_EMS && desc_ok && q >= 32 && pow2 && cfg->p0 <= EW_MAXNM && cfg->p0 <= q &&
-                           combos <= EW_MAXCOMBOS && !getenv("NBLDPC_FORCE_GENERIC");
+                           combos <= EW_MAXCOMBOS && fast_ok;
     }
     if (d->smem_iter > 227 * 1024) { nbl_set_error("decoder configuration needs more shared memory than one SM has"); return fail(NBL_ERR_ARG); }
     *out = d;
@@ -896,7 +885,8 @@ static int demap_common(nbl_decoder *d, int modulation, const double *y, int B, 
     }
     if (modulation != 2) {
         if (!constellation) { nbl_set_error("QAM demapping needs a constellation"); return NBL_ERR_ARG; }
-        CK(cudaMemcpyAsync(d->d_cons, constellation, 2 * q * sizeof(double), is_device_ptr(constellation) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d->stream));
+        if (constellation != d->d_cons)                             // nbl_simulate hands in the resident copy
+            CK(cudaMemcpyAsync(d->d_cons, constellation, 2 * q * sizeof(double), is_device_ptr(constellation) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d->stream));
     }
     const size_t tot = (size_t)B * N * q;
     const unsigned grid = (unsigned)((tot + 255) / 256);
@@ -1042,8 +1032,11 @@ __device__ inline bool crc_check(const int *sym, int K, int p, int crc_len) {
 
 // received samples of B frames.  BPSK: y[f][N*p] = (1 - 2 bit) + sigma n  (0 -> +1, 1 -> -1, BPSK.txt; bit b of
 // symbol s is sample s*p+b, Comm.cpp:272-279).  QAM: y[f][N][2] = constellation[symbol] + sigma (n_re, n_im).
+// ysym[s] = offset of symbol s's first sample inside a frame's y (punctured symbols: -1, not transmitted, Comm.cpp:290-308);
+// the noise of a sample depends on its position in the UNPUNCTURED frame, so puncturing does not move the other samples' noise.
 __global__ void k_sim_channel(int B, int N, int p, int modulation, uint64_t seed, uint64_t first_frame, double sigma,
-                              const uint8_t *__restrict__ tx, const double *__restrict__ cs, double *__restrict__ y) {
+                              const uint8_t *__restrict__ tx, const double *__restrict__ cs, const int *__restrict__ ysym, int ylen,
+                              double *__restrict__ y) {
     const int per = modulation == 2 ? (N * p + 1) / 2 : N;          // Philox blocks per frame (2 normals each)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * per) return;
@@ -1057,13 +1050,15 @@ __global__ void k_sim_channel(int B, int N, int p, int modulation, uint64_t seed
         for (int h = 0; h < 2; ++h) {
             const int b = 2 * j + h;
             if (b >= L) break;
-            const int bit = (cw[b / p] >> (b % p)) & 1;
-            y[(size_t)f * L + b] = (bit ? -1.0 : 1.0) + sigma * (h ? z1 : z0);
+            const int bit = (cw[b / p] >> (b % p)) & 1, off = ysym[b / p];
+            if (off >= 0) y[(size_t)f * ylen + off + b % p] = (bit ? -1.0 : 1.0) + sigma * (h ? z1 : z0);
         }
     } else {
-        const int sym = cw[j];
-        y[((size_t)f * N + j) * 2] = cs[2 * sym] + sigma * z0;
-        y[((size_t)f * N + j) * 2 + 1] = cs[2 * sym + 1] + sigma * z1;
+        const int sym = cw[j], off = ysym[j];
+        if (off >= 0) {
+            y[((size_t)f * ylen + off) * 2] = cs[2 * sym] + sigma * z0;
+            y[((size_t)f * ylen + off) * 2 + 1] = cs[2 * sym + 1] + sigma * z1;
+        }
     }
 }
 
@@ -1104,10 +1099,11 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
     if (cfg->modulation != 2 && !cfg->constellation) { nbl_set_error("nbl_simulate: QAM needs a constellation"); return NBL_ERR_ARG; }
     if (cfg->n_codewords < 0 || (cfg->n_codewords > 0 && !cfg->codewords)) { nbl_set_error("nbl_simulate: bad codeword pool"); return NBL_ERR_ARG; }
     const double mbits = cfg->modulation == 2 ? 1.0 : (double)p;
-    const double rate = (double)K / (double)N;
+    if (cfg->n_punct < 0 || cfg->n_punct >= N || (cfg->n_punct > 0 && !cfg->punct_sym)) { nbl_set_error("nbl_simulate: bad puncture list"); return NBL_ERR_ARG; }
+    const double rate = (double)K / (double)(N - cfg->n_punct);                                 // Comm.cpp:98: R = K / (N - punctured)
     const double sigma = 1.0 / sqrt(2.0 * mbits * rate * pow(10.0, cfg->ebn0_db / 10.0));      // Comm.cpp:176-177
     int rc, ylen;
-    if ((rc = setup_punct(d, cfg->modulation, nullptr, 0, &ylen))) return rc;
+    if ((rc = setup_punct(d, cfg->modulation, cfg->punct_sym, cfg->n_punct, &ylen))) return rc;
     // codeword pool -> device bytes
     if (cfg->n_codewords && !(d->pool_host.size() == (size_t)cfg->n_codewords * N &&
                               memcmp(d->pool_host.data(), cfg->codewords, d->pool_host.size() * sizeof(int)) == 0)) {
@@ -1160,9 +1156,9 @@ static int simulate_impl(nbl_decoder *d, const nbl_sim_config *cfg, unsigned lon
             CK(cudaGetLastError());
         }
         k_sim_channel<<<(unsigned)((nthr + 255) / 256), 256, 0, d->stream>>>(B, N, p, cfg->modulation, cfg->seed, cfg->first_frame + done, sigma,
-                                                                            d->d_tx, d->d_cons, d->d_ystage);
+                                                                            d->d_tx, d->d_cons, d->d_ysym, ylen, d->d_ystage);
         CK(cudaGetLastError());
-        if ((rc = demap_common(d, cfg->modulation, d->d_ystage, B, d->d_cons, sigma, nullptr, 0, true, nullptr))) return rc;
+        if ((rc = demap_common(d, cfg->modulation, d->d_ystage, B, d->d_cons, sigma, cfg->punct_sym, cfg->n_punct, true, nullptr))) return rc;
         rc = d->cfg.precision == NBL_PREC_F64 ? run_decode<double>(d, B, nullptr) : run_decode<float>(d, B, nullptr);
         if (rc) return rc;
         k_sim_count<<<(B + 127) / 128, 128, 0, d->stream>>>(B, N, K, p, cfg->crc_len, d->d_tx, d->d_out, d->d_conv, d->d_iters, dev_counters);
@@ -1179,6 +1175,39 @@ extern "C" int nbl_simulate_async(nbl_decoder *d, const nbl_sim_config *cfg, uin
     if (!is_device_ptr(dev_counters)) { nbl_set_error("nbl_simulate_async: counters must be device memory"); return NBL_ERR_ARG; }
     CK(cudaSetDevice(d->cfg.device));
     return simulate_impl(d, cfg, (unsigned long long *)dev_counters);
+}
+
+// One round of a sharded Monte-Carlo run: the multi-GPU form of one pass of the reference's frame loop (main.cpp:43-55: `parallel`
+// workers simulate one frame each, then their counters are added).  Local rank i (global rank r_i of `world`) simulates the
+// frames_per_rank frames starting at  cfg->first_frame + (round_index * world + r_i) * frames_per_rank  on decoders[i]; the
+// counter vectors are summed over all ranks on the device (nbl_allreduce_counters) and the total of the round is ADDED to
+// totals (host uint64[8]).  Every rank gets the same totals, so every rank takes the same stop decision.
+extern "C" int nbl_simulate_sharded(nbl_comm *comm, nbl_decoder *const *decoders, const nbl_sim_config *cfg, uint64_t frames_per_rank,
+                                    uint64_t round_index, uint64_t *totals) {
+    if (!comm || !decoders || !cfg || !totals) { nbl_set_error("nbl_simulate_sharded: null argument"); return NBL_ERR_ARG; }
+    const int n = nbl_comm_local_ranks(comm), world = nbl_comm_size(comm);
+    std::vector<uint64_t *> dev(n);
+    for (int i = 0; i < n; ++i) {
+        nbl_decoder *d = decoders[i];
+        if (!d) { nbl_set_error("nbl_simulate_sharded: null decoder"); return NBL_ERR_ARG; }
+        CK(cudaSetDevice(d->cfg.device));
+        if (!d->d_counters) CK(cudaMalloc((void **)&d->d_counters, NBL_NUM_COUNTERS * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(d->d_counters, 0, NBL_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
+        nbl_sim_config c = *cfg;
+        c.frames = frames_per_rank;
+        c.first_frame = cfg->first_frame + (round_index * (uint64_t)world + (uint64_t)nbl_comm_rank(comm, i)) * frames_per_rank;
+        const int rc = simulate_impl(d, &c, d->d_counters);         // asynchronous: the GPUs of this process run concurrently
+        if (rc) return rc;
+        dev[i] = (uint64_t *)d->d_counters;
+    }
+    int rc = nbl_allreduce_counters(comm, decoders, dev.data());
+    if (rc) return rc;
+    unsigned long long host[NBL_NUM_COUNTERS];
+    CK(cudaSetDevice(decoders[0]->cfg.device));
+    CK(cudaMemcpyAsync(host, decoders[0]->d_counters, sizeof host, cudaMemcpyDeviceToHost, decoders[0]->stream));
+    for (int i = 0; i < n; ++i) { CK(cudaSetDevice(decoders[i]->cfg.device)); CK(cudaStreamSynchronize(decoders[i]->stream)); }
+    for (int i = 0; i < NBL_NUM_COUNTERS; ++i) totals[i] += host[i];
+    return NBL_OK;
 }
 
 extern "C" int nbl_simulate(nbl_decoder *d, const nbl_sim_config *cfg, uint64_t *counters) {

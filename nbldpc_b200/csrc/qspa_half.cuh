@@ -128,7 +128,7 @@ __device__ __forceinline__ void qh_vn_phase(const IterParams<T> &P, const int *_
     uint8_t *vdecf = P.vdec + (size_t)f * g.E;
     // software pipeline over the edges: descriptor of edge d + 2 and messages of edge d + 1 are in flight during edge d
     int4 da[2]; int2 db[2];                                         // {variable, degree, edge ids 0..1}, {edge ids 2..3}
-    T lc[2][4], mm[2][QH_MAXDV][4]; int meta[2];                    // meta: own slot | degree << 4 | old decision + 1 << 8 | variable << 17
+    T lc[2][4], mm[2][QH_MAXDV][4]; unsigned meta[2];               // meta: own slot | degree << 4 | old decision + 1 << 8 | variable << 17 (N < 2^15, checked by the host)
     auto fetch_desc = [&](int d, int slot) {
         da[slot] = make_int4(0, 0, 0, 0); db[slot] = make_int2(0, 0);
         if (d < dcn) { da[slot] = *reinterpret_cast<const int4 *>(rd + QH_DSC * d); db[slot] = *reinterpret_cast<const int2 *>(rd + QH_DSC * d + 4); }
@@ -152,7 +152,7 @@ __device__ __forceinline__ void qh_vn_phase(const IterParams<T> &P, const int *_
             }
             bef = P.first ? 0 : (int)vdecf[e0 + d] + 1;
         }
-        meta[slot] = own | (nv << 4) | (bef << 8) | (da[slot].x << 17);
+        meta[slot] = (unsigned)own | ((unsigned)nv << 4) | ((unsigned)bef << 8) | ((unsigned)da[slot].x << 17);
     };
     sdw = 0u;
     int syn = 0;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void qh_vn_phase(const IterParams<T> &P, const int *_
             const int slot = d & 1;
             if (d + 1 < QH_MAXDC) fetch_msgs(d + 1, slot ^ 1);      // needs descriptor d + 1 (requested one step ago)
             const bool live = d < dcn;
-            const int e = e0 + d, own = meta[slot] & 15, nv = (meta[slot] >> 4) & 15, bef = (meta[slot] >> 8) & 511, col = meta[slot] >> 17;
+            const int e = e0 + d, own = (int)(meta[slot] & 15u), nv = (int)((meta[slot] >> 4) & 15u), bef = (int)((meta[slot] >> 8) & 511u), col = (int)(meta[slot] >> 17);
             if (live) {
                 tf[d] = *reinterpret_cast<const unsigned *>(g.pfwd + (size_t)e * Q + x0);
                 ti[d] = *reinterpret_cast<const unsigned *>(g.pinv + (size_t)e * Q + x0);

@@ -31,6 +31,7 @@
 // is replaced by the basic-set construction and the walk over its subsets (see the BS block in the kernel).
 #pragma once
 #include "dev_common.cuh"
+#include "iter_params.cuh"
 #include <type_traits>
 
 namespace nbl {

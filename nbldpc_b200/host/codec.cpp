@@ -52,7 +52,7 @@ bool CNBLDPC::Initial(CSimulation &sim) {
     basic_set_Nm = sim.bs_tems_nm; basic_set_Nc = sim.bs_tems_nc; basic_set_factor = sim.bs_tems_factor; basic_set_offset = sim.bs_tems_offset;   // NBLDPC.cpp:334-337
     OSD_Order = sim.OSD_order; OSD_Alpha = sim.OSD_factor; OSD_flag = sim.OSD_flag;     // NBLDPC.cpp:381-383
     CRCLen = sim.crcLen; CRCrate = sim.crc_correctLen;                                  // NBLDPC.cpp:437-438
-    precision_ = sim.precision;
+    precision_ = sim.precision; device_ = sim.device;
     if (DecodeMethod == EMS_DECODE && EMS_Nm > GFq) { std::cerr << "EMS configuration error! EMS_Nm is too large!" << std::endl; exit(-1); }
 
     post_.assign((size_t)CodeLen * (GFq - 1), 0.0);
@@ -127,8 +127,7 @@ int CNBLDPC::ensure_decoder(int batch) {
     if (dec_ && dec_batch_ >= batch) return 0;
     if (dec_) { nbl_decoder_destroy(dec_); dec_ = nullptr; }
     nbl_decoder_config cfg{};
-    cfg.method = DecodeMethod; cfg.max_iter = maxIter; cfg.precision = precision_; cfg.early_stop = 1; cfg.max_batch = batch; cfg.device = 0;
-    if (const char *dv = getenv("NBLDPC_DEVICE")) cfg.device = atoi(dv);
+    cfg.method = DecodeMethod; cfg.max_iter = maxIter; cfg.precision = precision_; cfg.early_stop = 1; cfg.max_batch = batch; cfg.device = device_;
     if (PunctureLen > 0) cfg.tie_mode = NBL_TIES_REFERENCE;    // erased symbols make configuration costs tie exactly
     if (DecodeMethod == EMS_DECODE) { cfg.p0 = EMS_Nm; cfg.p1 = EMS_Nc; cfg.factor = EMS_Correction_Factor; cfg.offset = EMS_Correction_Offset; }
     else if (DecodeMethod == T_EMS_DECODE) { cfg.p0 = TEMS_Nr; cfg.p1 = TEMS_Nc; cfg.factor = TEMS_Factor; cfg.offset = TEMS_Offset; }
@@ -187,6 +186,15 @@ int CNBLDPC::Decoding(double **L_ch, int *DecodeOutput, int *RelySeri_symbol, in
     case OSD_DECODE: return Decoding_OSD_bit(L_ch, DecodeOutput, RelySeri_bit, 1);
     default: std::cout << "Decode Method is not specified!" << std::endl; exit(-1);
     }
+    return 0;
+}
+
+// CComm::Demodulate on the device (bit-identical with the host form, tests/test_decode_gpu.py): y -> L_ch [B][N][q-1] host doubles
+int CNBLDPC::DemapBatch(int modulation, const double *y, int B, const double *constellation, double sigma, double *L_ch) {
+    ensure_decoder(B);
+    const int rc = modulation == 2 ? nbl_demap_bpsk(dec_, y, B, sigma, PuncturePosition, PunctureLen, L_ch)
+                                   : nbl_demap_qam(dec_, y, B, constellation, sigma, PuncturePosition, PunctureLen, L_ch);
+    if (rc != NBL_OK) die("demap");
     return 0;
 }
 

@@ -50,12 +50,13 @@ public:
     // decisions [B][CodeLen], return codes and iteration counts; demapping happens on the device.
     int DecodingBatch(int modulation, const double *y, int B, const double *constellation, double sigma,
                       int *DecodeOutput, int *converged, int *iterations);
+    int DemapBatch(int modulation, const double *y, int B, const double *constellation, double sigma, double *L_ch);
     nbl_code *code() { return code_; }
 
 private:
     nbl_code *code_ = nullptr;
     nbl_decoder *dec_ = nullptr;
-    int dec_batch_ = 0, precision_ = 1;
+    int dec_batch_ = 0, precision_ = 1, device_ = 0;
     std::vector<int> graph_;                   // backing store of the link tables
     std::vector<int *> rows_;
     std::vector<double> post_, lch_;

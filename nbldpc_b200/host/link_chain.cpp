@@ -71,8 +71,19 @@ double CComm::SetEbN0(CSimulation &sim, int parallel_order) {
 }
 
 int CComm::Transmission() {
-    GenerateMessage(); Encode(); Puncture(); Modulate(); Channel_AWGN(); Demodulate(); Decode();
+    GenerateMessage(); Encode(); Puncture(); Modulate(); Channel_AWGN(); DemodulateDevice(); Decode();      // front end + decoder on the GPU
     return 0;
+}
+
+int CComm::DemodulateDevice(void) {
+    const int per = modOrder == 2 ? 1 : 2;
+    std::vector<double> y((size_t)MOD_SYM_LEN * per), cons;
+    for (int s = 0; s < MOD_SYM_LEN; ++s) {
+        if (per == 1) y[s] = RX_MOD_SYM[s].Real;
+        else { y[2 * s] = RX_MOD_SYM[s].Real; y[2 * s + 1] = RX_MOD_SYM[s].Image; }
+    }
+    if (per == 2) for (int k = 0; k < modOrder; ++k) { cons.push_back(CONSTELLATION[k].Real); cons.push_back(CONSTELLATION[k].Image); }
+    return NBLDPC.DemapBatch(modOrder, y.data(), 1, per == 2 ? cons.data() : nullptr, sigma_n, RX_LLR_SYM[0]);   // the rows of RX_LLR_SYM are one dense block
 }
 
 int CComm::GenPN(void) {                        // 11-stage LFSR, feedback reg[10]^reg[3] after the shift (Comm.cpp:241-252)

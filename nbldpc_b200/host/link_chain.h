@@ -53,7 +53,8 @@ public:
 
     double *RX_LLR_BIT = nullptr;
     double **RX_LLR_SYM = nullptr;
-    int Demodulate(void);
+    int Demodulate(void);                       // host form (runs without a GPU; what the reference computes, same operation order)
+    int DemodulateDevice(void);                 // the same LLRs from the device demapper (nbl_demap_bpsk / nbl_demap_qam); Transmission() uses this one
 
     int *RX_DECODE_SYM = nullptr, *RX_DECODE_BIT = nullptr, *RX_MSG_SYM = nullptr, *RX_MSG_BIT = nullptr;
     int *ReliableSeri_Symbol = nullptr, *ReliableSeri_BIT = nullptr;

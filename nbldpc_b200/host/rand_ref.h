@@ -1,6 +1,8 @@
-// The reference's noise source, needed verbatim so that the harness feeds the decoder the same inputs:
-// three multiplicative congruential generators (moduli 61967 / 63443 / 63599) summed modulo 1, and the cosine
-// branch of Box-Muller with u1 drawn before u2 (Rand.cpp:17-38).
+// QUOTED FROM THE REFERENCE, not original work: Rand_Uniform / Rand_Norm below restate YongonY/NBLDPC Rand.cpp:17-38 almost
+// token for token, because parity needs the harness to feed the decoder bit-identical inputs -- the constants and the order
+// of the floating-point operations cannot differ: three multiplicative congruential generators (multipliers 249 / 251 / 252,
+// moduli 61967 / 63443 / 63599) summed modulo 1, and the cosine branch of Box-Muller with u1 drawn before u2.
+// Used by the parity harness only; the device Monte-Carlo draws its noise with Philox (csrc/decoder.cu).
 #pragma once
 #include <cmath>
 

@@ -26,7 +26,6 @@ int CSimulation::Initial(std::string profilename) {
     field(f, 2, randomMsg); field(f, 3, minErrFrame); field(f, 3, U_minErrFrame); field(f, 3, minSimCycle);
     field(f, 2, randomseed); field(f, 3, showSimFrameStep);
     if (!f) { std::cerr << "Profile " << profilename << " is incomplete" << std::endl; exit(-1); }
-    if (const char *p = getenv("NBLDPC_PRECISION")) precision = atoi(p);      // 0 = fp32 fast mode, 1 = fp64 parity mode
     EbN0 = snrBegin - snrStep;
     return 0;
 }

@@ -36,7 +36,8 @@ public:
     int minSimCycle = 0, minErrFrame = 0, U_minErrFrame = 0, showSimFrameStep = 1;
     // additions of this harness (not in the reference): decoded-iteration statistics and GPU precision
     double sumIterations = 0;
-    int precision = 1;      // NBL_PREC_F64 by default: bit-exact decisions with the reference
+    int precision = 1;      // NBL_PREC_F64 by default: bit-exact decisions with the reference (driver flag --fp32 / --fp64)
+    int device = 0;         // CUDA device of the per-frame / batched paths (driver flag --device)
     std::chrono::steady_clock::time_point start;
 
     int Initial(std::string profilename);

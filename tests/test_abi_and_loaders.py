@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(capi.lib_path())
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert capi.lib().nbl_abi_version() == 3
+    assert capi.lib().nbl_abi_version() == 4
 
 
 def test_gf_tables_match_oracle_and_reference_files():
@@ -108,3 +108,49 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
     code = capi.Code.from_checks(16, 4, [[(0, 1), (1, 2), (2, 3)], [(1, 1), (2, 1), (3, 5)]])
     with pytest.raises(capi.NblError, match="no CPU fallback"):
         capi.Decoder(code, capi.METHOD_TEMS, 10, 2, 2, 1.0, 0.5)
+
+
+def test_gf_tables_reject_polynomials_of_the_wrong_degree():
+    """a polynomial without bit q, or with bits above it, must be refused (it would index past the log tables)"""
+    for q, poly in ((64, 19), (16, 19 | 64), (16, 3), (256, 285 << 1), (16, -19)):
+        with pytest.raises(capi.NblError):
+            capi.gf_tables(q, poly)
+    capi.gf_tables(16, 25)                  # x^4 + x^3 + 1: the other primitive polynomial of GF(16) is accepted
+
+
+def test_code_create_argument_checks():
+    ok = [[(0, 1), (1, 2)], [(1, 3), (2, 1)]]
+    capi.Code.from_checks(16, 3, ok)
+    with pytest.raises(capi.NblError):      # the same (row, variable) edge twice
+        capi.Code.from_checks(16, 3, [[(0, 1), (0, 2)], [(1, 3), (2, 1)]])
+    with pytest.raises(capi.NblError):      # variable index out of range
+        capi.Code.from_checks(16, 3, [[(0, 1), (3, 2)], [(1, 3), (2, 1)]])
+    with pytest.raises(capi.NblError):      # coefficient out of range
+        capi.Code.from_checks(16, 3, [[(0, 1), (1, 16)], [(1, 3), (2, 1)]])
+    L = capi.lib()
+    h = ctypes.c_void_p()
+    cptr = np.array([0, 2, 1], np.int32); cvar = np.array([0, 1], np.int32); ccoef = np.array([1, 2], np.int32)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    assert L.nbl_code_create(ctypes.byref(h), 16, 0, 3, 2, ip(cptr), ip(cvar), ip(ccoef), None, None, None) < 0     # chk_ptr decreases
+    vptr = np.array([0, 1, 2, 2], np.int32)
+    cptr = np.array([0, 1, 2], np.int32)
+    assert L.nbl_code_create(ctypes.byref(h), 16, 0, 3, 2, ip(cptr), ip(cvar), ip(ccoef), ip(vptr), None, None) < 0  # var_ptr without lists
+
+
+def test_no_gpu_no_fallback_for_the_multi_gpu_entry_points():
+    """the communicator refuses to exist without its devices (and never falls back to a host reduction)"""
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.NblError):
+        capi.Comm(1)
+    with pytest.raises(capi.NblError):
+        capi.Comm.from_rank(1, 0, None, 0)
+
+
+def test_nothing_in_the_library_reads_the_environment():
+    """kernel selection is a field of nbl_decoder_config; a stray environment variable must not move a decode to another kernel"""
+    src = os.path.join(ROOT, "nbldpc_b200")
+    for sub in ("csrc", "host"):
+        for f in os.listdir(os.path.join(src, sub)):
+            if f.endswith((".cu", ".cuh", ".cpp", ".h")):
+                assert "getenv" not in open(os.path.join(src, sub, f)).read(), f

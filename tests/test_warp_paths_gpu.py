@@ -48,24 +48,15 @@ def _frames(code, F, sigma, rng):
     return np.stack([po.demap_bpsk(code["q"], code["N"], 1.0 + sigma * rng.standard_normal(code["N"] * p), sigma) for _ in range(F)])
 
 
-def _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset, env=None, max_iter=6, tie_mode=1):
+def _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset, kernel=0, max_iter=6, tie_mode=1):
     from nbldpc_b200 import capi
     from oracle import pyoracle as po
     path = tmp_path / ("code_%d_%d.txt" % (code["q"], code["N"]))
     path.write_text(po.code_text(code))
     oc = po.OracleCode(code)
     want = [oc.decode(4, max_iter, p0, p1, factor, offset, l) for l in lch]
-    old = {k: os.environ.get(k) for k in (env or {})}
-    os.environ.update(env or {})
-    try:
-        dec = capi.Decoder(capi.Code.from_file(str(path)), 4, max_iter, p0, p1, factor, offset, precision=capi.PREC_F64,
-                           max_batch=len(lch), tie_mode=tie_mode)               # 1: the warp kernel also in fp64
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+    dec = capi.Decoder(capi.Code.from_file(str(path)), 4, max_iter, p0, p1, factor, offset, precision=capi.PREC_F64,
+                       max_batch=len(lch), tie_mode=tie_mode, kernel=kernel)               # 1: the warp kernel also in fp64
     r = dec.decode(lch, want_post=True)
     assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
     assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
@@ -98,21 +89,16 @@ def test_parameter_branches(p0, p1, factor, offset, tmp_path):
         _check_against_oracle(code, tmp_path, lch, p0, p1, factor, offset)
 
 
-@pytest.mark.parametrize("env", [{"NBLDPC_WARP_GENERIC": "1"}, {"NBLDPC_FORCE_GENERIC": "1"}])
+@pytest.mark.parametrize("kernel", [2, 1])      # NBL_KERNEL_WARP_GENERIC, NBL_KERNEL_GROUP
 @pytest.mark.parametrize("name", ["cfg3_tems_gf256", "cfg5_tems_hbit256"])
-def test_golden_through_the_other_kernels(name, env, code_files):
+def test_golden_through_the_other_kernels(name, kernel, code_files):
     """the golden T-EMS frames through the degree-generic warp kernel and through the group kernel"""
     from nbldpc_b200 import capi
     z, meta = load_golden(name)
     code = load_product_code(code_files, meta["code"])
     F = len(z["ret"])
-    os.environ.update(env)
-    try:
-        dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
-                           precision=capi.PREC_F64, max_batch=F, tie_mode=1)
-    finally:
-        for k in env:
-            os.environ.pop(k, None)
+    dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                       precision=capi.PREC_F64, max_batch=F, tie_mode=1, kernel=kernel)
     r = dec.decode(golden_lch(z, meta))
     assert np.array_equal(r["converged"], z["ret"].astype(np.int32))
     assert np.array_equal(r["iterations"], z["iters"].astype(np.int32))
@@ -127,32 +113,22 @@ def test_fp32_regular_and_generic_kernels_agree(code_files):
     F = len(z["ret"])
     lch = golden_lch(z, meta)
     outs = []
-    for env in ({}, {"NBLDPC_WARP_GENERIC": "1"}):
-        os.environ.update(env)
-        try:
-            dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
-                               precision=capi.PREC_F32, max_batch=F)
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
+    for kernel in (0, 2):
+        dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                           precision=capi.PREC_F32, max_batch=F, kernel=kernel)
         outs.append(dec.decode(lch, want_post=True))
     for k in ("sym", "converged", "iterations", "post"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
 
 
-def _check_ems(code, tmp_path, lch, nm, nc, factor, offset, env=None, max_iter=6):
+def _check_ems(code, tmp_path, lch, nm, nc, factor, offset, kernel=0, max_iter=6):
     from nbldpc_b200 import capi
     from oracle import pyoracle as po
     path = tmp_path / ("ems_%d_%d.txt" % (code["q"], code["N"]))
     path.write_text(po.code_text(code))
     oc = po.OracleCode(code)
     want = [oc.decode(2, max_iter, nm, nc, factor, offset, l) for l in lch]
-    os.environ.update(env or {})
-    try:
-        dec = capi.Decoder(capi.Code.from_file(str(path)), 2, max_iter, nm, nc, factor, offset, precision=capi.PREC_F64, max_batch=len(lch))
-    finally:
-        for k in (env or {}):
-            os.environ.pop(k, None)
+    dec = capi.Decoder(capi.Code.from_file(str(path)), 2, max_iter, nm, nc, factor, offset, precision=capi.PREC_F64, max_batch=len(lch), kernel=kernel)
     r = dec.decode(lch, want_post=True)
     assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
     assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
@@ -177,7 +153,7 @@ def test_ems_warp_kernel_random_codes(q, regular, tmp_path):
     _check_ems(code, tmp_path, lch[:4], 8, 1, 1.3, 0.0)
     _check_ems(code, tmp_path, lch[:4], 16, 2, 1.0, 0.5)
     _check_ems(code, tmp_path, lch[:4], 6, 3, 1.0, 0.5)                              # n_m not a power of two: group kernel
-    _check_ems(code, tmp_path, lch[:4], 8, 3, 1.0, 0.5, env={"NBLDPC_WARP_GENERIC": "1"})
+    _check_ems(code, tmp_path, lch[:4], 8, 3, 1.0, 0.5, kernel=2)
 
 
 @pytest.mark.parametrize("q", [16, 32, 64, 128])
@@ -215,13 +191,8 @@ def test_qspa_half_warp_and_group_kernels_are_bit_identical(name, precision, cod
     code = load_product_code(code_files, meta["code"])
     lch = golden_lch(z, meta)
     outs = []
-    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
-        os.environ.update(env)
-        try:
-            dec = capi.Decoder(code, 1, meta["max_iter"], precision=precision, max_batch=len(lch))
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
+    for kernel in (0, 1):
+        dec = capi.Decoder(code, 1, meta["max_iter"], precision=precision, max_batch=len(lch), kernel=kernel)
         outs.append(dec.decode(lch, want_post=True))
     for k in ("sym", "converged", "iterations", "post"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
@@ -238,13 +209,8 @@ def test_qspa_warp_and_group_kernels_are_bit_identical(precision, code_files):
     code = load_product_code(code_files, meta["code"])
     lch = golden_lch(z, meta)
     outs = []
-    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
-        os.environ.update(env)
-        try:
-            dec = capi.Decoder(code, 1, meta["max_iter"], precision=precision, max_batch=len(lch))
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
+    for kernel in (0, 1):
+        dec = capi.Decoder(code, 1, meta["max_iter"], precision=precision, max_batch=len(lch), kernel=kernel)
         outs.append(dec.decode(lch, want_post=True))
     for k in ("sym", "converged", "iterations", "post"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
@@ -260,14 +226,9 @@ def test_bstems_warp_and_group_kernels_agree(name, precision, code_files):
     code = load_product_code(code_files, meta["code"])
     lch = golden_lch(z, meta)
     outs = []
-    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
-        os.environ.update(env)
-        try:
-            dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
-                               precision=precision, max_batch=len(lch))
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
+    for kernel in (0, 1):
+        dec = capi.Decoder(code, meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"],
+                           precision=precision, max_batch=len(lch), kernel=kernel)
         outs.append(dec.decode(lch, want_post=True))
     for k in ("sym", "converged", "iterations"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
@@ -298,13 +259,8 @@ def test_tems_gf16_kernel_on_the_reference_code(code_files):
     lch = golden_lch(z, meta)
     for precision, tol in ((capi.PREC_F64, 1e-8), (capi.PREC_F32, 1e-3)):
         outs = []
-        for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
-            os.environ.update(env)
-            try:
-                dec = capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=precision, max_batch=len(lch), tie_mode=1)
-            finally:
-                for k in env:
-                    os.environ.pop(k, None)
+        for kernel in (0, 1):
+            dec = capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=precision, max_batch=len(lch), tie_mode=1, kernel=kernel)
             outs.append(dec.decode(lch, want_post=True))
         same = (outs[0]["sym"] == outs[1]["sym"]).all(axis=1) & (outs[0]["iterations"] == outs[1]["iterations"])
         assert same.all() if precision == capi.PREC_F64 else same.mean() > 0.9
@@ -349,14 +305,9 @@ def test_ems_gf16_kernel_on_the_reference_code(code_files):
     code = load_product_code(code_files, meta["code"])
     lch = golden_lch(z, meta)
     outs = []
-    for env in ({}, {"NBLDPC_FORCE_GENERIC": "1"}):
-        os.environ.update(env)
-        try:
-            dec = capi.Decoder(code, 2, meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], precision=capi.PREC_F64,
-                               max_batch=len(lch))
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
+    for kernel in (0, 1):
+        dec = capi.Decoder(code, 2, meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], precision=capi.PREC_F64,
+                           max_batch=len(lch), kernel=kernel)
         outs.append((dec.kernel(), dec.decode(lch, want_post=True)))
     assert [k for k, _ in outs] == ["ems_gf16", "group"]
     for k in ("sym", "converged", "iterations", "post"):

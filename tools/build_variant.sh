@@ -3,4 +3,4 @@
 name=$1; shift
 cd "$(dirname "$0")/.."; mkdir -p variants
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -shared -cudart static \
-     -Iinclude "$@" -o variants/lib_$name.so nbldpc_b200/csrc/decoder.cu nbldpc_b200/csrc/encoder.cu nbldpc_b200/csrc/code.cpp
+     -Iinclude "$@" -o variants/lib_$name.so nbldpc_b200/csrc/decoder.cu nbldpc_b200/csrc/encoder.cu nbldpc_b200/csrc/code.cpp nbldpc_b200/csrc/comm.cpp -ldl

@@ -173,9 +173,8 @@ def main():
             d = np.abs(r["post"] - ref); d[~sel] = 0
             fi, vi, xi = np.unravel_index(d.argmax(), d.shape)
             print("worst entry frame %d var %d x %d: got %r ref %r; var punctured %s" % (fi, vi, xi, r["post"][fi, vi, xi], ref[fi, vi, xi], vi in punct))
-            os.environ["NBLDPC_FORCE_GENERIC"] = "1"
-            dec2 = capi.Decoder(capi.Code.from_file(path), method, max_iter, p0, p1, factor, offset, precision=capi.PREC_F64, max_batch=F, tie_mode=tie)
-            os.environ.pop("NBLDPC_FORCE_GENERIC")
+            dec2 = capi.Decoder(capi.Code.from_file(path), method, max_iter, p0, p1, factor, offset, precision=capi.PREC_F64, max_batch=F, tie_mode=tie,
+                                kernel=capi.KERNEL_GROUP)
             r2 = dec2.decode(got_L, want_post=True)
             print("group kernel == fast kernel:", all(np.array_equal(r[k], r2[k]) for k in ("sym", "converged", "iterations", "post")))
         if not ok:
