@@ -58,7 +58,9 @@ def test_fp32_fast_mode_within_tolerance(name, code_files):
     dec = _decoder(code, meta, capi.PREC_F32, F)
     r = dec.decode(golden_lch(z, meta), want_post=True)
     same = (r["iterations"] == z["iters"]) & (r["converged"] == z["ret"]) & (r["sym"] == z["dec_sym"]).all(axis=1)
-    assert same.mean() >= 0.8, same
+    print("%s: fp32 decisions / iteration counts identical to the reference on %d of %d frames" % (name, int(same.sum()), F))
+    # measured: every frame of every fixture agrees (311 of 311); one frame per fixture is left for an fp32 near-tie
+    assert same.sum() >= F - 1, (int(same.sum()), F)
     got = r["post"][:, :, z["lpost_idx"]][same]
     ref = z["lpost_sample"][same]
     sel = ref > -25.0 if meta["method"] == 1 else np.ones_like(ref, bool)
@@ -151,8 +153,9 @@ def test_tems_bitexact_mode_reproduces_reference_posteriors_bit_for_bit(name, co
     assert np.array_equal(r["post"][:, :, z["lpost_idx"]], z["lpost_sample"][:F])
 
 
-def test_fp32_fer_matches_the_reference_anchor_points(code_files):
-    """The fp32 fast path at the operating points for which BASELINE.md holds FER figures of the reference itself:
+def test_fp32_fer_anchor_points_hand_bounds(code_files):
+    """(superseded by tests/test_anchors_gpu.py, which computes the reference's confidence interval from its counts at every
+    anchor; kept as a second, independent seed)  The fp32 fast path at operating points for which BASELINE.md holds FER figures:
     H_bit_GF256, T-EMS 2/2/0.5, 3 dB, random messages: 54 / 2001 = 2.70e-2 (the reference's sample is small: +-3 sigma
     = +-1.1e-2); BDS (576,288) GF(64), EMS 8/3/0.5, 2 dB: 3.25e-2.  200 k device frames each (sigma ~ 4e-4)."""
     from nbldpc_b200 import capi
