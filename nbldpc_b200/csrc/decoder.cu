@@ -468,6 +468,14 @@ extern "C" const char *nbl_decoder_kernel(const nbl_decoder *d) {
     return "group";
 }
 
+#if TW_STATS
+extern "C" int nbl_dev_stats(unsigned long long *out, int reset) {      // development builds only
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, nbl::tw_stats, sizeof(unsigned long long) * 128));
+    if (reset) { unsigned long long z[128] = {0}; CK(cudaMemcpyToSymbol(nbl::tw_stats, z, sizeof z)); }
+    return 0;
+}
+#endif
 extern "C" void *nbl_decoder_stream(nbl_decoder *d) { return d ? (void *)d->stream : nullptr; }
 extern "C" int nbl_decoder_sync(nbl_decoder *d) {
     if (!d) { nbl_set_error("null decoder"); return NBL_ERR_ARG; }

@@ -136,6 +136,17 @@ template <typename T, int VEC> __device__ __forceinline__ void st_split(T *__res
         st_vec<T, PL::E16>(vec + h * (32 * PL::E16) + k * PL::E16, tmp);
     }
 }
+// the same from the byte address of the block's first piece
+template <typename T, int VEC> __device__ __forceinline__ void ld_split_bytes(const unsigned char *src, T (&v)[VEC]) {
+    using PL = PLayout<T, VEC>;
+#pragma unroll
+    for (int h = 0; h < PL::NP; ++h) {
+        T tmp[PL::E16];
+        ld_vec<T, PL::E16>(reinterpret_cast<const T *>(src + h * PL::PSTRIDE), tmp);
+#pragma unroll
+        for (int i = 0; i < PL::E16; ++i) v[h * PL::E16 + i] = tmp[i];
+    }
+}
 // VEC consecutive table bytes starting at a VEC-aligned offset, as one little-endian word
 template <int VEC> __device__ __forceinline__ unsigned long long ld_bytes(const uint8_t *__restrict__ p) {
     if constexpr (VEC == 8) return *reinterpret_cast<const unsigned long long *>(p);
@@ -155,6 +166,24 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) {
     return (int)((h >> (8 * (i & 3))) & 255u);
 }
 
+#ifndef TW_STATS
+#define TW_STATS 0
+#endif
+#if TW_STATS
+__device__ unsigned long long tw_stats[128];     // per iteration: rows, live entries, candidates of the second kind, blocks with a live entry
+#endif
+#ifndef TW_PHASE_SYNC
+#define TW_PHASE_SYNC 0        // experiment: CTA-wide barriers at the phase boundaries, so that the warps of a CTA fetch the same code
+#endif
+#if TW_PHASE_SYNC
+#define TW_PHASE() __syncthreads()
+#else
+#define TW_PHASE() __syncwarp()
+#endif
+#ifndef TW_GROUP
+#define TW_GROUP (-2)          // refresh schedule of the pruning bound of the pair search: > 0: every TW_GROUP eta-blocks; < 0: after blocks 1 .. -TW_GROUP, then at 2x the block index (the bound falls fastest at the start)
+#endif
+constexpr int TW_NOTAG = 0xffff;
 // IEEE division kept out of line (one copy of the routine; the correction factor is 1 in every shipped profile)
 template <typename T> __device__ __noinline__ T div_call(T a, T b) { return a / b; }
 
@@ -224,95 +253,24 @@ template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char 
     }
 }
 
-// q[i] = pc[c][i] + cost for the warp-uniform column c = bits 2*BL, 2*BL+1 of the block's column word: two UNIFORM branches
-// written in PTX, so that the four 4-instruction bodies are reached without a select chain.
 #ifndef TW_PREFETCH_VOLD
 #define TW_PREFETCH_VOLD 0
 #endif
-#ifndef TW_UNIFORM_CLS
-#define TW_UNIFORM_CLS 1
-#endif
-#ifndef TW_DISPATCH
-#define TW_DISPATCH 1          // 0: C++ if-tree, 1: PTX bra.uni tree
-#endif
-#define TW_ADD4(a, b, c, d) "add.rn.f32x2 %0, " #a ", cc; add.rn.f32x2 %1, " #b ", cc; add.rn.f32x2 %2, " #c ", cc; add.rn.f32x2 %3, " #d ", cc;"
-template <int BL>
-__device__ __forceinline__ void pick_add_ptx(unsigned cls, float cost, const Pair2<float> (&p)[TW_DC][4], Pair2<float> (&q)[4]) {
-    asm("{\n\t"
-        ".reg .b64 cc;\n\t"
-        ".reg .pred ph, pl;\n\t"
-        ".reg .b32 bh, bl;\n\t"
-        "mov.b64 cc, {%5, %5};\n\t"
-        "and.b32 bh, %4, %22;\n\t"
-        "and.b32 bl, %4, %23;\n\t"
-        "setp.ne.b32 ph, bh, 0;\n\t"
-        "setp.eq.b32 pl, bl, 0;\n\t"
-        "@ph bra.uni LH;\n\t"
-        "@pl bra.uni L0;\n\t"
-        "L1: " TW_ADD4(%10, %11, %12, %13) " bra.uni LD;\n\t"
-        "L0: " TW_ADD4(%6, %7, %8, %9) " bra.uni LD;\n\t"
-        "LH: @pl bra.uni L2;\n\t"
-        "L3: " TW_ADD4(%18, %19, %20, %21) " bra.uni LD;\n\t"
-        "L2: " TW_ADD4(%14, %15, %16, %17) "\n\t"
-        "LD:\n\t"
-        "}"
-        : "=l"(q[0].v), "=l"(q[1].v), "=l"(q[2].v), "=l"(q[3].v)
-        : "r"(cls), "f"(cost),
-          "l"(p[0][0].v), "l"(p[0][1].v), "l"(p[0][2].v), "l"(p[0][3].v), "l"(p[1][0].v), "l"(p[1][1].v), "l"(p[1][2].v), "l"(p[1][3].v),
-          "l"(p[2][0].v), "l"(p[2][1].v), "l"(p[2][2].v), "l"(p[2][3].v), "l"(p[3][0].v), "l"(p[3][1].v), "l"(p[3][2].v), "l"(p[3][3].v),
-          "n"(2u << (2 * BL)), "n"(1u << (2 * BL)));
-}
-#undef TW_ADD4
-// generic form (other vector widths, fp64 parity mode)
-template <typename T, int NP2, int BL> __device__ __forceinline__ void pick_add(unsigned cls, T cost, const Pair2<T> (&p)[TW_DC][NP2], Pair2<T> (&q)[NP2]) {
-    if constexpr (std::is_same<T, float>::value && NP2 == 4 && TW_DISPATCH != 0) pick_add_ptx<BL>(cls, cost, p, q);
-    else {
-        if (cls & (2u << (2 * BL))) {
-            if (cls & (1u << (2 * BL))) {
-#pragma unroll
-                for (int i = 0; i < NP2; ++i) q[i] = p[3][i].plus(cost);
-            } else {
-#pragma unroll
-                for (int i = 0; i < NP2; ++i) q[i] = p[2][i].plus(cost);
-            }
-        } else {
-            if (cls & (1u << (2 * BL))) {
-#pragma unroll
-                for (int i = 0; i < NP2; ++i) q[i] = p[1][i].plus(cost);
-            } else {
-#pragma unroll
-                for (int i = 0; i < NP2; ++i) q[i] = p[0][i].plus(cost);
-            }
-        }
-    }
-}
-
-// entries BL and BL+1 of an eta-block for all VEC outputs: output r takes element r ^ bl = half (r ^ bl) & 1 of pair (r ^ bl) >> 1
-template <typename T, int VEC, int BL>
-__device__ __forceinline__ void entry_sums(unsigned cls, const T (&cost)[VEC], const Pair2<T> (&pc)[TW_DC][VEC / 2], T (&t)[VEC]) {
-    Pair2<T> q[VEC / 2];
-    pick_add<T, VEC / 2, BL>(cls, cost[BL], pc, q);
-#pragma unroll
-    for (int r = 0; r < VEC; ++r) {
-        const int j = r ^ BL;
-        t[r] = (j & 1) ? q[j >> 1].hi() : q[j >> 1].lo();
-    }
-}
-template <typename T, int VEC, int BL>
-__device__ __forceinline__ void entry_pair(unsigned cls, const T (&cost)[VEC], const Pair2<T> (&pc)[TW_DC][VEC / 2], const T (&best)[VEC], T (&nb)[VEC]) {
-    T t0[VEC], t1[VEC];
-    entry_sums<T, VEC, BL>(cls, cost, pc, t0);
-    entry_sums<T, VEC, BL + 1>(cls, cost, pc, t1);
-#pragma unroll
-    for (int r = 0; r < VEC; ++r) nb[r] = min3(BL == 0 ? best[r] : nb[r], t0[r], t1[r]);
-}
-
 template <typename T, int N> __device__ __forceinline__ T vec_max(const T (&v)[N]) {
     if constexpr (N == 8) return max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), fmax(v[6], v[7]));
     else if constexpr (N == 4) return fmax(max3(v[0], v[1], v[2]), v[3]);
     else if constexpr (N == 2) return fmax(v[0], v[1]);
     else return v[0];
 }
+
+// warp maximum of non-negative values (they order like their bit patterns): one REDUX for fp32
+__device__ __forceinline__ float warp_max_nonneg(float v, float) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v))); }
+__device__ __forceinline__ double warp_max_nonneg(double v, double) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_max_nonneg(T v) { return warp_max_nonneg(v, T()); }
 
 // DecideLLRVector over a vector spread VEC-per-lane across the warp (x = VEC*lane + j): the largest strictly positive
 // entry, ties to the lowest symbol, 0 when nothing is positive.
@@ -358,10 +316,12 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
     constexpr int VB = (int)(Q * sizeof(T));                        // bytes of one message vector
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const DevGraph &g = P.g;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The warp index comes out of a shuffle and the latch out of a vote, so that the compiler KNOWS both exits are taken by whole
+    // warps: otherwise every warp collective below is compiled twice (a convergence test plus a divergent fall-back path).
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int f = (int)(blockIdx.z * 65535u + blockIdx.y), row = (int)blockIdx.x * TW_WARPS + warp;   // see launch_iterate_warp_dc
     if (f >= P.B || row >= g.M) return;
-    if (P.early_stop && P.done[f]) return;
+    if (P.early_stop && __any_sync(0xffffffffu, P.done[f] != 0)) return;
 
     unsigned char *slab = smem_raw + S::bytes_per_warp * warp;
     T *R1 = reinterpret_cast<T *>(slab);
@@ -470,7 +430,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
     unsigned long long tiv[TW_DC];
 #pragma unroll
     for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(P.pinv_sw + (size_t)(e0 + d) * Q + x0); }
-    __syncwarp();
+    TW_PHASE();
     // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)],  h^-1 (eta ^ beta_d) = h^-1 eta ^ decide ----
     T u[TW_DC][VEC];
 #pragma unroll
@@ -528,81 +488,142 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
             }
         }
     }
-    __syncwarp();
+    TW_PHASE();
     const unsigned long long c01w = ld_bytes<VEC>(c01 + x0);
     T *Tout = R1;
     if constexpr (!BS) {
-        // ---- pair search: best[s] = min_a m0(a) + D_{c0(a)}[s ^ a] ----------------------------------------------------------
+        // ---- pair search: deltaW[s] = min(m0(s), min_a m0(a) + D_{c0(a)}[s ^ a]), with EXACT pruning by value ---------------------
+        // best starts at the single-deviation cost m0(s), so it is at all times an upper bound of deltaW[s]; a tag is written only
+        // when a pair is STRICTLY cheaper.  tag = a (0 .. q-1): the entry whose candidate of the first kind won; 256 + a: of the
+        // second kind; TW_NOTAG: the single deviation stands.
+        //
+        // Let U >= max_s deltaW[s] (any upper bound: the running max of best).  A pair {x, y} can only be the cost of some s if
+        // cost <= U, and cost >= m0(x) + m0(y), so its lighter element has m0 <= U/2: an entry a with m0(a) > U/2 ("dead") is
+        // skipped altogether, because every pair it belongs to is also reached from its partner --
+        //   * different cheapest columns: m0(x) + m0(y) is the same sum from either side;
+        //   * same cheapest column c: the pair costs min(m0(x) + m1(y), m1(x) + m0(y)); the first kind of candidate, m0(a) +
+        //     D_c[.], covers the term in which the LIVE element pays m0; the term in which the live element a pays m1 while its
+        //     dead partner pays m0 is covered by a second kind of candidate, m1(a) + (m0(y) if c0(y) == c else inf), needed only
+        //     when m1(a) <= U/2 as well (else the partner is live and reaches the pair itself).
+        // U is refreshed from best every TW_GROUP blocks, so the bound tightens while the search runs.  On the headline workload
+        // ~50 of the 255 entries are live in the first iterations and ~11 in the last (tools/probe/prune_stats.py), ~5 need the
+        // second kind -- same minima, same recorded pairs as the full enumeration (no two configurations tie exactly); the full
+        // enumeration with its four-way column dispatch per entry, which this replaces, is in the history of this file.
+        // A live entry loads the block of ITS column only (the address carries the column), and because entries are few the tag
+        // is kept per entry: the recorded pair needs no second scan.
         T best[VEC]; int tag[VEC];
+        const unsigned char *myrec = blk + lane * (int)S::blk_stride;
+        ld_vec<T, VEC>(reinterpret_cast<const T *>(myrec), best);
+        if (lane == 0) best[0] = T(0);
 #pragma unroll
-        for (int r = 0; r < VEC; ++r) { best[r] = INF; tag[r] = 0; }
+        for (int r = 0; r < VEC; ++r) tag[r] = TW_NOTAG;
         if (P.p1 >= 2) {
+            const bool second = P.p0 >= 2;                              // n_r = 1: the second-cheapest column may not deviate
 #pragma unroll 1
-            for (int bh = 0; bh < 32; ++bh) {
-                // one eta-block: best = min(best, candidates of the block); tag the block where it got smaller
-                T cost[VEC]; unsigned cls;
-                ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);   // warp-uniform operands of the block's entries
-#if TW_UNIFORM_CLS
-                cls = __reduce_or_sync(0xffffffffu, cls);               // same value, but now provably uniform: uniform branches below
-#endif
-                const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
-                T nb[VEC];
-                if constexpr (VEC >= 2) {
-                    constexpr int NP2 = VEC / 2;
-                    Pair2<T> pc[TW_DC][NP2];
+            for (int g0 = 0, g1; g0 < 32; g0 = g1) {
+                g1 = TW_GROUP > 0 ? g0 + TW_GROUP : (g0 < -TW_GROUP ? g0 + 1 : 2 * g0);   // TW_GROUP < 0: refresh after blocks 1, 2, .. , -TW_GROUP, then doubling
+                // liveness of every entry against the current bound, one block per lane: bit j = first kind, bit 8 + j = second kind
+                const T Uh = T(0.5) * warp_max_nonneg<T>(vec_max<T, VEC>(best));
+                unsigned mymask = 0u;
+                {
+                    T c0v[VEC], c1v[VEC];
+                    ld_vec<T, VEC>(reinterpret_cast<const T *>(myrec), c0v);                       // +inf at eta = 0: never live
+                    ld_split<T, VEC>(sM1, lane, c1v);
 #pragma unroll
-                    for (int c = 0; c < TW_DC; ++c) ld_pairs<VEC>(Dk + c * VB, pc[c]);
-                    entry_pair<T, VEC, 0>(cls, cost, pc, best, nb);
-                    if constexpr (VEC > 2) entry_pair<T, VEC, 2>(cls, cost, pc, best, nb);
-                    if constexpr (VEC > 4) { entry_pair<T, VEC, 4>(cls, cost, pc, best, nb); entry_pair<T, VEC, 6>(cls, cost, pc, best, nb); }
-                } else {
-                    const T p = *reinterpret_cast<const T *>(Dk + (cls & 3) * VB);
-                    nb[0] = fmin(best[0], p + cost[0]);
+                    for (int j = 0; j < VEC; ++j) {
+                        if (c0v[j] <= Uh) mymask |= 1u << j;
+                        if (second && c1v[j] <= Uh && c0v[j] <= Uh) mymask |= 256u << j;
+                    }
                 }
+#pragma unroll 1
+                for (int bh = g0; bh < g1; ++bh) {
+                    const unsigned m = __reduce_or_sync(0xffffffffu, lane == bh ? mymask : 0u);    // warp-uniform by construction
+                    if (!m) continue;
+#if TW_STATS
+                    if (lane == 0) { atomicAdd(tw_stats + 8 * (P.iter & 15) + 1, (unsigned long long)__popc(m & 255u)); atomicAdd(tw_stats + 8 * (P.iter & 15) + 3, 1ULL);
+                                     atomicAdd(tw_stats + 8 * (P.iter & 15) + 2, (unsigned long long)__popc(m >> 8)); }
+#endif
+                    const unsigned char *rec = blk + bh * (int)S::blk_stride;
+                    const unsigned cls = *reinterpret_cast<const unsigned *>(rec + S::blk_cls);
+                    const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
 #pragma unroll
-                for (int r = 0; r < VEC; ++r) { if (nb[r] < best[r]) tag[r] = bh; best[r] = nb[r]; }
+                    for (int bl = 0; bl < VEC; ++bl) {
+                        if (m & (1u << bl)) {                           // first kind: m0(a) + D_{c0(a)}[s ^ a]
+                            const T cost = *reinterpret_cast<const T *>(rec + bl * (int)sizeof(T));
+                            const unsigned char *src = Dk + ((cls >> (2 * bl)) & 3u) * VB;
+                            const int a = VEC * bh + bl;
+                            if constexpr (VEC >= 2) {
+                                Pair2<T> p[VEC / 2], q[VEC / 2];
+                                ld_pairs<VEC>(src, p);
+#pragma unroll
+                                for (int i = 0; i < VEC / 2; ++i) q[i] = p[i].plus(cost);
+#pragma unroll
+                                for (int r = 0; r < VEC; ++r) {
+                                    const int j = r ^ bl;
+                                    const T cand = (j & 1) ? q[j >> 1].hi() : q[j >> 1].lo();
+                                    if (cand < best[r]) { best[r] = cand; tag[r] = a; }
+                                }
+                            } else {
+                                const T cand = *reinterpret_cast<const T *>(src) + cost;
+                                if (cand < best[0]) { best[0] = cand; tag[0] = a; }
+                            }
+                        }
+                    }
+                    // second kind (rare): ONE copy of the code for any entry; the tile is brought into the order of the lane's outputs
+                    // by three conditional exchange steps (index j = r ^ bl)
+                    for (unsigned m2 = m >> 8; m2; m2 &= m2 - 1u) {
+                        const int bl = __ffs((int)m2) - 1, a = VEC * bh + bl;
+                        const T m1a = sM1[PL::index(bh, bl)];
+                        const unsigned c = (cls >> (2 * bl)) & 3u;
+                        T dc[VEC], dx[VEC], cand[VEC];                  // D_c and D of another column of the row (degree >= 2: column
+                        ld_split_bytes<T, VEC>(Dk + c * VB, dc);        // 0 or 1 exists) differ exactly where c0(y) == c
+                        ld_split_bytes<T, VEC>(Dk + (c ? 0u : 1u) * VB, dx);
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) cand[j] = m1a + (dc[j] > dx[j] ? dx[j] : INF);
+#pragma unroll
+                        for (int bit = 1; bit < VEC; bit <<= 1) {
+                            const bool sw = (bl & bit) != 0;
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j)
+                                if (!(j & bit)) { const T lo = cand[j], hi = cand[j | bit]; cand[j] = sw ? hi : lo; cand[j | bit] = sw ? lo : hi; }
+                        }
+#pragma unroll
+                        for (int r = 0; r < VEC; ++r) if (cand[r] < best[r]) { best[r] = cand[r]; tag[r] = 256 + a; }
+                    }
+                }
             }
+#if TW_STATS
+            if (lane == 0) atomicAdd(tw_stats + 8 * (P.iter & 15), 1ULL);
+#endif
         }
-        // ---- deltaW and the recorded path of each owned s --------------------------------------------------------------------
-        // single deviation: (s, c0(s));  pair: a in column ca, b = s ^ a in column cb, costs ua = m0(a), ub = D_ca[b]
+        // ---- the recorded path of each owned s: straight from the tag -------------------------------------------------------
+        // single deviation: (s, c0(s));  pair: a in column ca at cost ua, b = s ^ a in column cb at cost ub
         unsigned path[VEC];   // swz(a) | swz(b) << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
         T va[VEC], vb[VEC];                                             // dw - ua, dw - ub of pair paths
-        {
-            T m0[VEC];
-            ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0);
-            if (lane == 0) m0[0] = T(0);
 #pragma unroll
-            for (int r = 0; r < VEC; ++r) {
-                const int s = x0 + r;
-                va[r] = T(0); vb[r] = T(0);
-                path[r] = s == 0 ? 0u : (0x100000u << (byte_of(c01w, r) & 15));
-                const bool pair = best[r] < m0[r];                      // never for s == 0 (m0 = 0)
-                if (!pair) best[r] = m0[r];                             // from here on best = deltaW
-                else {
-                    // recover the pair from the winning block: the first entry in search order that attains the minimum
-                    const int bh = tag[r], k = lane ^ bh;
-                    T cost[VEC]; unsigned cls;
-                    ld_blk<T, VEC>(blk + bh * (int)S::blk_stride, cost, cls);
-                    const unsigned char *Dk = slab + k * (PL::E16 * (int)sizeof(T));
-                    int bl0 = 0; T ub = T(0), ua = T(0);
-#pragma unroll
-                    for (int bl = VEC - 1; bl >= 0; --bl) {             // descending: the smallest matching eta remains
-                        constexpr int E16 = PL::E16;
-                        const int j = r ^ bl;
-                        const int cofs = (int)((cls >> (2 * bl)) & 3u) * VB;
-                        const T dv = *reinterpret_cast<const T *>(Dk + cofs + (j / E16) * PL::PSTRIDE + (j % E16) * (int)sizeof(T));
-                        if (dv + cost[bl] == best[r]) { bl0 = bl; ub = dv; ua = cost[bl]; }
-                    }
-                    const int aa = VEC * bh + bl0, bb = s ^ aa;
-                    const int ca = (cls >> (2 * bl0)) & 3, kb = c01[bb];
-                    const int cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
-                    va[r] = best[r] - ua; vb[r] = best[r] - ub;
-                    const unsigned sa = (unsigned)PL::index(bh, bl0), sb = (unsigned)PL::index(lane, r) ^ sa;   // the layout is linear
-                    path[r] = sa | (sb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
+        for (int r = 0; r < VEC; ++r) {
+            const int s = x0 + r;
+            va[r] = T(0); vb[r] = T(0);
+            path[r] = s == 0 ? 0u : (0x100000u << (byte_of(c01w, r) & 15));
+            if (tag[r] != TW_NOTAG) {
+                const int aa = tag[r] & 255, bb = s ^ aa, ka = c01[aa], kb = c01[bb];
+                const unsigned sa = (unsigned)PL::swz(aa), sb = (unsigned)PL::index(lane, r) ^ sa;    // the layout is linear over XOR
+                int ca, cb; T ua, ub;
+                if (tag[r] < 256) {                                     // a pays its cheapest column, b the cheapest one that is not ca
+                    ca = ka & 15;
+                    cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
+                    ua = *reinterpret_cast<const T *>(blk + (aa / VEC) * (int)S::blk_stride + (aa % VEC) * (int)sizeof(T));
+                    ub = R1[ca * Q + sb];                               // D_ca[b]
+                } else {                                                // a pays its SECOND-cheapest column, b its cheapest one (= c0(a))
+                    ca = ka >> 4; cb = ka & 15;
+                    ua = sM1[sa];
+                    ub = *reinterpret_cast<const T *>(blk + (bb / VEC) * (int)S::blk_stride + (bb % VEC) * (int)sizeof(T));
                 }
+                va[r] = best[r] - ua; vb[r] = best[r] - ub;
+                path[r] = sa | (sb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
             }
         }
-        __syncwarp();                                                  // everyone is done with D
+        TW_PHASE();                                                  // everyone is done with D
         // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
 #pragma unroll
         for (int d = 0; d < TW_DC; ++d) {
@@ -623,7 +644,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
                 atomic_min_nonneg(Tout + cb * Q + a, vb[r]);
             }
         }
-        __syncwarp();
+        TW_PHASE();
     } else {
         // ---- BS-TEMS (Decoding_BS_TEMS, NBLDPC.cpp:1145-1396).  As the reference runs it the T-EMS stage only leaves the
         //      all-zero configuration (TEMS_Nr is never set in this mode); every other syndrome is reached by a subset of the
@@ -750,7 +771,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
             st_split<T, VEC>(Tout + d * Q, lane, tv);
         }
     }
-    __syncwarp();
+    TW_PHASE();
     // ---- normal domain, un-permute, correct (NBLDPC.cpp:1105-1128) ------------------------------------------------------
     T *coutf = P.c2v_out + (size_t)f * g.E * Q + VEC * lane;
     unsigned long long tnext = ld_bytes<VEC>(P.pfwd_sw + (size_t)e0 * Q + x0);
