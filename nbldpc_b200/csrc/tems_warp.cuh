@@ -61,6 +61,7 @@ template <typename T, int VEC> struct PLayout {
     static constexpr int PSTRIDE = 32 * E16 * (int)sizeof(T);     // bytes between pieces
     __host__ __device__ static constexpr int index(int k, int j) { return (j / E16) * (32 * E16) + k * E16 + (j % E16); }
     __host__ __device__ static constexpr int swz(int x) { return index(x / VEC, x % VEC); }
+    __device__ static __forceinline__ int index_rt(int k, int j) { return (j / E16) * (32 * E16) + k * E16 + (j % E16); }   // j known at run time only
 };
 
 template <typename T, int Q> struct TwSmem {
@@ -180,9 +181,6 @@ __device__ unsigned long long tw_stats[128];     // per iteration: rows, live en
 #else
 #define TW_PHASE() __syncwarp()
 #endif
-#ifndef TW_GROUP
-#define TW_GROUP (-2)          // refresh schedule of the pruning bound of the pair search: > 0: every TW_GROUP eta-blocks; < 0: after blocks 1 .. -TW_GROUP, then at 2x the block index (the bound falls fastest at the start)
-#endif
 constexpr int TW_NOTAG = 0xffff;
 // IEEE division kept out of line (one copy of the routine; the correction factor is 1 in every shipped profile)
 template <typename T> __device__ __noinline__ T div_call(T a, T b) { return a / b; }
@@ -263,6 +261,16 @@ template <typename T, int N> __device__ __forceinline__ T vec_max(const T (&v)[N
     else return v[0];
 }
 
+// v[r] for an index known at run time only (N a power of two): a tree of N - 1 selects, no local memory
+template <typename V, int N> __device__ __forceinline__ V pick(const V (&v)[N], int r) {
+    if constexpr (N == 1) return v[0];
+    else {
+        V t[N / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) t[i] = (r & 1) ? v[2 * i + 1] : v[2 * i];
+        return pick<V, N / 2>(t, r >> 1);
+    }
+}
 // warp maximum of non-negative values (they order like their bit patterns): one REDUX for fp32
 __device__ __forceinline__ float warp_max_nonneg(float v, float) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v))); }
 __device__ __forceinline__ double warp_max_nonneg(double v, double) {
@@ -301,6 +309,39 @@ template <int VEC> __device__ __forceinline__ int row_byte(unsigned long long w,
 template <typename T, int VEC> __device__ __forceinline__ void ld_blk(const unsigned char *rec, T (&cost)[VEC], unsigned &cls) {
     ld_vec<T, VEC>(reinterpret_cast<const T *>(rec), cost);
     cls = *reinterpret_cast<const unsigned *>(rec + VEC * sizeof(T));
+}
+
+// The pair behind a tag of the pruned search, for the output s (split-layout index sidx) whose deltaW is dw: element a in column
+// ca at cost ua and b = s ^ a in column cb at cost ub.  Returns the packed path  sb | sa << 8 | ca << 16 | cb << 18 | (deviating
+// columns) << 20 | 1 << 24  and the two landing values dw - ua, dw - ub.  Out of line on purpose: ONE copy for a lane's VEC outputs.
+template <typename T> struct TwPair { unsigned path; T va, vb; };
+template <typename T, int Q>
+__device__ __noinline__ TwPair<T> tw_pair_of_tag(const unsigned char *slab, int tg, int s, unsigned sidx, T dw) {
+    constexpr int VEC = Q / 32;
+    using PL = PLayout<T, VEC>;
+    using S = TwSmem<T, Q>;
+    const unsigned char *blk = slab + S::off_blk;
+    const T *sM1 = reinterpret_cast<const T *>(slab + S::off_m1);
+    const uint8_t *c01 = slab + S::off_c01;
+    const int aa = tg & 255, bb = s ^ aa, ka = c01[aa], kb = c01[bb];
+    const unsigned sa = (unsigned)PL::swz(aa), sb = sidx ^ sa;          // the layout is linear over XOR
+    const T m0b = *reinterpret_cast<const T *>(blk + (bb / VEC) * (int)S::blk_stride + (bb % VEC) * (int)sizeof(T));
+    int ca, cb; T ua, ub;
+    if (tg < 256) {                                                 // a pays its cheapest column, b the cheapest one that is not ca
+        ca = ka & 15;
+        const bool same = (kb & 15) == ca;
+        cb = same ? (kb >> 4) : (kb & 15);
+        ua = *reinterpret_cast<const T *>(blk + (aa / VEC) * (int)S::blk_stride + (aa % VEC) * (int)sizeof(T));
+        ub = same ? sM1[sb] : m0b;                                  // D_ca[b]
+    } else {                                                        // a pays its SECOND-cheapest column, b its cheapest one (= c0(a))
+        ca = ka >> 4; cb = ka & 15;
+        ua = sM1[sa];
+        ub = m0b;
+    }
+    TwPair<T> out;
+    out.path = sb | (sa << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
+    out.va = dw - ua; out.vb = dw - ub;
+    return out;
 }
 
 // DC > 0: every check row has exactly DC edges (no degree guards in the unrolled stages); DC == 0: row degree from the
@@ -343,41 +384,45 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
     const int x0 = VEC * lane;
     int syn_dec = 0, syn = 0;
     unsigned sdecw = 0, sbetaw = 0;                                 // byte d: decide(v2c_d), beta_d = h_d * decide(v2c_d)
-    // ---- steps A-C for the row's variables (NBLDPC.cpp:977-1052); the loads of edge d+1 are in flight during edge d ----
-    T nl[2][VEC], nm[2][TW_HOIST][VEC]; int4 nd[2]; int nbefore[2];
-    unsigned long long ntf[2];                                      // the lane's own bytes of the edge's h * x row
-    auto fetch = [&](int d, int slot) {
-        nd[slot] = *reinterpret_cast<const int4 *>(rd + TW_DSC * d);                // {variable, degree, edge id 0, edge id 1}
-        ld_vec<T, VEC>(lchf + (size_t)nd[slot].x * Q, nl[slot]);
-        ntf[slot] = ld_bytes<VEC>(g.pfwd + (size_t)(e0 + d) * Q + x0);
-        const int nv = DV ? DV : nd[slot].y;
+    // ---- steps A-C for the row's variables (NBLDPC.cpp:977-1052) -----------------------------------------------------------
+    // ONE copy of the code, rolled over the row's edges (the kernel is bound by instruction fetch: see DESIGN.md): the inputs of
+    // edge d + 1 are requested into the SAME registers as soon as edge d has formed its sums, so they are in flight during the
+    // decisions, the stores and the table look-ups of edge d.
+    T a0[VEC], a1[VEC], a2[VEC];                                    // channel LLRs, first and second message of the variable
+    int4 nd; int nbefore;
+    unsigned long long ntf;                                         // the lane's own bytes of the edge's h * x row
+    auto fetch = [&](int d) {
+        nd = *reinterpret_cast<const int4 *>(rd + TW_DSC * d);      // {variable, degree, edge id 0, edge id 1}
+        ld_vec<T, VEC>(lchf + (size_t)nd.x * Q, a0);
+        ntf = ld_bytes<VEC>(g.pfwd + (size_t)(e0 + d) * Q + x0);
+        const int nv = DV ? DV : nd.y;
+        if (!P.first && 0 < nv) ld_vec<T, VEC>(cinf + (size_t)nd.z * Q, a1);
+        else {                                                      // iteration 1: c2v == 0 (x + 0 and x - 0 are exact)
 #pragma unroll
-        for (int j = 0; j < TW_HOIST; ++j) {
-            if (!P.first && j < nv) ld_vec<T, VEC>(cinf + (size_t)(j == 0 ? nd[slot].z : nd[slot].w) * Q, nm[slot][j]);
-            else {                                                  // iteration 1: c2v == 0 (x + 0 and x - 0 are exact)
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) nm[slot][j][i] = T(0);
-            }
+            for (int i = 0; i < VEC; ++i) a1[i] = T(0);
         }
-        nbefore[slot] = P.first ? -1 : (int)vdecf[e0 + d];
+        if (!P.first && 1 < nv) ld_vec<T, VEC>(cinf + (size_t)nd.w * Q, a2);
+        else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) a2[i] = T(0);
+        }
+        nbefore = P.first ? -1 : (int)vdecf[e0 + d];
     };
-    auto edge = [&](int d, int slot) {
-        const int e = e0 + d, col = nd[slot].x, nv = DV ? DV : nd[slot].y;
+    fetch(0);
+#pragma unroll 1
+    for (int d = 0; d < dcn; ++d) {
+        const int e = e0 + d, col = nd.x, nv = DV ? DV : nd.y, before = nbefore;
+        const unsigned long long tf = ntf;
+        const bool mine0 = nd.z == e;                               // warp-uniform
         T post[VEC], vnew[VEC], own[VEC];
-#if TW_PREFETCH_VOLD
-        T vold[VEC];                                                // the damping operand, fetched before it is known to be needed
-        const bool damping = !P.first && P.w_old != T(0);
-        if (damping) ld_vec<T, VEC>(v2cf + (size_t)e * Q, vold);
-#endif
-        const bool mine0 = nd[slot].z == e;                         // warp-uniform
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            post[i] = nl[slot][i] + nm[slot][0][i];
-            own[i] = mine0 ? nm[slot][0][i] : (TW_HOIST > 1 ? nm[slot][1][i] : T(0));
+            post[i] = a0[i] + a1[i];
+            own[i] = mine0 ? a1[i] : a2[i];
         }
-        if (TW_HOIST > 1 && (DV ? DV > 1 : nv > 1)) {
+        if (DV ? DV > 1 : nv > 1) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) post[i] = post[i] + nm[slot][1][i];
+            for (int i = 0; i < VEC; ++i) post[i] = post[i] + a2[i];
         } else if (!mine0) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) own[i] = T(0);
@@ -394,36 +439,25 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
         }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) vnew[i] = post[i] - own[i];
+        if (d + 1 < dcn) fetch(d + 1);                              // a0 .. a2 are consumed: the next edge's loads go out now
         const int dpost = warp_decide<T, VEC>(post, lane);
         int dfin = warp_decide<T, VEC>(vnew, lane);
-        if (!P.first && P.w_old != T(0) && dfin != nbefore[slot]) { // warp-uniform
-#if !TW_PREFETCH_VOLD
+        if (!P.first && P.w_old != T(0) && dfin != before) {        // warp-uniform
             T vold[VEC];
             ld_vec<T, VEC>(v2cf + (size_t)e * Q, vold);
-#endif
 #pragma unroll
             for (int i = 0; i < VEC; ++i) vnew[i] = P.w_old * vold[i] + P.w_new * vnew[i];   // -fmad=false
             dfin = warp_decide<T, VEC>(vnew, lane);
         }
         st_vec<T, VEC>(v2cf + (size_t)e * Q, vnew);
         st_split<T, VEC>(R1 + d * Q, lane, vnew);
-        const int bt = row_byte<VEC>(ntf[slot], dfin);
+        const int bt = row_byte<VEC>(tf, dfin);
         if (lane == 0) { vdecf[e] = (uint8_t)dfin; P.dec[(size_t)f * g.N + col] = (uint8_t)dpost; }
         sdecw |= (unsigned)dfin << (8 * d); sbetaw |= (unsigned)bt << (8 * d);
         syn ^= bt;
         int bp = bt;
-        if (dpost != dfin) bp = row_byte<VEC>(ntf[slot], dpost);    // warp-uniform
+        if (dpost != dfin) bp = row_byte<VEC>(tf, dpost);           // warp-uniform
         syn_dec ^= bp;
-    };
-    fetch(0, 0);
-#pragma unroll 1
-    for (int d = 0; d < dcn; d += 2) {
-        if (d + 1 < dcn) fetch(d + 1, 1);
-        edge(d, 0);
-        if (d + 1 < dcn) {
-            if (d + 2 < dcn) fetch(d + 2, 0);
-            edge(d + 1, 1);
-        }
     }
     if (lane == 0 && syn_dec != 0) P.flag[f] = 1;
     // the lane's own bytes of the rows h^-1 * x, as split-layout indices
@@ -431,57 +465,64 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
 #pragma unroll
     for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(P.pinv_sw + (size_t)(e0 + d) * Q + x0); }
     TW_PHASE();
-    // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)],  h^-1 (eta ^ beta_d) = h^-1 eta ^ decide ----
-    T u[TW_DC][VEC];
-#pragma unroll
-    for (int d = 0; d < TW_DC; ++d) {
-        if (DC || d < dcn) {
-            const int sd = PL::swz((sdecw >> (8 * d)) & 255);
-            const T vmax = R1[d * Q + sd];
-            const G gv(slab32 + d * VB, sd);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) u[d][j] = vmax - gv.at(tiv[d], j);
-        } else {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) u[d][j] = INF;
-        }
-    }
-    __syncwarp();                                                  // all reads of v2c in R1 are done
-    // ---- column order per eta (TEMS_Get_Min): c0, c1, m0, m1;  D_c and the block records for the search -------------------
+    // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)],  h^-1 (eta ^ beta_d) = h^-1 eta ^ decide,
+    //      and the column order per eta (TEMS_Get_Min): c0, c1, m0, m1 -- rolled over the lane's VEC elements (one copy of the
+    //      four gathers and of the ordering network); the results go to the block records, M1 and c01, none of which the gathers read
     {
-        T m0[VEC], m1[VEC]; unsigned long long c01w = 0; unsigned cls = 0;
+        unsigned key[TW_DC]; T vmx[TW_DC];
 #pragma unroll
+        for (int d = 0; d < TW_DC; ++d) {
+            key[d] = 0u; vmx[d] = INF;
+            if (DC || d < dcn) {
+                const int sd = PL::swz((sdecw >> (8 * d)) & 255);
+                vmx[d] = R1[d * Q + sd];
+                key[d] = S::xor_gather ? ((slab32 + d * VB) ^ ((unsigned)sd << G::SH)) : ((unsigned)sd << G::SH);
+            }
+        }
+        unsigned char *mine = blk + lane * (int)S::blk_stride;
+        unsigned cls = 0;
+#pragma unroll 1
         for (int j = 0; j < VEC; ++j) {
-            const T a = u[0][j], b = u[1][j], c = u[2][j], dd = u[3][j];
-            m0[j] = fmin(min3(a, b, c), dd);
-            const int k0 = (a == m0[j]) ? 0 : (b == m0[j]) ? 1 : (c == m0[j]) ? 2 : 3;      // stable: the lower column wins ties
+            T uu[TW_DC];
+#pragma unroll
+            for (int d = 0; d < TW_DC; ++d) {
+                uu[d] = INF;
+                if (DC || d < dcn) {
+                    const unsigned bb = ((unsigned)(tiv[d] >> (8 * j)) & 255u) << G::SH;
+                    uu[d] = vmx[d] - lds_addr(S::xor_gather ? (bb ^ key[d]) : (slab32 + d * VB + (bb ^ key[d])), T());
+                }
+            }
+            const T a = uu[0], b = uu[1], c = uu[2], dd = uu[3];
+            const T m0 = fmin(min3(a, b, c), dd);
+            const int k0 = (a == m0) ? 0 : (b == m0) ? 1 : (c == m0) ? 2 : 3;                   // stable: the lower column wins ties
             const T a1 = k0 == 0 ? INF : a, b1 = k0 == 1 ? INF : b, c1 = k0 == 2 ? INF : c, d1 = k0 == 3 ? INF : dd;
-            m1[j] = fmin(min3(a1, b1, c1), d1);
+            const T m1 = fmin(min3(a1, b1, c1), d1);
             int k1 = (k0 != 3) ? 3 : 2;                             // lowest column other than k0 that attains m1 (row degree >= 2)
-            if (c1 == m1[j]) k1 = 2;
-            if (b1 == m1[j]) k1 = 1;
-            if (a1 == m1[j]) k1 = 0;
-            c01w |= (unsigned long long)(k0 | (k1 << 4)) << (8 * j);
+            if (c1 == m1) k1 = 2;
+            if (b1 == m1) k1 = 1;
+            if (a1 == m1) k1 = 0;
+            *reinterpret_cast<T *>(mine + j * (int)sizeof(T)) = (x0 + j == 0) ? INF : m0;       // the search never takes eta = 0
+            sM1[PL::index_rt(lane, j)] = m1;
+            c01[x0 + j] = (uint8_t)(k0 | (k1 << 4));
             cls |= (unsigned)k0 << (2 * j);
         }
-        st_bytes<VEC>(c01 + x0, c01w);
-        st_split<T, VEC>(sM1, lane, m1);
-        {
-            T rcost[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) rcost[j] = (x0 + j == 0) ? INF : m0[j];
-            unsigned char *mine = blk + lane * (int)S::blk_stride;
-            st_vec<T, VEC>(reinterpret_cast<T *>(mine), rcost);
-            *reinterpret_cast<unsigned *>(mine + S::blk_cls) = cls;
-        }
+        *reinterpret_cast<unsigned *>(mine + S::blk_cls) = cls;
+    }
+    __syncwarp();                                                  // all reads of v2c in R1 are done; records, M1 and c01 are visible
+    if constexpr (!BS) {
+        // D_c[x]: cheapest allowed column of x other than c (the candidate vectors of the search), over the dead v2c
+        T m0[VEC], m1[VEC];
+        ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0);
+        ld_split<T, VEC>(sM1, lane, m1);
+        const unsigned long long cw = ld_bytes<VEC>(c01 + x0);
         const T second_ok = P.p0 >= 2 ? T(0) : INF;                 // n_r = 1: only the cheapest column may deviate
 #pragma unroll
         for (int c = 0; c < TW_DC; ++c) {
-            if (!BS && (DC || c < dcn)) {                           // D_c[x]: cheapest allowed column of x other than c
+            if (DC || c < dcn) {
                 T dcv[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    const T v = ((byte_of(c01w, j) & 15) == c) ? (m1[j] + second_ok) : m0[j];
+                    const T v = ((byte_of(cw, j) & 15) == c) ? (m1[j] + second_ok) : m0[j];
                     dcv[j] = (x0 + j == 0) ? INF : v;
                 }
                 st_split<T, VEC>(R1 + c * Q, lane, dcv);
@@ -505,7 +546,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
         //     D_c[.], covers the term in which the LIVE element pays m0; the term in which the live element a pays m1 while its
         //     dead partner pays m0 is covered by a second kind of candidate, m1(a) + (m0(y) if c0(y) == c else inf), needed only
         //     when m1(a) <= U/2 as well (else the partner is live and reaches the pair itself).
-        // U is refreshed from best every TW_GROUP blocks, so the bound tightens while the search runs.  On the headline workload
+        // U is refreshed from best before every round of blocks, so the bound tightens while the search runs.  On the headline workload
         // ~50 of the 255 entries are live in the first iterations and ~11 in the last (tools/probe/prune_stats.py), ~5 need the
         // second kind -- same minima, same recorded pairs as the full enumeration (no two configurations tie exactly); the full
         // enumeration with its four-way column dispatch per entry, which this replaces, is in the history of this file.
@@ -519,9 +560,12 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
         for (int r = 0; r < VEC; ++r) tag[r] = TW_NOTAG;
         if (P.p1 >= 2) {
             const bool second = P.p0 >= 2;                              // n_r = 1: the second-cheapest column may not deviate
+            // The bound is refreshed before block 0, 1, 2, 4, 8 and 16: it falls fastest at the start.  (Measured alternatives: a
+            // refresh every 2 / 4 / 8 blocks -- 2.56 / 2.52 / 2.63 ms per launch against 2.44 -- and rounds of blocks in ascending
+            // order of their cheapest entry, which kept 60 entries live where this schedule keeps 49, and was slower.)
 #pragma unroll 1
             for (int g0 = 0, g1; g0 < 32; g0 = g1) {
-                g1 = TW_GROUP > 0 ? g0 + TW_GROUP : (g0 < -TW_GROUP ? g0 + 1 : 2 * g0);   // TW_GROUP < 0: refresh after blocks 1, 2, .. , -TW_GROUP, then doubling
+                g1 = g0 < 2 ? g0 + 1 : 2 * g0;
                 // liveness of every entry against the current bound, one block per lane: bit j = first kind, bit 8 + j = second kind
                 const T Uh = T(0.5) * warp_max_nonneg<T>(vec_max<T, VEC>(best));
                 unsigned mymask = 0u;
@@ -596,35 +640,23 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
             if (lane == 0) atomicAdd(tw_stats + 8 * (P.iter & 15), 1ULL);
 #endif
         }
-        // ---- the recorded path of each owned s: straight from the tag -------------------------------------------------------
-        // single deviation: (s, c0(s));  pair: a in column ca at cost ua, b = s ^ a in column cb at cost ub
-        unsigned path[VEC];   // swz(a) | swz(b) << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
+        // ---- the recorded path of each owned s, straight from the tag (tw_pair_of_tag: one out-of-line copy of the code for the
+        //      lane's VEC outputs -- the kernel must stay inside the instruction cache), and the output trellis (NBLDPC.cpp:1084-1094):
+        //      Tout[d][t] = min over s of (deltaW[s] - dU[d][eta_d(s)]) at t = s ^ eta_d(s); column d of the path of s lands on s
+        //      itself when the path does not deviate there (value deltaW[s]), on the partner's index when it does
+        unsigned path[VEC];   // sb | sa << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
         T va[VEC], vb[VEC];                                             // dw - ua, dw - ub of pair paths
 #pragma unroll
         for (int r = 0; r < VEC; ++r) {
             const int s = x0 + r;
             va[r] = T(0); vb[r] = T(0);
-            path[r] = s == 0 ? 0u : (0x100000u << (byte_of(c01w, r) & 15));
+            path[r] = s == 0 ? 0u : (0x100000u << (byte_of(c01w, r) & 15));      // single deviation of s in c0(s)
             if (tag[r] != TW_NOTAG) {
-                const int aa = tag[r] & 255, bb = s ^ aa, ka = c01[aa], kb = c01[bb];
-                const unsigned sa = (unsigned)PL::swz(aa), sb = (unsigned)PL::index(lane, r) ^ sa;    // the layout is linear over XOR
-                int ca, cb; T ua, ub;
-                if (tag[r] < 256) {                                     // a pays its cheapest column, b the cheapest one that is not ca
-                    ca = ka & 15;
-                    cb = ((kb & 15) != ca) ? (kb & 15) : (kb >> 4);
-                    ua = *reinterpret_cast<const T *>(blk + (aa / VEC) * (int)S::blk_stride + (aa % VEC) * (int)sizeof(T));
-                    ub = R1[ca * Q + sb];                               // D_ca[b]
-                } else {                                                // a pays its SECOND-cheapest column, b its cheapest one (= c0(a))
-                    ca = ka >> 4; cb = ka & 15;
-                    ua = sM1[sa];
-                    ub = *reinterpret_cast<const T *>(blk + (bb / VEC) * (int)S::blk_stride + (bb % VEC) * (int)sizeof(T));
-                }
-                va[r] = best[r] - ua; vb[r] = best[r] - ub;
-                path[r] = sa | (sb << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
+                const TwPair<T> pr = tw_pair_of_tag<T, Q>(slab, tag[r], s, (unsigned)PL::index(lane, r), best[r]);
+                path[r] = pr.path; va[r] = pr.va; vb[r] = pr.vb;
             }
         }
-        TW_PHASE();                                                  // everyone is done with D
-        // ---- output trellis Tout[d][t] (NBLDPC.cpp:1084-1094): own index first ... ----------------------------------------
+        __syncwarp();                                                  // everyone is done with D: its area becomes the output trellis
 #pragma unroll
         for (int d = 0; d < TW_DC; ++d) {
             if (DC || d < dcn) {
@@ -635,13 +667,12 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
             }
         }
         __syncwarp();
-        // ... then the entries of two-deviation paths, which land on another index (values are >= 0: ordered like their bits)
+        // ... then the landings of the two-deviation paths (values are >= 0: ordered like their bit patterns)
 #pragma unroll
         for (int r = 0; r < VEC; ++r) {
             if (path[r] >> 24) {
-                const int a = path[r] & 255, b = (path[r] >> 8) & 255, ca = (path[r] >> 16) & 3, cb = (path[r] >> 18) & 3;
-                atomic_min_nonneg(Tout + ca * Q + b, va[r]);
-                atomic_min_nonneg(Tout + cb * Q + a, vb[r]);
+                atomic_min_nonneg(Tout + ((path[r] >> 16) & 3u) * Q + (path[r] & 255u), va[r]);
+                atomic_min_nonneg(Tout + ((path[r] >> 18) & 3u) * Q + ((path[r] >> 8) & 255u), vb[r]);
             }
         }
         TW_PHASE();
