@@ -134,13 +134,41 @@ def port_run(frames):
     return {"frames": frames, "seconds": t, "threads": 1, "info_bits_per_frame": 256}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def leaf_rate():
+    """FADD2 + FMNMX3 min-plus leaves per clock per SM, measured NOW on this GPU by tools/ubench/pipes2 (built by
+    __graft_entry__.build()); None when the binary is missing"""
+    exe = os.path.join(ROOT, "tools", "ubench", "pipes2")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        for line in out.splitlines():
+            if line.startswith("{"):
+                d = json.loads(line)
+                d["table"] = [l.split(" / clk")[0].strip() for l in out.splitlines() if " / clk / SM" in l]
+                return d
+    except (OSError, subprocess.SubprocessError, ValueError):
+        pass
+    return None
+
+
 def cpu_baseline(threads, frames_per_thread, tag):
     r = reference_run(threads, frames_per_thread, "/tmp/nbldpc_ref_bench_%s" % tag)
     kind = "reference"
     if r is None:
         r, kind = port_run(8), "port"
     mbps = r["frames"] * r["info_bits_per_frame"] / r["seconds"] / 1e6
-    return {"value": mbps, "unit": "Mbit/s", "cores": r["threads"], "kind": kind,
+    return {"value": mbps, "unit": "Mbit/s", "cores": r["threads"], "kind": kind, "cpu_model": cpu_model(),
             "sample": "%d frames of the same workload (%d threads x %d, max 10 iterations with the reference's early stop), %.1f s"
                       % (r["frames"], r["threads"], r["frames"] // r["threads"], r["seconds"]),
             "frames_per_s": r["frames"] / r["seconds"]}
@@ -164,11 +192,68 @@ def main_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": threads * fpt, "iterations": "max 10, reference early stop",
-                       "host": "%d threads" % threads},
-            "cpu_baseline": {"value": value, "unit": "Mbit/s", "cores": threads, "kind": last["kind"], "sample": last["sample"]},
+                       "host": "%d threads of %s" % (threads, cpu_model())},
+            "cpu_baseline": {"value": value, "unit": "Mbit/s", "cores": threads, "kind": last["kind"], "cpu_model": cpu_model(), "sample": last["sample"]},
             "e2e": {"value": value, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+def other_configs(capi, torch, stream, seed):
+    """One short device Monte-Carlo run of every other BASELINE.json configuration (cfg1, cfg2, cfg4, cfg5): decoded Mbit/s, FER,
+    mean iterations, the kernel family that served it and the fraction of the HBM roofline of SURVEY 8(d) (algorithmic bytes
+    4 q (4E + N) per frame-iteration x iterations actually run).  fp32 fast mode, random messages with CRC-8 encoded on the device
+    (cfg4: all symbols through the Gray 256-QAM soft demapper), device time by CUDA events.  N = 1 only."""
+    import numpy as np
+    bundle = json.load(open(os.path.join(ROOT, "tests", "golden", "codes.json")))
+    peaks, _ = measured_peaks()
+
+    def code_of(name):
+        path = "/tmp/nbldpc_bench_%s.txt" % name
+        if name == "H_bit_GF256":
+            open(path, "w").write("".join("\t".join(r) + "\t\n" for r in bundle["h_bit"][name]))
+            return capi.Code.from_hbit(path, 256)
+        open(path, "w").write(bundle_code_text(name))
+        return capi.Code.from_file(path)
+
+    out = []
+    cases = [("cfg1", "divsalar.UNBLDPC.128.64.GF.16", capi.METHOD_QSPA, 0, 0, 0.0, 3.0, 148 * 512, 1, 2, None),
+             ("cfg2", "BDS.576.288.GF.64", capi.METHOD_EMS, 8, 3, 0.5, 2.0, 148 * 128, 0, 2, None),
+             ("cfg2", "BDS.576.288.GF.64", capi.METHOD_EMS, 8, 3, 0.5, 2.0, 148 * 128, 1, 2, None),
+             ("cfg4", "divsalar.CNBLDPC.512.256.GF.256", capi.METHOD_QSPA, 0, 0, 0.0, 12.0, 148 * 16, 1, 256, "GRAY_256QAM"),
+             ("cfg5", "H_bit_GF256", capi.METHOD_TEMS, 2, 2, 0.5, 4.0, 148 * 512, 1, 2, None)]
+    for tag, name, method, p0, p1, offset, ebn0, batch, early_stop, modulation, cons in cases:
+        code = code_of(name)
+        dec = capi.Decoder(code, method, 10, p0, p1, 1.0, offset, precision=capi.PREC_F32, early_stop=early_stop, max_batch=batch,
+                           stream=stream)
+        cnt = torch.zeros(capi.NUM_COUNTERS, dtype=torch.int64, device="cuda")
+        kw = dict(modulation=modulation, constellation=np.array(bundle["constellations"][cons], np.float64) if cons else None,
+                  random_msg=1, crc_len=8)
+        for i in range(2):
+            dec.simulate_async(ebn0, batch, cnt, seed=seed, first_frame=i * batch, **kw)
+        torch.cuda.synchronize()
+        cnt.zero_()
+        steps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            dec.simulate_async(ebn0, batch, cnt, seed=seed, first_frame=(2 + i) * batch, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        c = cnt.cpu().numpy()
+        frames, K = int(c[0]), code.N - code.M
+        mean_it = float(c[6]) / max(1, frames)
+        its = mean_it if early_stop else 10.0
+        gbs = frames * its * 4 * code.q * (4 * code.E + code.N) / (ms * 1e-3) / 1e9
+        out.append({"cfg": tag, "code": name, "decoder": {1: "QSPA", 2: "EMS 8/3/0.5", 4: "T-EMS 2/2/0.5"}[method],
+                    "modulation": "BPSK" if modulation == 2 else "Gray %d-QAM" % modulation, "ebn0_db": ebn0,
+                    "iterations": "max 10, early stop" if early_stop else "fixed 10", "mean_iterations": mean_it,
+                    "info_mbit_s": frames * K * code.p / (ms * 1e-3) / 1e6, "frames": frames, "fer": float(c[1]) / max(1, frames),
+                    "kernel_family": dec.kernel(), "hbm_gb_s": gbs, "hbm_frac": gbs / peaks["hbm_gbs"]})
+        dec.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -242,6 +327,7 @@ def main_ours(args):
     cnt = counters.cpu().numpy().astype(np.int64)
     launches_per_step = dec.last_timing()[1]
     it_ms = dec.iter_timing()
+    kernel_family = dec.kernel()
     frames_total = B * args.steps * world
     value = frames_total * info_bits / (ms * 1e-3) / 1e6
     # ---- same with the reference's early-stop rule ----
@@ -269,31 +355,50 @@ def main_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     h2d, d2h = y_host.numel() * 8, out_host.numel() * 4 + conv_host.numel() * 4 + iters_host.numel() * 4
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        dec.close(); dec_es.close()
+        other = other_configs(capi, torch, stream, args.seed)
     if rank == 0:
         peaks, peak_src = measured_peaks()
         E, N, q = code.E, code.N, code.q
         bytes_iter = 4 * q * (4 * E + N)                       # algorithmic bytes per frame-iteration, fp32
         leaves = 93.6e3                                        # reference's own leaf counter per check
-        ops_iter = code.M * leaves * 2
+        ops_iter = code.M * leaves * 2                         # M * L * 2 lane-ops (one add + one compare per leaf)
         k_ms = sum(it_ms) / max(1, len(it_ms))
-        achieved = bytes_iter * B / (k_ms * 1e-3) / 1e9
-        alu_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+        hbm_achieved = bytes_iter * B / (k_ms * 1e-3) / 1e9
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        nominal_alu = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6          # 1 lane-op per FP32 lane and clock
+        ub = leaf_rate() if world == 1 else None
+        if ub:      # measured in this run: FADD2 + FMNMX3 leaves per clock per SM (2 lane-ops each) at the clock seen under load
+            alu_peak, alu_src = ub["leaf_per_clk_sm"] * 2 * 148 * sm_mhz * 1e6, "measured in this run (tools/ubench/pipes2: %.1f FADD2+FMNMX3 leaves / clk / SM at %.0f MHz)" % (ub["leaf_per_clk_sm"], sm_mhz)
+        else:
+            alu_peak, alu_src = nominal_alu, "nominal 148 SM x 128 lanes x max clock (micro-benchmark binary missing)"
+        alu_achieved = ops_iter * B / (k_ms * 1e-3)
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):                               # dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture,
             t = json.load(open(tpath))                          # scaled from the captured batch to this launch's frames
             traffic, traffic_src = t["bytes_per_frame_iteration"] * B, t["capture"]
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+        # T_roof = max(B_iter / BW_hbm, Ops_iter / P_alu); the T-EMS check node at q = 256 is ALU bound
+        t_hbm, t_alu = bytes_iter / (peaks["hbm_gbs"] * 1e9), ops_iter / alu_peak
+        roofline = {"bound": "alu" if t_alu >= t_hbm else "hbm",
+                    "achieved": alu_achieved / 1e12, "peak": alu_peak / 1e12, "unit": "Tlaneop/s", "frac": alu_achieved / alu_peak,
+                    "definition": "SURVEY 8(d): reference leaf count per check (93.6 k) x 2 lane-ops x M checks per frame-iteration, over the "
+                                  "duration of one iteration launch; the kernel reaches the same minima with an exact value bound that "
+                                  "skips most leaves (DESIGN.md 4.1), so this is reference-equivalent work, not instructions issued",
+                    "peak_source": alu_src, "frac_of_nominal_peak": alu_achieved / nominal_alu, "nominal_peak": nominal_alu / 1e12,
                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": bytes_iter * B,
-                    "kernel": "k_iterate_tems_warp<float,256,4,2>", "kernel_family": dec.kernel(), "kernel_ms": k_ms, "launches_timed": len(it_ms),
-                    "peak_source": peak_src,
-                    "alu": {"note": "T-EMS check node is FP32-issue bound (SURVEY 8d): reference leaf count x 2 lane-ops",
-                            "achieved_tlaneops": ops_iter * B / (k_ms * 1e-3) / 1e12, "peak_tlaneops": alu_peak / 1e12,
-                            "frac": ops_iter * B / (k_ms * 1e-3) / alu_peak}}
+                    "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
+                            "peak_source": peak_src, "note": "secondary term of SURVEY 8(d): algorithmic bytes 4 q (4E + N) per frame-iteration"},
+                    "t_roof_us_per_frame_iteration": {"hbm": t_hbm * 1e6, "alu": t_alu * 1e6, "measured": k_ms * 1e3 / B},
+                    "kernel": "k_iterate_tems_warp<float,256,4,2>", "kernel_family": kernel_family, "kernel_ms": k_ms, "launches_timed": len(it_ms),
+                    "micro_benchmark": ub}
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(os.cpu_count() or 1, args.ref_frames_per_thread, "main")
             cb.pop("frames_per_s", None)
+        e2e_es = B * args.steps * world * info_bits / (ms_e2e_es * 1e-3) / 1e6
         line = {"metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -307,11 +412,18 @@ def main_ours(args):
                         "fer": e2e_fer},
                 "early_stop": {"value": frames_total * info_bits / (ms_es * 1e-3) / 1e6, "unit": "Mbit/s",
                                "mean_iterations": float(cnt_es[6]) / max(1, cnt_es[0]), "fer": float(cnt_es[1]) / max(1, cnt_es[0]),
-                               "e2e": B * args.steps * world * info_bits / (ms_e2e_es * 1e-3) / 1e6},
+                               "e2e": e2e_es},
+                # the reference arm (--impl reference) stops a frame at its first zero syndrome; this is our arm under the same rule,
+                # through the same host-buffer call as `e2e`: the like-for-like numerator for the driver's reference value
+                "reference_like_for_like": {"e2e_early_stop": e2e_es, "unit": "Mbit/s", "iterations": "max 10, syndrome early stop (the reference's rule)",
+                                            "mean_iterations": float(cnt_es[6]) / max(1, cnt_es[0])},
                 "gpu_launches": int(launches_per_step * args.steps), "e2e_gpu_launches": int(e2e_launches * args.steps),
                 "roofline": roofline, "clocks": clocks}
+        if other is not None:
+            line["configs"] = other
         if cb:
             line["cpu_baseline"] = cb
+            line["reference_like_for_like"]["cpu_reference"] = cb["value"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -326,7 +438,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=148 * 64, help="frames per step per GPU")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--ref-frames-per-thread", type=int, default=6)
+    ap.add_argument("--ref-frames-per-thread", type=int, default=40, help="frames per host thread of one reference / cpu_baseline sample (about 14 s on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
     a = ap.parse_args()
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

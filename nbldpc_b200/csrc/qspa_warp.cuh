@@ -55,10 +55,12 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_qspa_warp(const IterP
     constexpr int VB = (int)(Q * sizeof(T));
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const DevGraph &g = P.g;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index out of a shuffle, latch out of a vote: both exits are provably taken by whole warps, so the warp collectives
+    // below are not compiled with a second, divergent fall-back path (see tems_warp.cuh)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int f = (int)(blockIdx.z * 65535u + blockIdx.y), row = (int)blockIdx.x * TW_WARPS + warp;
     if (f >= P.B || row >= g.M) return;
-    if (P.early_stop && P.done[f]) return;
+    if (P.early_stop && __any_sync(0xffffffffu, P.done[f] != 0)) return;
 
     unsigned char *slab = smem_raw + S::bytes_per_warp * warp;
     T *V = reinterpret_cast<T *>(slab);

@@ -37,8 +37,8 @@ CASES = {
     "cfg3_tems_gf256_lowsnr": dict(code="divsalar.UNBLDPC.512.256.GF.256", GFq=256, method=4, snr=1.25, frames=6),
     "cfg4_qspa_gf256_qam": dict(code="divsalar.CNBLDPC.512.256.GF.256", GFq=256, method=1, snr=13.0, frames=2,
                                 nqam=256, constellation="GRAY_256QAM.txt", random_msg=0),
-    "cfg4_try10": dict(code="divsalar.CNBLDPC.512.256.GF.256", GFq=256, method=1, snr=5.0, frames=8, nqam=256, constellation="GRAY_256QAM.txt", random_msg=0),
-    "cfg4_try11": dict(code="divsalar.CNBLDPC.512.256.GF.256", GFq=256, method=1, snr=6.0, frames=8, nqam=256, constellation="GRAY_256QAM.txt", random_msg=0),
+    "cfg4_try10": dict(code="divsalar.CNBLDPC.512.256.GF.256", GFq=256, method=1, snr=4.0, frames=8, nqam=256, constellation="GRAY_256QAM.txt", random_msg=0),
+    "cfg4_try11": dict(code="divsalar.CNBLDPC.512.256.GF.256", GFq=256, method=1, snr=3.0, frames=8, nqam=256, constellation="GRAY_256QAM.txt", random_msg=0),
     "cfg4_try115": dict(code="divsalar.CNBLDPC.512.256.GF.256", GFq=256, method=1, snr=9.0, frames=8, nqam=256, constellation="GRAY_256QAM.txt", random_msg=0),
     "cfg5_tems_hbit256": dict(code="H_bit_GF256", GFq=256, method=4, snr=3.0, frames=24),
     "x_tems_gf16_dc5": dict(code="divsalar.UNBLDPC.128.64.GF.16", GFq=16, method=4, snr=2.0, frames=24, tems_nr=2, tems_nc=3),

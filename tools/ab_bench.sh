@@ -1,7 +1,7 @@
 #!/bin/bash
 # development aid (run on the GPU box): bench every variants/lib_*.so given, print value / kernel ms / FER
 for v in "$@"; do
-  NBLDPC_LIB=variants/lib_$v.so python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bv_$v.json 2> gpurun_out/bv_$v.err
+  NBLDPC_LIB=variants/lib_$v.so python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/bv_$v.json 2> gpurun_out/bv_$v.err
   python - "$v" <<'PY'
 import json,sys
 v=sys.argv[1]
