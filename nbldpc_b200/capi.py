@@ -237,6 +237,25 @@ def sim_config(ebn0_db, frames, seed=1, first_frame=0, modulation=2, constellati
     return cfg, (cs, cw, ps)
 
 
+def _preload_nccl():
+    """A Python process that will also import torch must end up with ONE NCCL: torch's bundled copy (same soname as the system's,
+    newer API).  If torch is not loaded yet, map its libnccl.so.2 first so that the library's dlopen finds that copy already
+    there; without torch installed the library falls back to the system's NCCL by itself."""
+    import importlib.util
+    import sys
+    if "torch" in sys.modules:
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except (ImportError, OSError, ValueError):
+        pass
+
+
 class Comm:
     """nbl_comm: the ranks whose Monte-Carlo counters are summed (NCCL).  Comm(n) = one process driving GPUs 0..n-1;
     Comm.from_rank(world, rank, id128, device) = one process per GPU (id128 from Comm.unique_id() on rank 0)."""
@@ -245,6 +264,8 @@ class Comm:
         if _handle is not None:
             self._h = _handle
             return
+        if n_devices > 1:
+            _preload_nccl()
         h = C.c_void_p()
         dv = np.ascontiguousarray(devices, np.int32) if devices is not None else None
         _check(lib().nbl_comm_create(C.byref(h), n_devices, _ip(dv)))
@@ -252,12 +273,15 @@ class Comm:
 
     @staticmethod
     def unique_id():
+        _preload_nccl()
         buf = np.zeros(128, np.uint8)
         _check(lib().nbl_comm_unique_id(_ptr(buf)))
         return buf
 
     @classmethod
     def from_rank(cls, world, rank, id128, device):
+        if world > 1:
+            _preload_nccl()
         h = C.c_void_p()
         ident = np.ascontiguousarray(id128, np.uint8) if id128 is not None else None
         _check(lib().nbl_comm_create_rank(C.byref(h), world, rank, _ptr(ident), device))

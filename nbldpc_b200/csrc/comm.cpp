@@ -3,8 +3,8 @@
 // The reference runs `parallel` CPU workers and adds their six counters serially on the host (main.cpp:46-51,
 // Comm.cpp:484-493).  Here frames are sharded over GPUs by global frame index (nbl_sim_config.first_frame) and the
 // 8 x u64 counter vector of every GPU is summed IN PLACE by one ncclAllReduce on each decoder's stream -- the only
-// collective of the path.  NCCL is bound at run time (dlopen of libnccl.so.2: torch's bundled copy when the process
-// already holds it, the system's otherwise), so single-GPU users of the library need no NCCL at all.
+// collective of the path.  NCCL is bound at run time (dlopen of libnccl.so.2: the copy the process already holds -- e.g.
+// torch's bundled one -- else the system's), so single-GPU users of the library need no NCCL at all.
 #include "internal.h"
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -33,10 +33,13 @@ NcclApi *nccl() {
     static bool tried = false;
     if (tried) return api.handle ? &api : nullptr;
     tried = true;
-    void *h = nullptr;
+    // A copy the process already holds wins (a Python process that imported torch has torch's bundled NCCL under the same
+    // soname: two different NCCL versions must never meet in one process); otherwise the system's.  RTLD_LOCAL: our binding
+    // goes through dlsym, nothing else should resolve against it.
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
-        h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
         if (h) break;
+        h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     }
     if (!h) return nullptr;
 #define BIND(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, sym)); if (!api.field) return nullptr;

@@ -4,7 +4,9 @@ global frame range.  Launch:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 --master-port 29533 tools/shard_check.py
 
-cfg5 of BASELINE.json (H_bit_GF256, T-EMS 2/2/0.5, early stop) at 4 dB with CRC-8 messages; rank 0 prints one JSON line."""
+cfg5 of BASELINE.json (H_bit_GF256, T-EMS 2/2/0.5, early stop) at 4 dB with CRC-8 messages; rank 0 prints one JSON line.
+With --abi-comm the counters are summed by the library's own communicator (nbl_comm_create_rank + nbl_allreduce_counters: one rank
+per process, the NCCL id handed over with torch.distributed) instead of torch.distributed's all_reduce."""
 import json
 import os
 import sys
@@ -40,8 +42,21 @@ def main():
         dec.simulate_async(snr, hi - lo, dev, seed=seed, first_frame=lo, random_msg=1, crc_len=8)
         return dev
 
+    abi = "--abi-comm" in sys.argv
+    comm = None
+    if abi and world > 1:
+        ident = torch.from_numpy(capi.Comm.unique_id()).cuda() if rank == 0 else torch.zeros(128, dtype=torch.uint8, device="cuda")
+        dist.broadcast(ident, 0)
+        comm = capi.Comm.from_rank(world, rank, ident.cpu().numpy(), local)
+
     def all_reduce(v):
-        if world > 1:
+        if world > 1 and comm is not None:        # nbl_allreduce_counters on the decoder's stream, in place on a device vector
+            t = torch.from_numpy(v).cuda()
+            torch.cuda.current_stream().synchronize()
+            comm.allreduce_counters([dec], [t])
+            dec.sync()
+            v[:] = t.cpu().numpy()
+        elif world > 1:
             t = torch.from_numpy(v).cuda()
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             v[:] = t.cpu().numpy()
@@ -59,7 +74,7 @@ def main():
         for k in range(rounds * world):
             again += simulate(k * batch, (k + 1) * batch).cpu().numpy()
         assert (again == alone).all(), (again, alone)           # and the run is deterministic
-        print(json.dumps({"world": world, "frames": int(total[0]), "merged": [int(x) for x in total], "one_rank": [int(x) for x in alone],
+        print(json.dumps({"world": world, "collective": "nbl_allreduce_counters (C ABI, ncclCommInitRank)" if comm is not None else "torch.distributed all_reduce", "frames": int(total[0]), "merged": [int(x) for x in total], "one_rank": [int(x) for x in alone],
                           "identical": bool((total == alone).all())}), flush=True)
     if world > 1:
         dist.barrier()
