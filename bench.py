@@ -258,6 +258,9 @@ def other_configs(capi, torch, stream, seed):
 
 # ------------------------------------------------------------------------------------------------------
 def main_ours(args):
+    # NCCL's own banner / debug lines must not land on stdout, which carries only the JSON line: set before torch (and with it
+    # NCCL) is loaded, because NCCL reads its debug settings once, at its first call
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -270,7 +273,6 @@ def main_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the decode path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's own banner / debug lines: not on stdout, which carries the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     code_path = "/tmp/nbldpc_bench_code_%d.txt" % rank

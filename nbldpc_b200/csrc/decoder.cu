@@ -606,7 +606,9 @@ template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const 
         }
         if (d->qspa_half_path) {
             const long long rows = (long long)P.B * P.g.M, per_cta = QH_ROWS * QH_WARPS;
-            k_iterate_qspa_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, QhSmem<T>::bytes, d->stream>>>(P, d->d_rowdesc8);
+            const size_t smem = QhQspaSmem<T>::bytes(P.g.max_dc);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_iterate_qspa_half<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_iterate_qspa_half<T><<<(unsigned)((rows + per_cta - 1) / per_cta), 32 * QH_WARPS, smem, d->stream>>>(P, d->d_rowdesc8);
             CK(cudaGetLastError());
             return NBL_OK;
         }

@@ -221,69 +221,168 @@ __device__ __forceinline__ void qh_vn_phase(const IterParams<T> &P, const int *_
     if (R.active && l4 == 0 && syn != 0) P.flag[f] = 1;
 }
 
+// The QSPA kernel is written as ROLLED loops over the row's edges (one copy of the variable-node step, of the forward
+// transform and of the output stage): unrolled over 8 edges it was ~4 400 instructions, 70 KB, and ran at 92 % of the GPC
+// instruction cache's request rate -- bound by instruction fetch, like the T-EMS warp kernel before it was folded.
+// Per-edge state that the unrolled form kept in registers lives in shared memory: the transformed distributions F[d].
+template <typename T> struct QhQspaSmem {
+    // per warp:  F [dc][QH_ROWS][16] doubles (transformed input distributions of the warp's eight rows),
+    //            V [QH_ROWS][16] T (the current edge's vector in natural order, for the gathers), R [QH_ROWS][16] doubles
+    static constexpr size_t f_bytes_per_edge = (size_t)QH_ROWS * 16 * sizeof(double);
+    static constexpr size_t r_bytes = (size_t)QH_ROWS * 16 * sizeof(double);
+    static constexpr size_t v_bytes = (size_t)QH_ROWS * 16 * sizeof(T);
+    __host__ __device__ static size_t bytes_per_warp(int max_dc) { return f_bytes_per_edge * max_dc + r_bytes + v_bytes; }
+    __host__ __device__ static size_t bytes(int max_dc) { return bytes_per_warp(max_dc) * QH_WARPS; }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 4 : 2) k_iterate_qspa_half(const IterParams<T> P, const int *__restrict__ desc) {
+__global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 6 : 2) k_iterate_qspa_half(const IterParams<T> P, const int *__restrict__ desc) {
     constexpr int Q = 16;
     extern __shared__ __align__(16) unsigned char qh_raw[];
     const DevGraph &g = P.g;
     QhRow<T> R;
     if (!qh_setup<T>(P, R)) return;
-    const int warp = threadIdx.x >> 5, l4 = R.l4, x0 = R.x0, f = R.f, e0 = R.e0, dcn = R.dcn, dmax = R.dmax;
-    T *sV = reinterpret_cast<T *>(qh_raw + QhSmem<T>::bytes_per_warp * warp) + R.rw * 16;
-    double *sR = reinterpret_cast<double *>(qh_raw + QhSmem<T>::bytes_per_warp * warp + QhSmem<T>::v_bytes) + R.rw * 16;
-    T V[QH_MAXDC][4];
-    unsigned tf[QH_MAXDC], ti[QH_MAXDC];                            // my four bytes of the rows h * x and h^-1 * x
-    unsigned sdw;                                                   // nibble d: decide(v2c_d)
-    qh_vn_phase<T>(P, desc, R, V, tf, ti, sdw);
-    // ---- check node: distributions in the syndrome domain, maximum normalised to 1, transformed ------------------------------
-    double F[QH_MAXDC][4];
+    const int warp = __shfl_sync(QH_FULL, (int)(threadIdx.x >> 5), 0), lane = R.lane, l4 = R.l4, x0 = R.x0, f = R.f, e0 = R.e0, dcn = R.dcn, dmax = R.dmax;
+    unsigned char *slab = qh_raw + QhQspaSmem<T>::bytes_per_warp(g.max_dc) * warp;
+    double *sF = reinterpret_cast<double *>(slab) + R.rw * 16 + x0;                              // + d * QH_ROWS * 16: my four points of edge d
+    double *sR = reinterpret_cast<double *>(slab + QhQspaSmem<T>::f_bytes_per_edge * g.max_dc) + R.rw * 16;
+    T *sV = reinterpret_cast<T *>(slab + QhQspaSmem<T>::f_bytes_per_edge * g.max_dc + QhQspaSmem<T>::r_bytes) + R.rw * 16;
+    const int *rd = desc + (size_t)R.row * (QH_MAXDC * QH_DSC);
+    const T *lchf = P.lch + (size_t)f * g.N * Q + x0;
+    const T *cinf = P.c2v_in + (size_t)f * g.E * Q + x0;
+    T *v2cf = P.v2c + (size_t)f * g.E * Q + x0;
+    uint8_t *vdecf = P.vdec + (size_t)f * g.E;
+    // ---- steps A-C (NBLDPC.cpp:676-744) and the forward transform, edge by edge.  The descriptor of edge d + 2 and the messages
+    //      of edge d + 1 are requested while edge d is worked on -- into the registers edge d has just consumed.
+    int4 da, na; int2 db, nb;                                       // {variable, degree, edge ids 0..1}, {edge ids 2..3}: current, next
+    T lc[4], mm[QH_MAXDV][4]; unsigned meta;                        // meta: own slot | degree << 4 | old decision + 1 << 8 | variable << 17
+    auto fetch_desc = [&](int d, int4 &a, int2 &b) {
+        a = make_int4(0, 0, 0, 0); b = make_int2(0, 0);
+        if (d < dcn) { a = *reinterpret_cast<const int4 *>(rd + QH_DSC * d); b = *reinterpret_cast<const int2 *>(rd + QH_DSC * d + 4); }
+    };
+    auto fetch_msgs = [&](int d) {                                  // from the descriptor in (da, db)
+        const int ej[QH_MAXDV] = {da.z, da.w, db.x, db.y};
+        const int nv = da.y;
+        int own = QH_MAXDV, bef = 0;
 #pragma unroll
-    for (int d = 0; d < QH_MAXDC; ++d) {
+        for (int i = 0; i < 4; ++i) lc[i] = T(0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) F[d][i] = 1.0;
-        if (d < dmax) {
-            qh_store4<T>(sV + x0, V[d]);
-            __syncwarp();
-            const double vmax = (double)sV[(sdw >> (4 * d)) & 15u];
-            double t[4];
+        for (int j = 0; j < QH_MAXDV; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = qspa_exp<T>((double)sV[(ti[d] >> (8 * i)) & 255u] - vmax);   // P[s] = p[h^-1 s]
-            __syncwarp();
-            qh_wht(t, l4);
-            if (d < dcn) {                                          // edges another row has and this one lacks: factor 1
+            for (int i = 0; i < 4; ++i) mm[j][i] = T(0);
+        if (d < dcn) {
+            qh_load4<T>(lchf + (size_t)da.x * Q, lc);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) F[d][i] = t[i];
+            for (int j = 0; j < QH_MAXDV; ++j) {
+                if (!P.first && j < nv) qh_load4<T>(cinf + (size_t)ej[j] * Q, mm[j]);
+                if (j < nv && ej[j] == e0 + d) own = j;
+            }
+            bef = P.first ? 0 : (int)vdecf[e0 + d] + 1;
+        }
+        meta = (unsigned)own | ((unsigned)nv << 4) | ((unsigned)bef << 8) | ((unsigned)da.x << 17);
+    };
+    int syn = 0;
+    fetch_desc(0, da, db);
+    fetch_msgs(0);
+    fetch_desc(1, na, nb);
+#pragma unroll 1
+    for (int d = 0; d < dmax; ++d) {                                // dmax: the longest of the warp's rows (warp-uniform)
+        const bool live = d < dcn;
+        const int e = e0 + d, own = (int)(meta & 15u), nv = (int)((meta >> 4) & 15u), bef = (int)((meta >> 8) & 511u), col = (int)(meta >> 17);
+        unsigned tfw = 0u, tiw = 0u;                                // my four bytes of the rows h * x and h^-1 * x
+        if (live) {
+            tfw = *reinterpret_cast<const unsigned *>(g.pfwd + (size_t)e * Q + x0);
+            tiw = *reinterpret_cast<const unsigned *>(g.pinv + (size_t)e * Q + x0);
+        }
+        T post[4], mine[4], vnew[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { post[i] = lc[i]; mine[i] = T(0); }
+#pragma unroll
+        for (int j = 0; j < QH_MAXDV; ++j)
+            if (j < nv) {                                           // iteration 1: + 0, exact
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { post[i] = post[i] + mm[j][i]; if (j == own) mine[i] = mm[j][i]; }
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vnew[i] = post[i] - mine[i];
+        da = na; db = nb;                                           // lc, mm and the descriptor are consumed: the next edge goes out
+        if (d + 1 < dmax) fetch_msgs(d + 1);
+        if (d + 2 < dmax) fetch_desc(d + 2, na, nb);
+        const int dpost = qh_decide<T>(post, x0);
+        int dfin = qh_decide<T>(vnew, x0);
+        const bool need = live && !P.first && P.w_old != T(0) && dfin != bef - 1;
+        if (__any_sync(QH_FULL, need)) {                            // warp-uniform
+            T vd[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) vd[i] = vnew[i];
+            if (need) {
+                T vold[4];
+                qh_load4<T>(v2cf + (size_t)e * Q, vold);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vd[i] = P.w_old * vold[i] + P.w_new * vnew[i];        // -fmad=false
+            }
+            const int d2 = qh_decide<T>(vd, x0);
+            if (need) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vnew[i] = vd[i];
+                dfin = d2;
             }
         }
+        if (live) {
+            qh_store4<T>(v2cf + (size_t)e * Q, vnew);
+            if (l4 == 0) { vdecf[e] = (uint8_t)dfin; P.dec[(size_t)f * g.N + col] = (uint8_t)dpost; }
+        }
+        // h * decision: byte dpost & 3 of the word of lane dpost >> 2 of this row
+        const unsigned hw = __shfl_sync(QH_FULL, tfw, (lane & ~3) + (dpost >> 2));
+        if (live) syn ^= (int)((hw >> (8 * (dpost & 3))) & 255u);
+        // check node, forward half: the distribution in the syndrome domain, maximum normalised to 1, transformed
+        qh_store4<T>(sV + x0, vnew);
+        __syncwarp();
+        const double vmax = (double)sV[dfin];
+        double t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = qspa_exp<T>((double)sV[(tiw >> (8 * i)) & 255u] - vmax);       // P[s] = p[h^-1 s]
+        __syncwarp();
+        qh_wht(t, l4);
+        if (!live) {                                                // edges another row of the warp has and this one lacks: factor 1
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = 1.0;
+        }
+        qh_store4<double>(sF + (size_t)d * (QH_ROWS * 16), t);
     }
+    if (R.active && l4 == 0 && syn != 0) P.flag[f] = 1;
+    __syncwarp();
+    // ---- check node, backward half: product of the other edges' transforms (ascending, * 1.0 is exact), inverse transform, log ----
     T *coutf = P.c2v_out + (size_t)f * g.E * Q + x0;
+#pragma unroll 1
+    for (int d = 0; d < dmax; ++d) {
+        double r[4] = {1.0, 1.0, 1.0, 1.0};
+#pragma unroll 1
+        for (int l = 0; l < dmax; ++l) {
+            if (l != d) {
+                double fl4[4];
+                qh_load4<double>(sF + (size_t)l * (QH_ROWS * 16), fl4);
 #pragma unroll
-    for (int d = 0; d < QH_MAXDC; ++d) {
-        if (d < dmax) {
-            double r[4] = {1.0, 1.0, 1.0, 1.0};
-#pragma unroll
-            for (int l = 0; l < QH_MAXDC; ++l)
-                if (l != d) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) r[i] *= F[l][i];    // * 1.0 is exact
-                }
-            qh_wht(r, l4);
-            qh_store4<double>(sR + x0, r);
-            __syncwarp();
-            // floor at the fp64 noise of the transform (see cn_qspa.cuh), log, un-permute
-            const double tot = sR[0];
-            const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
-            const double lt = qspa_log<T>(tot > fl ? tot : fl);
-            T out[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double a = sR[(tf[d] >> (8 * i)) & 255u];
-                out[i] = (T)(qspa_log<T>(a > fl ? a : fl) - lt);
+                for (int i = 0; i < 4; ++i) r[i] *= fl4[i];
             }
-            __syncwarp();
-            if (l4 == 0) out[0] = T(0);
-            if (d < dcn) qh_store4<T>(coutf + (size_t)(e0 + d) * Q, out);
         }
+        const unsigned tfw = d < dcn ? *reinterpret_cast<const unsigned *>(g.pfwd + (size_t)(e0 + d) * Q + x0) : 0u;
+        qh_wht(r, l4);
+        qh_store4<double>(sR + x0, r);
+        __syncwarp();
+        // floor at the fp64 noise of the transform (see cn_qspa.cuh), log, un-permute
+        const double tot = sR[0];
+        const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
+        const double lt = qspa_log<T>(tot > fl ? tot : fl);
+        T out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double a = sR[(tfw >> (8 * i)) & 255u];
+            out[i] = (T)(qspa_log<T>(a > fl ? a : fl) - lt);
+        }
+        __syncwarp();
+        if (l4 == 0) out[0] = T(0);
+        if (d < dcn) qh_store4<T>(coutf + (size_t)(e0 + d) * Q, out);
     }
 }
 
