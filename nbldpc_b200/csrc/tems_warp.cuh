@@ -1,32 +1,35 @@
 // Fast path of the fused iteration kernel for T-EMS with n_c <= 2 (the headline configuration):
 // ONE WARP per (frame, check row), VEC = Q/32 consecutive field elements per lane.
 //
-// Same results as the generic group kernel (decoder.cu / cn_tems.cuh).  Two resources bound it, in this order on B200:
-// the shared-memory pipe (128 B/clk per SM, shared by four schedulers: one wavefront costs as much as four issue slots)
-// and instruction issue.  The organisation follows from that:
+// Same results as the generic group kernel (decoder.cu / cn_tems.cuh).  What shaped it, in the order the measurements forced it
+// (DESIGN.md 4.1 has the numbers):
+//   * INSTRUCTION FETCH.  Unrolled over the lane's elements, the row's edges and the outputs, the kernel was 3 800 SASS
+//     instructions (60 KB) and ran at 85-95 % of the request rate of the GPC-level instruction cache
+//     (gcc__cache_requests_type_instruction): every round of optimisation that only removed instructions left its duration
+//     where it was.  So there is ONE copy of everything now -- the variable-node step is a rolled loop over the edges, the delta
+//     domain and the column order a rolled loop over the lane's elements, the pair recovery an out-of-line function -- and both
+//     exits of the kernel are provably taken by whole warps (warp index out of a shuffle, latch out of a vote), which stops the
+//     compiler from emitting a second, divergent version of every warp collective.  1 960 instructions, 31 KB: the cache
+//     requests fell from 5 M to 15 k per launch.
+//   * the pair search uses the structure of the allowed sets.  Let c0(x), c1(x) be the cheapest / second cheapest column of
+//     eta = x and m0(x) <= m1(x) their costs (TEMS_Min).  For a pair (a, b) with a ^ b = s the cheapest valid assignment of two
+//     DIFFERENT columns is m0(a) + m0(b) when c0(a) != c0(b), else min(m0(a) + m1(b), m1(a) + m0(b)); columns beyond the second
+//     never win.  So with  D_c[x] = (c0(x) == c ? m1(x) : m0(x))  -- the cheapest column of x other than c --
+//         deltaW2[s] = min over a != 0 of  m0(a) + D_{c0(a)}[s ^ a]
+//     (255 x q candidates where the reference enumerates ~94 k configurations; n_r = 1: D_c[x] = +inf where c0(x) == c);
+//   * and it is PRUNED BY VALUE, exactly: an entry a whose m0(a) exceeds half of the largest deltaW any output can still have
+//     cannot be the lighter element of a winning pair and is skipped -- its pairs are reached from their other element (see the
+//     search for the one case that needs a second kind of candidate).  ~50 of the 255 entries survive in the first iterations,
+//     ~11 in the last; the minima and the recorded pairs are those of the full enumeration;
+//   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; entry a = VEC*bh + bl reads block k = t ^ bh of D_{c0(a)}
+//     (its column is part of the ADDRESS: no dispatch), permuted by bl, which is a compile-time constant of the VEC unrolled
+//     entry bodies; sums are FADD2 (two per instruction, sm_100a);
 //   * no block-level barriers: every exchange between lanes is a __syncwarp on the warp's private smem slab;
-//   * the pair search uses the structure of the allowed sets.  Let c0(x), c1(x) be the cheapest / second cheapest
-//     column of eta = x and m0(x) <= m1(x) their costs (TEMS_Min).  For a pair (a, b) with a ^ b = s the cheapest
-//     valid assignment of two DIFFERENT columns is m0(a) + m0(b) when c0(a) != c0(b), else
-//     min(m0(a) + m1(b), m1(a) + m0(b)); columns beyond the second never win (c1(b) != c0(b) is always available).
-//     So with  D_c[x] = (c0(x) == c ? m1(x) : m0(x))  -- the cheapest column of x other than c --
-//         deltaW2[s] = min over a != 0 of  m0(a) + D_{c0(a)}[s ^ a] ,
-//     255 x q leaves instead of the ~94 k configurations the reference enumerates (or the 98 k of a per-column
-//     scan), every leaf useful.  (n_r = 1: D_c[x] = +inf where c0(x) == c.  n_r >= 2 all give this minimum.)
-//   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; the VEC entries a = VEC*bh + bl of eta-block bh all
-//     read block k = t ^ bh of some D_c, permuted by bl.  The TW_DC candidate vectors are loaded ONCE per block with
-//     conflict-free 128-bit loads (2 bytes of shared-memory traffic per leaf instead of 4) and every entry picks its
-//     column with a warp-uniform branch; a leaf pair is one FADD2 (two sums) and half an FMNMX3:
-//         best[r] = min3(best[r], d[r ^ bl] + m0(a), d'[r ^ bl'] + m0(a'));
-//   * arg-min bookkeeping is done per eta-block (2 instructions per output per block: "did this block improve it" is
-//     one compare of the running minimum before and after); the winning block is re-scanned once at the end to recover
-//     the exact pair of the recorded path;
-//   * all message-sized vectors in shared memory (v2c, D_c, the output trellis) use the same split layout, so that the
-//     128-bit accesses of a lane to its own elements are conflict free; gathers go through table bytes that are stored
-//     pre-swizzled to that layout, for the lane's own elements only:  h^-1 (eta ^ beta) = h^-1 eta ^ decide(v2c)  and
-//     h x ^ (syn ^ beta)  need no data-dependent table row, an address is  base ^ (byte ^ key) << 2  (one shift, one LOP3),
-//     and the scalar look-ups beta = h * decide(.) are two shuffles out of registers;
-//   * the search loop does one eta-block per trip so that its body stays inside the instruction cache.
+//   * all message-sized vectors in shared memory (v2c, D_c, the output trellis) use the same split layout, so that the 128-bit
+//     accesses of a lane to its own elements are conflict free; gathers go through table bytes that are stored pre-swizzled to
+//     that layout, for the lane's own elements only:  h^-1 (eta ^ beta) = h^-1 eta ^ decide(v2c)  and  h x ^ (syn ^ beta)  need
+//     no data-dependent table row, an address is  base ^ (byte ^ key) << 2, and the scalar look-ups beta = h * decide(.) are
+//     two shuffles out of registers.
 // BS-TEMS (decode method 7) runs on the same kernel with BS = 1: everything around the search is shared, the search itself
 // is replaced by the basic-set construction and the walk over its subsets (see the BS block in the kernel).
 #pragma once
@@ -251,9 +254,6 @@ template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char 
     }
 }
 
-#ifndef TW_PREFETCH_VOLD
-#define TW_PREFETCH_VOLD 0
-#endif
 template <typename T, int N> __device__ __forceinline__ T vec_max(const T (&v)[N]) {
     if constexpr (N == 8) return max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), fmax(v[6], v[7]));
     else if constexpr (N == 4) return fmax(max3(v[0], v[1], v[2]), v[3]);

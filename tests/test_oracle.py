@@ -27,12 +27,15 @@ def test_oracle_reproduces_reference_golden(name):
 
 
 def test_oracle_qspa_gf256_qam_one_frame():
+    """the frame of the 256-QAM fixture that needs the fewest iterations (the oracle's box-plus, like the reference's, takes ~2.6 s
+    per frame-iteration); tests/golden/make_golden.py pinned all eight, including the two that do not converge"""
     z, meta = load_golden("cfg4_qspa_gf256_qam")
     oc = po.OracleCode(get_code_dict(meta["code"]))
-    lch = golden_lch(z, meta, 1)
-    ret, it, out, post = oc.decode(1, meta["max_iter"], 0, 0, 1.0, 0.0, lch[0])
-    assert (ret, it) == (int(z["ret"][0]), int(z["iters"][0])) and np.array_equal(out, z["dec_sym"][0])
-    assert np.array_equal(post[:, z["lpost_idx"]], z["lpost_sample"][0])
+    f = int(np.argmin(z["iters"]))
+    lch = golden_lch(z, meta)[f]
+    ret, it, out, post = oc.decode(1, meta["max_iter"], 0, 0, 1.0, 0.0, lch)
+    assert (ret, it) == (int(z["ret"][f]), int(z["iters"][f])) and np.array_equal(out, z["dec_sym"][f])
+    assert np.array_equal(post[:, z["lpost_idx"]], z["lpost_sample"][f])
 
 
 def test_gf_tables_properties():
