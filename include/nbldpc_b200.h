@@ -277,6 +277,10 @@ int nbl_decoder_last_timing(nbl_decoder *dec, float *kernel_ms, int *launches);
 /* per-launch duration (ms) of the fused iteration kernel in the last decode on this decoder: ms[i] is
  * iteration i+1.  Synchronises the stream.  Returns the number of entries written (<= capacity). */
 int nbl_decoder_iter_timing(nbl_decoder *dec, float *ms, int capacity);
+/* frames that had not yet returned (the reference returns a frame at its first zero syndrome, NBLDPC.cpp:1016-1026) when each
+ * iteration of the last decode on this decoder ran: active[i] is iteration i+1.  With early_stop = 1 the iteration kernels work on
+ * these frames only; beside nbl_decoder_iter_timing this shows what the tail iterations cost per active frame.  Synchronises. */
+int nbl_decoder_iter_active(nbl_decoder *dec, int *active, int capacity);
 
 #ifdef __cplusplus
 }

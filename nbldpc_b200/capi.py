@@ -85,6 +85,7 @@ def lib():
         L.nbl_simulate_async.argtypes = [vp, C.POINTER(SimConfig), vp]
         L.nbl_decoder_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.nbl_decoder_iter_timing.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.nbl_decoder_iter_active.argtypes = [vp, ip, C.c_int]
         L.nbl_comm_create.argtypes = [C.POINTER(vp), C.c_int, ip]
         L.nbl_comm_unique_id.argtypes = [vp]
         L.nbl_comm_create_rank.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, C.c_int]
@@ -430,6 +431,12 @@ class Decoder:
         ms = (C.c_float * 64)()
         n = _check(lib().nbl_decoder_iter_timing(self._h, ms, 64))
         return [ms[i] for i in range(n)]
+
+    def iter_active(self):
+        """frames still decoding when each iteration of the last decode ran"""
+        a = np.zeros(64, np.int32)
+        n = _check(lib().nbl_decoder_iter_active(self._h, _ip(a), 64))
+        return a[:n].tolist()
 
     def close(self):
         if self._h:

@@ -163,9 +163,12 @@ __global__ void k_syndrome(DevGraph g, int B, int early_stop, const uint8_t *__r
 }
 
 // per frame: latch the result at the first zero syndrome (or at max_iter), as the reference returns it.  One warp per frame.
+// active[iter - 1] += frames that were still decoding when iteration `iter` ran (one atomic per CTA): the early-stop statistics
 __global__ void k_finalize(int B, int N, int iter, int max_iter, int *flag, uint8_t *done, int *iters, int *conv,
-                           const uint8_t *__restrict__ dec, int *out_sym, uint8_t *newly) {
+                           const uint8_t *__restrict__ dec, int *out_sym, uint8_t *newly, int *active) {
     const int f = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    const int was_active = __syncthreads_count(f < B && lane == 0 && !done[f]);
+    if (threadIdx.x == 0 && was_active) atomicAdd(active + iter - 1, was_active);
     if (f >= B) return;
     int l = 0;
     if (lane == 0) {
@@ -249,7 +252,7 @@ struct nbl_decoder {
     uint8_t *d_pfwd = nullptr, *d_pinv = nullptr, *d_pfwd_sw = nullptr, *d_pinv_sw = nullptr;
     void *d_lch = nullptr, *d_v2c = nullptr, *d_c2v[2] = {nullptr, nullptr};
     uint8_t *d_vdec = nullptr, *d_dec = nullptr, *d_done = nullptr, *d_newly = nullptr;
-    int *d_flag = nullptr, *d_iters = nullptr, *d_conv = nullptr, *d_out = nullptr;
+    int *d_flag = nullptr, *d_iters = nullptr, *d_conv = nullptr, *d_out = nullptr, *d_active = nullptr;
     double *d_stage = nullptr;   size_t stage_bytes = 0;     // staging for host LLR inputs / outputs (doubles)
     double *d_ystage = nullptr;  size_t ystage_bytes = 0;    // staging for host received samples
     std::vector<int> punct_cache; int punct_mod = -1, punct_ylen = 0;
@@ -325,7 +328,7 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
     cudaSetDevice(d->cfg.device);
     void *ptrs[] = {d->d_chk_ptr, d->d_chk_var, d->d_var_ptr, d->d_var_edge, d->d_ysym, d->d_rowdesc, d->d_pfwd, d->d_pinv, d->d_pfwd_sw, d->d_pinv_sw, d->d_lch, d->d_v2c,
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
-                    d->d_out, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg, d->d_osd_H0, d->d_osd_sum, d->d_osd_status, d->d_rowdesc8};
+                    d->d_out, d->d_active, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg, d->d_osd_H0, d->d_osd_sum, d->d_osd_status, d->d_rowdesc8};
     if (d->sim_enc) nbl_encoder_destroy(d->sim_enc);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : d->it_ev) if (e) cudaEventDestroy(e);
@@ -429,6 +432,7 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     ALLOC(d->d_vdec, B * E); ALLOC(d->d_dec, B * N); ALLOC(d->d_done, B); ALLOC(d->d_newly, B);
     ALLOC(d->d_flag, B * sizeof(int)); ALLOC(d->d_iters, B * sizeof(int)); ALLOC(d->d_conv, B * sizeof(int));
     ALLOC(d->d_out, B * N * sizeof(int));
+    ALLOC(d->d_active, (size_t)cfg->max_iter * sizeof(int));
     ALLOC(d->d_ysym, N * sizeof(int));
     ALLOC(d->d_cons, 2 * q * sizeof(double));
 #undef ALLOC
@@ -503,6 +507,16 @@ extern "C" int nbl_decoder_iter_timing(nbl_decoder *d, float *ms, int capacity) 
     CK(cudaStreamSynchronize(d->stream));
     int n = d->it_recorded < capacity ? d->it_recorded : capacity;
     for (int i = 0; i < n; ++i) CK(cudaEventElapsedTime(&ms[i], d->it_ev[2 * i], d->it_ev[2 * i + 1]));
+    return n;
+}
+
+// frames still decoding when each iteration of the last decode ran: active[i] for iteration i + 1 (max_iter entries)
+extern "C" int nbl_decoder_iter_active(nbl_decoder *d, int *active, int capacity) {
+    if (!d || !active) { nbl_set_error("nbl_decoder_iter_active: null argument"); return NBL_ERR_ARG; }
+    CK(cudaSetDevice(d->cfg.device));
+    CK(cudaStreamSynchronize(d->stream));
+    const int n = d->cfg.max_iter < capacity ? d->cfg.max_iter : capacity;
+    CK(cudaMemcpy(active, d->d_active, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
     return n;
 }
 
@@ -661,6 +675,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
     d->last_launches = 0; d->it_recorded = 0;
     CK(cudaMemsetAsync(d->d_flag, 0, (size_t)B * sizeof(int), d->stream));
     CK(cudaMemsetAsync(d->d_done, 0, (size_t)B, d->stream));
+    CK(cudaMemsetAsync(d->d_active, 0, (size_t)c.max_iter * sizeof(int), d->stream));
     const bool osd_acc = d->osd_on && d->osd.order >= 0 && !d->osd.flag;
     if (osd_acc) CK(cudaMemsetAsync(d->d_osd_sum, 0, (size_t)B * d->osd.nbit * sizeof(double), d->stream));
     CK(cudaEventRecord(d->ev0, d->stream));
@@ -698,7 +713,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
             CK(cudaGetLastError());
             d->last_launches += 2;
         }
-        k_finalize<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, d->stream>>>(B, d->g.N, it, c.max_iter, d->d_flag, d->d_done, d->d_iters, d->d_conv, d->d_dec, d->d_out, d->d_newly);
+        k_finalize<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, d->stream>>>(B, d->g.N, it, c.max_iter, d->d_flag, d->d_done, d->d_iters, d->d_conv, d->d_dec, d->d_out, d->d_newly, d->d_active);
         CK(cudaGetLastError());
         d->last_launches += 1;
         if (post_dev) {

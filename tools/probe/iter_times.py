@@ -15,4 +15,9 @@ for es in (0, 1):
     for rep in range(3):
         c = dec.simulate(2.5, B, seed=1 + rep, random_msg=1, crc_len=8)
     t = dec.iter_timing()
+    act = dec.iter_active()
     print(os.environ.get("NBLDPC_LIB", "lib"), "early_stop", es, "iter ms:", " ".join("%.2f" % x for x in t), " sum %.2f" % sum(t), " FER %.4f" % (c[1] / c[0]))
+    print("   active frames:", " ".join(str(x) for x in act))
+    full = max(t[1:4])
+    print("   ms per iteration if cost were proportional to the active frames:", " ".join("%.2f" % (full * a / B) for a in act[:len(t)]),
+          " sum %.2f" % sum(full * a / B for a in act[:len(t)]))
