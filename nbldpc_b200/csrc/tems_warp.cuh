@@ -48,9 +48,9 @@ constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, 
                               // (spare of edge 0 = first edge id of the row, spare of edge 1 = row degree)
 constexpr int TW_HOIST = 2;   // messages of a variable fetched ahead (its degree may be larger: slow loop)
 #ifndef TW_MIN_CTAS_VALUE
-#define TW_MIN_CTAS_VALUE 5
+#define TW_MIN_CTAS_VALUE 6
 #endif
-constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident CTAs per SM the register allocation aims for (5 x 4 warps)
+constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident CTAs per SM the register allocation aims for (6 x 4 warps at 80 registers: measured +2.7 % over 5 x 4 at 96; 7 spills)
 #ifndef TW_MINB_VALUE
 #define TW_MINB_VALUE (TW_MIN_CTAS * 4 / TW_WARPS)
 #endif
@@ -175,14 +175,6 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) {
 #endif
 #if TW_STATS
 __device__ unsigned long long tw_stats[128];     // per iteration: rows, live entries, candidates of the second kind, blocks with a live entry
-#endif
-#ifndef TW_PHASE_SYNC
-#define TW_PHASE_SYNC 0        // experiment: CTA-wide barriers at the phase boundaries, so that the warps of a CTA fetch the same code
-#endif
-#if TW_PHASE_SYNC
-#define TW_PHASE() __syncthreads()
-#else
-#define TW_PHASE() __syncwarp()
 #endif
 constexpr int TW_NOTAG = 0xffff;
 // IEEE division kept out of line (one copy of the routine; the correction factor is 1 in every shipped profile)
@@ -464,7 +456,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
     unsigned long long tiv[TW_DC];
 #pragma unroll
     for (int d = 0; d < TW_DC; ++d) { tiv[d] = 0; if (DC || d < dcn) tiv[d] = ld_bytes<VEC>(P.pinv_sw + (size_t)(e0 + d) * Q + x0); }
-    TW_PHASE();
+    __syncwarp();
     // ---- delta domain (TEMS_Get_deltaU): dU[d][eta] = max_d - V_d[h^-1 (eta ^ beta_d)],  h^-1 (eta ^ beta_d) = h^-1 eta ^ decide,
     //      and the column order per eta (TEMS_Get_Min): c0, c1, m0, m1 -- rolled over the lane's VEC elements (one copy of the
     //      four gathers and of the ordering network); the results go to the block records, M1 and c01, none of which the gathers read
@@ -529,7 +521,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
             }
         }
     }
-    TW_PHASE();
+    __syncwarp();
     const unsigned long long c01w = ld_bytes<VEC>(c01 + x0);
     T *Tout = R1;
     if constexpr (!BS) {
@@ -675,7 +667,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
                 atomic_min_nonneg(Tout + ((path[r] >> 18) & 3u) * Q + ((path[r] >> 8) & 255u), vb[r]);
             }
         }
-        TW_PHASE();
+        __syncwarp();
     } else {
         // ---- BS-TEMS (Decoding_BS_TEMS, NBLDPC.cpp:1145-1396).  As the reference runs it the T-EMS stage only leaves the
         //      all-zero configuration (TEMS_Nr is never set in this mode); every other syndrome is reached by a subset of the
@@ -802,7 +794,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
             st_split<T, VEC>(Tout + d * Q, lane, tv);
         }
     }
-    TW_PHASE();
+    __syncwarp();
     // ---- normal domain, un-permute, correct (NBLDPC.cpp:1105-1128) ------------------------------------------------------
     T *coutf = P.c2v_out + (size_t)f * g.E * Q + VEC * lane;
     unsigned long long tnext = ld_bytes<VEC>(P.pfwd_sw + (size_t)e0 * Q + x0);
