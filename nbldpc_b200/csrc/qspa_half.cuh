@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 6 : 2) k_itera
     if (!qh_setup<T>(P, R)) return;
     const int warp = __shfl_sync(QH_FULL, (int)(threadIdx.x >> 5), 0), lane = R.lane, l4 = R.l4, x0 = R.x0, f = R.f, e0 = R.e0, dcn = R.dcn, dmax = R.dmax;
     unsigned char *slab = qh_raw + QhQspaSmem<T>::bytes_per_warp(g.max_dc) * warp;
-    double *sF = reinterpret_cast<double *>(slab) + R.rw * 16 + x0;                              // + d * QH_ROWS * 16: my four points of edge d
+    // my four points of edge d live at sF + d * QH_ROWS * 16 as two 16-byte pieces, piece h of all lanes contiguous (only this lane
+    // ever reads them back): 128-bit accesses without bank conflicts (a lane's 32 bytes in one run are a 2-way conflict)
+    double *sF = reinterpret_cast<double *>(slab) + 2 * lane;
     double *sR = reinterpret_cast<double *>(slab + QhQspaSmem<T>::f_bytes_per_edge * g.max_dc) + R.rw * 16;
     T *sV = reinterpret_cast<T *>(slab + QhQspaSmem<T>::f_bytes_per_edge * g.max_dc + QhQspaSmem<T>::r_bytes) + R.rw * 16;
     const int *rd = desc + (size_t)R.row * (QH_MAXDC * QH_DSC);
@@ -348,7 +350,11 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 6 : 2) k_itera
 #pragma unroll
             for (int i = 0; i < 4; ++i) t[i] = 1.0;
         }
-        qh_store4<double>(sF + (size_t)d * (QH_ROWS * 16), t);
+        {
+            double *dst = sF + (size_t)d * (QH_ROWS * 16);
+            *reinterpret_cast<double2 *>(dst) = make_double2(t[0], t[1]);
+            *reinterpret_cast<double2 *>(dst + 64) = make_double2(t[2], t[3]);
+        }
     }
     if (R.active && l4 == 0 && syn != 0) P.flag[f] = 1;
     __syncwarp();
@@ -360,10 +366,9 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 6 : 2) k_itera
 #pragma unroll 1
         for (int l = 0; l < dmax; ++l) {
             if (l != d) {
-                double fl4[4];
-                qh_load4<double>(sF + (size_t)l * (QH_ROWS * 16), fl4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) r[i] *= fl4[i];
+                const double *srcF = sF + (size_t)l * (QH_ROWS * 16);
+                const double2 fa = *reinterpret_cast<const double2 *>(srcF), fb = *reinterpret_cast<const double2 *>(srcF + 64);
+                r[0] *= fa.x; r[1] *= fa.y; r[2] *= fb.x; r[3] *= fb.y;
             }
         }
         const unsigned tfw = d < dcn ? *reinterpret_cast<const unsigned *>(g.pfwd + (size_t)(e0 + d) * Q + x0) : 0u;
