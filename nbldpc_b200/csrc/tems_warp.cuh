@@ -176,7 +176,10 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) {
 #if TW_STATS
 __device__ unsigned long long tw_stats[128];     // per iteration: rows, live entries, candidates of the second kind, blocks with a live entry
 #endif
-constexpr int TW_NOTAG = 0xffff;
+// tag of an output of the pruned search: a1 | a2 << 8 = the two entries of the body whose candidate won (a1 == a2: a lone
+// entry), TW_SECOND | a | a << 8 = a candidate of the second kind of entry a, TW_NOTAG = the single deviation stands
+constexpr int TW_SECOND = 0x10000;
+constexpr int TW_NOTAG = 0x20000;
 // IEEE division kept out of line (one copy of the routine; the correction factor is 1 in every shipped profile)
 template <typename T> __device__ __noinline__ T div_call(T a, T b) { return a / b; }
 
@@ -228,6 +231,21 @@ template <> struct Pair2<double> {
     __device__ __forceinline__ double hi() const { return b; }
     __device__ __forceinline__ Pair2 plus(double c) const { Pair2 r; r.a = a + c; r.b = b + c; return r; }
 };
+// best = min(best, c1, c2); the tag is rewritten only when the minimum FALLS (strict: the first of equal costs stays).  fp32: one
+// FMNMX3, one FSETP, one SEL per output for two candidates.
+__device__ __forceinline__ void min_tag2(float &best, int &tag, float c1, float c2, int tg) {
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tmin.f32 t, %1, %2, %3;\n\tsetp.lt.f32 p, t, %1;\n\tselp.b32 %0, %4, %0, p;\n\tmov.f32 %1, t;\n\t}"
+        : "+r"(tag), "+f"(best) : "f"(c1), "f"(c2), "r"(tg));
+}
+__device__ __forceinline__ void min_tag2(double &best, int &tag, double c1, double c2, int tg) {
+    const double t = fmin(fmin(best, c1), c2);
+    if (t < best) tag = tg;
+    best = t;
+}
+// 16 bytes of a split-layout vector as two FADD2 operands, by 32-bit shared address
+__device__ __forceinline__ void lds_pairs(unsigned addr, Pair2<float> &p0, Pair2<float> &p1) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(p0.v), "=l"(p1.v) : "r"(addr) : "memory");
+}
 // the VEC/2 pairs of block k of a split-layout vector from shared memory (src = first piece of the block)
 template <int VEC> __device__ __forceinline__ void ld_pairs(const unsigned char *src, Pair2<float> (&p)[VEC / 2]) {
     if constexpr (VEC >= 4) {
@@ -315,11 +333,18 @@ __device__ __noinline__ TwPair<T> tw_pair_of_tag(const unsigned char *slab, int 
     const unsigned char *blk = slab + S::off_blk;
     const T *sM1 = reinterpret_cast<const T *>(slab + S::off_m1);
     const uint8_t *c01 = slab + S::off_c01;
-    const int aa = tg & 255, bb = s ^ aa, ka = c01[aa], kb = c01[bb];
+    int aa = tg & 255;
+    const int a2 = (tg >> 8) & 255;
+    if (a2 != aa) {                                                 // which entry of the body attained dw: the first one unless its candidate differs
+        const T c = *reinterpret_cast<const T *>(blk + (aa / VEC) * (int)S::blk_stride + (aa % VEC) * (int)sizeof(T)) +
+                    reinterpret_cast<const T *>(slab)[(c01[aa] & 15) * Q + (int)(sidx ^ (unsigned)PL::swz(aa))];
+        if (c != dw) aa = a2;
+    }
+    const int bb = s ^ aa, ka = c01[aa], kb = c01[bb];
     const unsigned sa = (unsigned)PL::swz(aa), sb = sidx ^ sa;          // the layout is linear over XOR
     const T m0b = *reinterpret_cast<const T *>(blk + (bb / VEC) * (int)S::blk_stride + (bb % VEC) * (int)sizeof(T));
     int ca, cb; T ua, ub;
-    if (tg < 256) {                                                 // a pays its cheapest column, b the cheapest one that is not ca
+    if (!(tg & TW_SECOND)) {                                        // a pays its cheapest column, b the cheapest one that is not ca
         ca = ka & 15;
         const bool same = (kb & 15) == ca;
         cb = same ? (kb >> 4) : (kb & 15);
@@ -552,14 +577,21 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
         for (int r = 0; r < VEC; ++r) tag[r] = TW_NOTAG;
         if (P.p1 >= 2) {
             const bool second = P.p0 >= 2;                              // n_r = 1: the second-cheapest column may not deviate
-            // The bound is refreshed before block 0, 1, 2, 4, 8 and 16: it falls fastest at the start.  (Measured alternatives: a
-            // refresh every 2 / 4 / 8 blocks -- 2.56 / 2.52 / 2.63 ms per launch against 2.44 -- and rounds of blocks in ascending
-            // order of their cheapest entry, which kept 60 entries live where this schedule keeps 49, and was slower.)
+            // TWO ROUNDS.  Round 0 takes the light entries, m0 <= U0/4 (U0 = max_s m0(s), the bound before any pair is known): they
+            // are the ones that pull the bound down.  Round 1 takes what is still live against the refreshed bound, m0 <= U1/2, and
+            // has not been handled.  Any schedule is exact as long as every entry with m0 <= U/2 for the FINAL bound U has been
+            // handled at the end (U only falls); this one keeps fewer entries live than a refresh per block range (offline on dumped
+            // rows: 51 against 68 in iteration 2, 72 against 79 later), and -- the point -- it leaves enough entries per round that
+            // they can be taken TWO AT A TIME: within a round the entries with the same position bl inside their eta-block (bl fixes
+            // the register permutation, so it must be a compile-time constant of the body) come out of one ballot, and a body
+            // handles two of them: 16 candidates by 8 FADD2, one FMNMX3 + one compare + one predicated tag write per output, where
+            // one entry at a time costs a compare and two selects per candidate.  The tag names both entries; which of the two
+            // attained the minimum is settled once per output in tw_pair_of_tag.
+            unsigned done = 0u;                                         // bit j: first kind handled, bit 8 + j: second kind handled (my block)
 #pragma unroll 1
-            for (int g0 = 0, g1; g0 < 32; g0 = g1) {
-                g1 = g0 < 2 ? g0 + 1 : 2 * g0;
-                // liveness of every entry against the current bound, one block per lane: bit j = first kind, bit 8 + j = second kind
-                const T Uh = T(0.5) * warp_max_nonneg<T>(vec_max<T, VEC>(best));
+            for (int round = 0; round < 2; ++round) {
+                const T U = warp_max_nonneg<T>(vec_max<T, VEC>(best));
+                const T th = (round == 0 ? T(0.25) : T(0.5)) * U;
                 unsigned mymask = 0u;
                 {
                     T c0v[VEC], c1v[VEC];
@@ -567,49 +599,118 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
                     ld_split<T, VEC>(sM1, lane, c1v);
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
-                        if (c0v[j] <= Uh) mymask |= 1u << j;
-                        if (second && c1v[j] <= Uh && c0v[j] <= Uh) mymask |= 256u << j;
+                        if (c0v[j] <= th) mymask |= 1u << j;
+                        if (second && c1v[j] <= th && c0v[j] <= th) mymask |= 256u << j;
                     }
                 }
-#pragma unroll 1
-                for (int bh = g0; bh < g1; ++bh) {
-                    const unsigned m = __reduce_or_sync(0xffffffffu, lane == bh ? mymask : 0u);    // warp-uniform by construction
-                    if (!m) continue;
+                mymask &= ~done; done |= mymask;
+                if constexpr (sizeof(T) == 4 && VEC == 8) {
+                    // fp32, q = 256.  Of the three bits of bl only the lower two permute registers (which pair of a 16-byte piece, which
+                    // half of the pair); bit 2 selects the PIECE, i.e. it is part of the address.  So there are four bodies (classes
+                    // bc = bl & 3), each serving both pieces, and a class has enough entries per round to fill its bodies in pairs.
+                    // The entries of a class are compacted into a list of 8-byte records {m0(a), w} first -- lane-parallel: every lane
+                    // (= eta-block) places its up to two entries by a prefix count over two ballots -- with
+                    //   w = bh << 4 | (bl >> 2) << 9 | c0(a) << 10 | a << 16:  block address of D_c0(a) = ((slab + lane * 16) ^ (w & 0x3f0)) + (w & 0xc00),
+                    // so that a body costs one broadcast LDS.128 for both records and three instructions per address.  The list lives
+                    // in the c01 area (+ the slab's spare bytes); c01 is put back from registers after the search.
+                    static_assert(S::bytes_per_warp - S::off_c01 >= 512, "the entry list needs 64 records");
+                    uint2 *list = reinterpret_cast<uint2 *>(slab + S::off_c01);
+                    const unsigned list32 = slab32 + (unsigned)S::off_c01, X = slab32 + ((unsigned)lane << 4);
+                    const unsigned lt = (1u << lane) - 1u;
+                    const unsigned mycls = *reinterpret_cast<const unsigned *>(myrec + S::blk_cls);
+#pragma unroll
+                    for (int bc = 0; bc < 4; ++bc) {
+                        const bool lA = (mymask >> bc) & 1u, lB = (mymask >> (bc + 4)) & 1u;
+                        const unsigned mA = __ballot_sync(0xffffffffu, lA), mB = __ballot_sync(0xffffffffu, lB);
+                        const int nA = __popc(mA), n = nA + __popc(mB);
+                        if (n == 0) continue;                           // warp-uniform
 #if TW_STATS
-                    if (lane == 0) { atomicAdd(tw_stats + 8 * (P.iter & 15) + 1, (unsigned long long)__popc(m & 255u)); atomicAdd(tw_stats + 8 * (P.iter & 15) + 3, 1ULL);
-                                     atomicAdd(tw_stats + 8 * (P.iter & 15) + 2, (unsigned long long)__popc(m >> 8)); }
+                        if (lane == 0) { atomicAdd(tw_stats + 8 * (P.iter & 15) + 1, (unsigned long long)n); atomicAdd(tw_stats + 8 * (P.iter & 15) + 3, (unsigned long long)((n + 1) / 2)); }
 #endif
+                        if (lA) list[__popc(mA & lt)] = make_uint2(*reinterpret_cast<const unsigned *>(myrec + bc * 4),
+                                                                   ((unsigned)lane << 4) | (((mycls >> (2 * bc)) & 3u) << 10) | ((unsigned)(VEC * lane + bc) << 16));
+                        if (lB) list[nA + __popc(mB & lt)] = make_uint2(*reinterpret_cast<const unsigned *>(myrec + (bc + 4) * 4),
+                                                                        ((unsigned)lane << 4) | 512u | (((mycls >> (2 * bc + 8)) & 3u) << 10) | ((unsigned)(VEC * lane + bc + 4) << 16));
+                        if (lane == 0 && (n & 1)) list[n] = make_uint2(__float_as_uint(INF), 0u);   // a lone last entry: its partner's candidates are +inf
+                        __syncwarp();
+#pragma unroll 1
+                        for (int i = 0; i < n; i += 2) {
+                            unsigned c1b, w1, c2b, w2;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c1b), "=r"(w1), "=r"(c2b), "=r"(w2) : "r"(list32 + 8u * (unsigned)i) : "memory");
+                            const unsigned ad1 = (X ^ (w1 & 0x3f0u)) + (w1 & 0xc00u), ad2 = (X ^ (w2 & 0x3f0u)) + (w2 & 0xc00u);
+                            const int tg = (int)__byte_perm(w1, w2, 0x3362);    // a1 | a2 << 8
+                            const float cost1 = __uint_as_float(c1b), cost2 = __uint_as_float(c2b);
+                            Pair2<float> p1[4], p2[4];                  // [0..1]: the piece that feeds outputs 0..3, [2..3]: outputs 4..7
+                            lds_pairs(ad1, p1[0], p1[1]); lds_pairs(ad1 ^ 512u, p1[2], p1[3]);
+                            lds_pairs(ad2, p2[0], p2[1]); lds_pairs(ad2 ^ 512u, p2[2], p2[3]);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { p1[k] = p1[k].plus(cost1); p2[k] = p2[k].plus(cost2); }
+#pragma unroll
+                            for (int r = 0; r < VEC; ++r) {
+                                const int j = (r & 4) | ((r ^ bc) & 3);
+                                const float c1 = (j & 1) ? p1[j >> 1].hi() : p1[j >> 1].lo();
+                                const float c2 = (j & 1) ? p2[j >> 1].hi() : p2[j >> 1].lo();
+                                min_tag2(best[r], tag[r], c1, c2, tg);
+                            }
+                        }
+                        __syncwarp();                                   // the list is rewritten by the next class
+                    }
+                } else {
+#pragma unroll
+                for (int bl = 0; bl < VEC; ++bl) {
+                    unsigned mb = __ballot_sync(0xffffffffu, (mymask >> bl) & 1u);                 // bit bh: entry VEC * bh + bl is to be handled
+#pragma unroll 1
+                    while (mb) {                                        // warp-uniform
+                        const int bh1 = __ffs((int)mb) - 1; mb &= mb - 1u;
+                        const bool two = mb != 0u;
+                        const int bh2 = two ? __ffs((int)mb) - 1 : bh1; mb &= mb - 1u;
+#if TW_STATS
+                        if (lane == 0) { atomicAdd(tw_stats + 8 * (P.iter & 15) + 1, two ? 2ULL : 1ULL); atomicAdd(tw_stats + 8 * (P.iter & 15) + 3, 1ULL); }
+#endif
+                        const unsigned char *rec1 = blk + bh1 * (int)S::blk_stride, *rec2 = blk + bh2 * (int)S::blk_stride;
+                        const T cost1 = *reinterpret_cast<const T *>(rec1 + bl * (int)sizeof(T));
+                        const T cost2r = *reinterpret_cast<const T *>(rec2 + bl * (int)sizeof(T));
+                        const T cost2 = two ? cost2r : INF;             // a lone entry: its partner's candidates are +inf
+                        const unsigned col1 = (*reinterpret_cast<const unsigned *>(rec1 + S::blk_cls) >> (2 * bl)) & 3u;
+                        const unsigned col2 = (*reinterpret_cast<const unsigned *>(rec2 + S::blk_cls) >> (2 * bl)) & 3u;
+                        const unsigned char *src1 = slab + (lane ^ bh1) * (PL::E16 * (int)sizeof(T)) + col1 * VB;
+                        const unsigned char *src2 = slab + (lane ^ bh2) * (PL::E16 * (int)sizeof(T)) + col2 * VB;
+                        const int tg = (VEC * bh1 + bl) | ((VEC * bh2 + bl) << 8);
+                        if constexpr (VEC >= 2) {
+                            Pair2<T> p1[VEC / 2], p2[VEC / 2];
+                            ld_pairs<VEC>(src1, p1);
+                            ld_pairs<VEC>(src2, p2);
+#pragma unroll
+                            for (int i = 0; i < VEC / 2; ++i) { p1[i] = p1[i].plus(cost1); p2[i] = p2[i].plus(cost2); }
+#pragma unroll
+                            for (int r = 0; r < VEC; ++r) {
+                                const int j = r ^ bl;
+                                const T c1 = (j & 1) ? p1[j >> 1].hi() : p1[j >> 1].lo();
+                                const T c2 = (j & 1) ? p2[j >> 1].hi() : p2[j >> 1].lo();
+                                min_tag2(best[r], tag[r], c1, c2, tg);
+                            }
+                        } else {
+                            const T c1 = *reinterpret_cast<const T *>(src1) + cost1, c2 = *reinterpret_cast<const T *>(src2) + cost2;
+                            min_tag2(best[0], tag[0], c1, c2, tg);
+                        }
+                    }
+                }
+                }
+                // second kind (rare): ONE copy of the code for any entry; the tile is brought into the order of the lane's outputs
+                // by three conditional exchange steps (index j = r ^ bl)
+                unsigned b2 = __ballot_sync(0xffffffffu, (mymask >> 8) != 0u);
+#pragma unroll 1
+                while (b2) {
+                    const int bh = __ffs((int)b2) - 1; b2 &= b2 - 1u;
                     const unsigned char *rec = blk + bh * (int)S::blk_stride;
                     const unsigned cls = *reinterpret_cast<const unsigned *>(rec + S::blk_cls);
                     const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
-#pragma unroll
-                    for (int bl = 0; bl < VEC; ++bl) {
-                        if (m & (1u << bl)) {                           // first kind: m0(a) + D_{c0(a)}[s ^ a]
-                            const T cost = *reinterpret_cast<const T *>(rec + bl * (int)sizeof(T));
-                            const unsigned char *src = Dk + ((cls >> (2 * bl)) & 3u) * VB;
-                            const int a = VEC * bh + bl;
-                            if constexpr (VEC >= 2) {
-                                Pair2<T> p[VEC / 2], q[VEC / 2];
-                                ld_pairs<VEC>(src, p);
-#pragma unroll
-                                for (int i = 0; i < VEC / 2; ++i) q[i] = p[i].plus(cost);
-#pragma unroll
-                                for (int r = 0; r < VEC; ++r) {
-                                    const int j = r ^ bl;
-                                    const T cand = (j & 1) ? q[j >> 1].hi() : q[j >> 1].lo();
-                                    if (cand < best[r]) { best[r] = cand; tag[r] = a; }
-                                }
-                            } else {
-                                const T cand = *reinterpret_cast<const T *>(src) + cost;
-                                if (cand < best[0]) { best[0] = cand; tag[0] = a; }
-                            }
-                        }
-                    }
-                    // second kind (rare): ONE copy of the code for any entry; the tile is brought into the order of the lane's outputs
-                    // by three conditional exchange steps (index j = r ^ bl)
-                    for (unsigned m2 = m >> 8; m2; m2 &= m2 - 1u) {
+                    for (unsigned m2 = __shfl_sync(0xffffffffu, mymask, bh) >> 8; m2; m2 &= m2 - 1u) {
                         const int bl = __ffs((int)m2) - 1, a = VEC * bh + bl;
-                        const T m1a = sM1[PL::index(bh, bl)];
+#if TW_STATS
+                        if (lane == 0) atomicAdd(tw_stats + 8 * (P.iter & 15) + 2, 1ULL);
+#endif
+                        const T m1a = sM1[PL::index_rt(bh, bl)];
                         const unsigned c = (cls >> (2 * bl)) & 3u;
                         T dc[VEC], dx[VEC], cand[VEC];                  // D_c and D of another column of the row (degree >= 2: column
                         ld_split_bytes<T, VEC>(Dk + c * VB, dc);        // 0 or 1 exists) differ exactly where c0(y) == c
@@ -624,13 +725,17 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
                                 if (!(j & bit)) { const T lo = cand[j], hi = cand[j | bit]; cand[j] = sw ? hi : lo; cand[j | bit] = sw ? lo : hi; }
                         }
 #pragma unroll
-                        for (int r = 0; r < VEC; ++r) if (cand[r] < best[r]) { best[r] = cand[r]; tag[r] = 256 + a; }
+                        for (int r = 0; r < VEC; ++r) if (cand[r] < best[r]) { best[r] = cand[r]; tag[r] = TW_SECOND | a | (a << 8); }
                     }
                 }
             }
 #if TW_STATS
             if (lane == 0) atomicAdd(tw_stats + 8 * (P.iter & 15), 1ULL);
 #endif
+        }
+        if constexpr (sizeof(T) == 4 && VEC == 8) {                    // the entry list of the search lay over c01
+            st_bytes<VEC>(c01 + x0, c01w);
+            __syncwarp();
         }
         // ---- the recorded path of each owned s, straight from the tag (tw_pair_of_tag: one out-of-line copy of the code for the
         //      lane's VEC outputs -- the kernel must stay inside the instruction cache), and the output trellis (NBLDPC.cpp:1084-1094):
