@@ -41,16 +41,17 @@ namespace nbl {
 
 constexpr int TW_DC = 4;      // maximum check degree served by the fast path
 #ifndef TW_WARPS_VALUE
-#define TW_WARPS_VALUE 4
+#define TW_WARPS_VALUE 2
 #endif
 constexpr int TW_WARPS = TW_WARPS_VALUE;   // warps (= check rows) per CTA
 constexpr int TW_DSC = 8;     // ints per edge in the row descriptor: variable, degree, up to 5 edge ids, 1 spare
                               // (spare of edge 0 = first edge id of the row, spare of edge 1 = row degree)
 constexpr int TW_HOIST = 2;   // messages of a variable fetched ahead (its degree may be larger: slow loop)
 #ifndef TW_MIN_CTAS_VALUE
-#define TW_MIN_CTAS_VALUE 6
+#define TW_MIN_CTAS_VALUE 5
 #endif
-constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident CTAs per SM the register allocation aims for (6 x 4 warps at 80 registers: measured +2.7 % over 5 x 4 at 96; 7 spills)
+constexpr int TW_MIN_CTAS = TW_MIN_CTAS_VALUE;   // resident groups of 4 warps per SM the register allocation aims for (round 2, two-at-a-time search: 5 at 96 registers
+                                                 // = 6 at 80 + 3 %; CTAs of 2 warps instead of 4: + 1.5 %)
 #ifndef TW_MINB_VALUE
 #define TW_MINB_VALUE (TW_MIN_CTAS * 4 / TW_WARPS)
 #endif
@@ -170,6 +171,15 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) {
     return (int)((h >> (8 * (i & 3))) & 255u);
 }
 
+#ifndef TW_TH0
+#define TW_TH0 0.2       // round 0 of the pair search takes the entries with m0 <= TW_TH0 * U0
+#endif
+#ifndef TW_ROUNDS
+#define TW_ROUNDS 2
+#endif
+#ifndef TW_TH1
+#define TW_TH1 0.3
+#endif
 #ifndef TW_STATS
 #define TW_STATS 0
 #endif
@@ -366,7 +376,7 @@ __device__ __noinline__ TwPair<T> tw_pair_of_tag(const unsigned char *slab, int 
 // BS == 1: BS-TEMS (decode method 7) -- same variable-node step, delta domain, column order, fill-in and output stage; the
 // pair search is replaced by the basic-set construction and the walk over its subsets (see the BS block below).
 template <typename T, int Q, int DC, int DV, int BS = 0>
-__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_MINB_VALUE) : 1) k_iterate_tems_warp(const IterParams<T> P) {
+__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / TW_WARPS : TW_MINB_VALUE) : 1) k_iterate_tems_warp(const IterParams<T> P) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
     using S = TwSmem<T, Q>;
@@ -577,7 +587,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
         for (int r = 0; r < VEC; ++r) tag[r] = TW_NOTAG;
         if (P.p1 >= 2) {
             const bool second = P.p0 >= 2;                              // n_r = 1: the second-cheapest column may not deviate
-            // TWO ROUNDS.  Round 0 takes the light entries, m0 <= U0/4 (U0 = max_s m0(s), the bound before any pair is known): they
+            // TWO ROUNDS.  Round 0 takes the light entries, m0 <= U0/5 (U0 = max_s m0(s), the bound before any pair is known): they
             // are the ones that pull the bound down.  Round 1 takes what is still live against the refreshed bound, m0 <= U1/2, and
             // has not been handled.  Any schedule is exact as long as every entry with m0 <= U/2 for the FINAL bound U has been
             // handled at the end (U only falls); this one keeps fewer entries live than a refresh per block range (offline on dumped
@@ -589,9 +599,11 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 : TW_M
             // attained the minimum is settled once per output in tw_pair_of_tag.
             unsigned done = 0u;                                         // bit j: first kind handled, bit 8 + j: second kind handled (my block)
 #pragma unroll 1
-            for (int round = 0; round < 2; ++round) {
+            T U0 = T(0);
+            for (int round = 0; round < TW_ROUNDS; ++round) {
                 const T U = warp_max_nonneg<T>(vec_max<T, VEC>(best));
-                const T th = (round == 0 ? T(0.25) : T(0.5)) * U;
+                if (round == 0) U0 = U;
+                const T th = round == TW_ROUNDS - 1 ? T(0.5) * U : round == 0 ? T(TW_TH0) * U : fmin(T(0.5) * U, T(TW_TH1) * U0);
                 unsigned mymask = 0u;
                 {
                     T c0v[VEC], c1v[VEC];
