@@ -15,11 +15,19 @@ ap.add_argument("--file", default="tems_warp.cuh")
 ap.add_argument("--ranges", default="")
 ap.add_argument("--inner", action="store_true", help="break each line down by the innermost line of the chain")
 ap.add_argument("--opmix", default="", help="LO-HI: dynamic opcode mix (per row) of the instructions of these lines")
+ap.add_argument("--kernel", default="", help="substring of the mangled kernel name: take only that .text section of a multi-kernel cubin")
 a = ap.parse_args()
 
-txt = subprocess.run(["nvdisasm", "-gi", "-c", a.cubin], capture_output=True, text=True).stdout
+txt = subprocess.run(["nvdisasm", "-gi", "-c", a.cubin], capture_output=True, text=True).stdout.splitlines()
+if a.kernel:
+    sel = []; on = False
+    for l in txt:
+        if re.match(r"\s*\.section\s+\.text\.", l): on = a.kernel in l
+        elif re.match(r"\s*\.section\s", l): on = False
+        if on: sel.append(l)
+    txt = sel
 keys = []; chain = []; fresh = True
-for l in txt.splitlines():
+for l in txt:
     if "//##" in l:
         if fresh: chain = []; fresh = False
         for m in re.finditer(r'"([^"]+)", line (\d+)', l):
