@@ -605,9 +605,10 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
                 if (round == 0) U0 = U;
                 const T th = round == TW_ROUNDS - 1 ? T(0.5) * U : round == 0 ? T(TW_TH0) * U : fmin(T(0.5) * U, T(TW_TH1) * U0);
                 unsigned mymask = 0u;
+                T c0v[VEC];                                             // m0 of my block's entries (kept for the entry list)
+                ld_vec<T, VEC>(reinterpret_cast<const T *>(myrec), c0v);                           // +inf at eta = 0: never live
                 {
-                    T c0v[VEC], c1v[VEC];
-                    ld_vec<T, VEC>(reinterpret_cast<const T *>(myrec), c0v);                       // +inf at eta = 0: never live
+                    T c1v[VEC];
                     ld_split<T, VEC>(sM1, lane, c1v);
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) {
@@ -639,9 +640,9 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
 #if TW_STATS
                         if (lane == 0) { atomicAdd(tw_stats + 8 * (P.iter & 15) + 1, (unsigned long long)n); atomicAdd(tw_stats + 8 * (P.iter & 15) + 3, (unsigned long long)((n + 1) / 2)); }
 #endif
-                        if (lA) list[__popc(mA & lt)] = make_uint2(*reinterpret_cast<const unsigned *>(myrec + bc * 4),
+                        if (lA) list[__popc(mA & lt)] = make_uint2(__float_as_uint(c0v[bc]),
                                                                    ((unsigned)lane << 4) | (((mycls >> (2 * bc)) & 3u) << 10) | ((unsigned)(VEC * lane + bc) << 16));
-                        if (lB) list[nA + __popc(mB & lt)] = make_uint2(*reinterpret_cast<const unsigned *>(myrec + (bc + 4) * 4),
+                        if (lB) list[nA + __popc(mB & lt)] = make_uint2(__float_as_uint(c0v[bc + 4]),
                                                                         ((unsigned)lane << 4) | 512u | (((mycls >> (2 * bc + 8)) & 3u) << 10) | ((unsigned)(VEC * lane + bc + 4) << 16));
                         if (lane == 0 && (n & 1)) list[n] = make_uint2(__float_as_uint(INF), 0u);   // a lone last entry: its partner's candidates are +inf
                         __syncwarp();
