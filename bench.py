@@ -195,7 +195,7 @@ def main_reference(args):
                        "host": "%d threads of %s" % (threads, cpu_model())},
             "cpu_baseline": {"value": value, "unit": "Mbit/s", "cores": threads, "kind": last["kind"], "cpu_model": cpu_model(), "sample": last["sample"]},
             "e2e": {"value": value, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     return 0
 
 
@@ -431,7 +431,7 @@ def main_ours(args):
         if cb:
             line["cpu_baseline"] = cb
             line["reference_like_for_like"]["cpu_reference"] = cb["value"]
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -449,4 +449,12 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
     a = ap.parse_args()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
+    # stdout carries the JSON line and nothing else: whatever a library writes to file descriptor 1 while the bench runs (NCCL's
+    # version banner, when the box presets NCCL_DEBUG) is sent to stderr; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _emit = lambda text: (_real_stdout.write(text + "\n"), _real_stdout.flush())
+    rc = main_reference(a) if a.impl == "reference" else main_ours(a)
+    sys.stdout.flush()
+    sys.exit(rc)
