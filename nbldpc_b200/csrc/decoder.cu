@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 using namespace nbl;
@@ -241,6 +242,11 @@ __global__ void k_demap_qam(int B, int N, int q, int ylen, const double *__restr
 // host side
 // ======================================================================================================
 struct nbl_decoder {
+    // small batches (the reference's per-frame call shape, B = 1): the launch sequence of one decode is captured once per
+    // (batch size, posterior wanted, arithmetic) and replayed as ONE graph launch -- 27 kernel launches cost more than the
+    // kernels themselves there.  Dropped when the OSD set-up changes.
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int> graph_launches;
     const nbl_code *code = nullptr;
     nbl_decoder_config cfg{};
     cudaStream_t stream = nullptr;
@@ -330,6 +336,7 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
                     d->d_c2v[0], d->d_c2v[1], d->d_vdec, d->d_dec, d->d_done, d->d_newly, d->d_flag, d->d_iters, d->d_conv,
                     d->d_out, d->d_active, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg, d->d_osd_H0, d->d_osd_sum, d->d_osd_status, d->d_rowdesc8};
     if (d->sim_enc) nbl_encoder_destroy(d->sim_enc);
+    for (auto &kv : d->graphs) cudaGraphExecDestroy(kv.second);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : d->it_ev) if (e) cudaEventDestroy(e);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -669,7 +676,41 @@ template <typename T, int Q> static int launch_posterior_tq(nbl_decoder *d, int 
 
 // Runs the iterations on the frames whose channel LLRs are already in d_lch.  Results stay on the device
 // (d_out, d_conv, d_iters); post_dev (device doubles) is optional.
+template <typename T> static int enqueue_decode(nbl_decoder *d, int B, double *post_dev, bool timed);
+constexpr int NBL_GRAPH_MAX_B = 64;       // batches up to this size go through a captured graph
+
+static void drop_graphs(nbl_decoder *d) {
+    for (auto &kv : d->graphs) cudaGraphExecDestroy(kv.second);
+    d->graphs.clear(); d->graph_launches.clear();
+}
+
 template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_dev) {
+    if (B > NBL_GRAPH_MAX_B) return enqueue_decode<T>(d, B, post_dev, true);
+    const int key = (B << 2) | (post_dev ? 1 : 0) | (sizeof(T) == 8 ? 2 : 0);
+    auto it = d->graphs.find(key);
+    if (it == d->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_decode<T>(d, B, post_dev, false);
+        const cudaError_t e = cudaStreamEndCapture(d->stream, &graph);
+        if (rc != NBL_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+        if (e != cudaSuccess || !graph) { nbl_set_error(std::string("stream capture of the decode failed: ") + cudaGetErrorString(e)); cudaGetLastError(); return NBL_ERR_CUDA; }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { nbl_set_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ei)); return NBL_ERR_CUDA; }
+        it = d->graphs.emplace(key, exec).first;
+        d->graph_launches[key] = d->last_launches;
+    }
+    d->last_launches = d->graph_launches[key]; d->it_recorded = 0;     // kernels inside the graph; per-iteration events are not recorded
+    CK(cudaEventRecord(d->ev0, d->stream));
+    CK(cudaGraphLaunch(it->second, d->stream));
+    CK(cudaEventRecord(d->ev1, d->stream));
+    d->timing_pending = true;
+    return NBL_OK;
+}
+
+template <typename T> static int enqueue_decode(nbl_decoder *d, int B, double *post_dev, bool timed) {
     const nbl_decoder_config &c = d->cfg;
     const int q = d->g.q;
     d->last_launches = 0; d->it_recorded = 0;
@@ -678,7 +719,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
     CK(cudaMemsetAsync(d->d_active, 0, (size_t)c.max_iter * sizeof(int), d->stream));
     const bool osd_acc = d->osd_on && d->osd.order >= 0 && !d->osd.flag;
     if (osd_acc) CK(cudaMemsetAsync(d->d_osd_sum, 0, (size_t)B * d->osd.nbit * sizeof(double), d->stream));
-    CK(cudaEventRecord(d->ev0, d->stream));
+    if (timed) CK(cudaEventRecord(d->ev0, d->stream));
     T w_old = 0, w_new = 1;
     if (c.method == NBL_METHOD_QSPA) { w_old = (T)0.5; w_new = (T)0.5; }          // NBLDPC.cpp:739
     if (c.method == NBL_METHOD_TEMS || c.method == NBL_METHOD_BSTEMS) { w_old = (T)0.25; w_new = (T)0.75; }   // NBLDPC.cpp:1046, 1262
@@ -699,11 +740,10 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
             P.lch = (const T *)d->d_lch; P.v2c = (T *)d->d_v2c; P.c2v_in = cin; P.c2v_out = cout;
             P.vdec = d->d_vdec; P.dec = d->d_dec; P.flag = d->d_flag; P.done = d->d_done;
             P.pfwd_sw = d->d_pfwd_sw; P.pinv_sw = d->d_pinv_sw;
-            CK(cudaEventRecord(d->it_ev[2 * (it - 1)], d->stream));
+            if (timed) CK(cudaEventRecord(d->it_ev[2 * (it - 1)], d->stream));
             DISPATCH_Q(q, rc = (launch_iterate_tq<T, QQ>(d, P)));
             if (rc) return rc;
-            CK(cudaEventRecord(d->it_ev[2 * (it - 1) + 1], d->stream));
-            d->it_recorded = it;
+            if (timed) { CK(cudaEventRecord(d->it_ev[2 * (it - 1) + 1], d->stream)); d->it_recorded = it; }
             d->last_launches += 1;
         } else {      // last iteration: the reference's final check-node pass cannot change any output
             DISPATCH_Q(q, rc = (launch_posterior_tq<T, QQ>(d, B, it == 1, cin, nullptr, nullptr)));
@@ -727,8 +767,7 @@ template <typename T> static int run_decode(nbl_decoder *d, int B, double *post_
         CK(cudaGetLastError());
         d->last_launches += 1;
     }
-    CK(cudaEventRecord(d->ev1, d->stream));
-    d->timing_pending = true;
+    if (timed) { CK(cudaEventRecord(d->ev1, d->stream)); d->timing_pending = true; }
     return NBL_OK;
 }
 
@@ -760,6 +799,7 @@ static std::vector<std::vector<uint8_t>> osd_crc_rows(int kbit, int crc_len, int
 
 extern "C" int nbl_decoder_enable_osd(nbl_decoder *d, const nbl_osd_config *cfg) {
     if (!d || !cfg) { nbl_set_error("nbl_decoder_enable_osd: null argument"); return NBL_ERR_ARG; }
+    drop_graphs(d);                                                 // the captured launch sequences depend on the OSD set-up
     if (cfg->order < 0) { d->osd_on = false; return NBL_OK; }
     if (cfg->order > 3) { nbl_set_error("OSD order must be 0..3"); return NBL_ERR_ARG; }
     if (cfg->crc_len != 8 && cfg->crc_len != 16 && cfg->crc_len != 24) {
