@@ -186,3 +186,27 @@ def test_fp32_and_fp64_agree_on_the_same_frames(code_files):
     assert a[0] == b[0] == 4 * B
     assert b[1] > 300                                              # the point is not trivial
     assert abs(int(a[1]) - int(b[1])) <= 2 and abs(int(a[2]) - int(b[2])) <= 20 and abs(int(a[6]) - int(b[6])) <= 20, (a, b)
+
+
+@pytest.mark.parametrize("precision_name", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["cfg3_tems_gf256", "cfg2_ems_gf64", "cfg1_qspa_gf16"])
+def test_graph_replay_and_direct_launches_agree(name, precision_name, code_files):
+    """Batches of up to 64 frames replay a captured CUDA graph of the decode, larger ones launch kernel by kernel: the same
+    frames through both paths (and through the replayed graph a second and third time) give identical outputs, posteriors
+    bit for bit."""
+    from nbldpc_b200 import capi
+    if name not in golden_names():
+        pytest.skip("fixture not present")
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    lch = golden_lch(z, meta)[:8]
+    prec = capi.PREC_F64 if precision_name == "f64" else capi.PREC_F32
+    big = np.concatenate([lch] * 9)                                  # 72 frames > 64: direct launches
+    dec = _decoder(code, meta, prec, len(big))
+    direct = dec.decode(big, want_post=True)
+    runs = [dec.decode(lch, want_post=True) for _ in range(3)]       # capture + replay, replay, replay
+    for r in runs:
+        for k in ("sym", "converged", "iterations"):
+            assert np.array_equal(r[k], direct[k][:8]) and np.array_equal(r[k], direct[k][64:72])
+        assert np.array_equal(r["post"], direct["post"][:8])
+    assert dec.decode(lch[:1])["iterations"][0] == direct["iterations"][0]      # another batch size: another graph
