@@ -142,13 +142,30 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
         // SortLLRVector, first n_m places: descending, ties -> larger symbol first.  Only place 0 and the SET of the other
         // n_m - 1 entries matter downstream (a maximum over all combinations), so the r-th winner simply stays in lane r
         // until the list is written once, with its syndrome h * symbol and its address offset in B.
+        K rk = K(0); int rs = 0;
+        if constexpr (VEC == 2) {
+            // two elements per lane (q = 64): the lane keeps them ORDERED (hi first; equal keys: the larger symbol first), so a
+            // round is one REDUX over the hi keys, a vote for the highest lane holding the maximum, one shuffle for its symbol,
+            // and in that lane "lo moves up"
+            const K k0 = order_key(vnew[0]), k1 = order_key(vnew[1]);
+            const bool up = k1 >= k0;
+            K hi = up ? k1 : k0, lo = up ? k0 : k1;
+            int xhi = x0 + (up ? 1 : 0), xlo = x0 + (up ? 0 : 1);
+#pragma unroll 1
+            for (int r = 0; r < nm; ++r) {
+                K kmax; int src;
+                warp_argmax<false>(hi, FULL, kmax, src);                                   // highest lane among ties
+                const int xw = __shfl_sync(FULL, xhi, src);
+                if (lane == src) { hi = lo; xhi = xlo; lo = K(0); }                         // taken
+                if (lane == r) { rk = kmax; rs = xw; }
+            }
+        } else {
         K key[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) key[j] = order_key(vnew[j]);
         K lk = key[0];
 #pragma unroll
         for (int j = 1; j < VEC; ++j) lk = key[j] >= lk ? key[j] : lk;
-        K rk = K(0); int rs = 0;
 #pragma unroll 1
         for (int r = 0; r < nm; ++r) {
             K kmax; int src;
@@ -165,6 +182,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
                 for (int j = 1; j < VEC; ++j) lk = key[j] >= lk ? key[j] : lk;
             }
             if (lane == r) { rk = kmax; rs = xw; }
+        }
         }
         if (lane < nm) {
             const int sy = g.pfwd[(size_t)e * Q + rs];
@@ -277,9 +295,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
                 __syncwarp();
                 const unsigned X = slab32 + (unsigned)S::off_b + 8u * (unsigned)lane;
                 const int *lo = skof + ol * EW_MAXNM;
-#pragma unroll 1
-                for (int k = 0; k < nm; k += 2) {
-                    const bool two = k + 1 < nm;
+                auto pair = [&](int k, bool two) {
                     const T v0 = lv[k], v1 = two ? lv[k + 1] : -Real<T>::inf();
                     Pair2<float> pa, pb;
                     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(pa.v) : "r"(X ^ (unsigned)lo[k]) : "memory");
@@ -287,7 +303,15 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_ems_warp(const IterPa
                     pa = pa.plus(v0); pb = pb.plus(v1);
                     b2[0] = max3(b2[0], pa.lo(), pb.lo());
                     b2[1] = max3(b2[1], pa.hi(), pb.hi());
+                };
+                int k = 0;
+#pragma unroll 1
+                for (; k + 8 <= nm; k += 8) {                       // n_m = 8, 16: four pairs per trip, list offsets as immediates
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) pair(k + 2 * kk, true);
                 }
+#pragma unroll 1
+                for (; k < nm; k += 2) pair(k, k + 1 < nm);
             } else {
                 __syncwarp();
 #pragma unroll 1
