@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 6 : 2) k_itera
     // my four points of edge d live at sF + d * QH_ROWS * 16 as two 16-byte pieces, piece h of all lanes contiguous (only this lane
     // ever reads them back): 128-bit accesses without bank conflicts (a lane's 32 bytes in one run are a 2-way conflict)
     double *sF = reinterpret_cast<double *>(slab) + 2 * lane;
-    double *sR = reinterpret_cast<double *>(slab + QhQspaSmem<T>::f_bytes_per_edge * g.max_dc) + R.rw * 16;
+    T *sY = reinterpret_cast<T *>(slab + QhQspaSmem<T>::f_bytes_per_edge * g.max_dc) + R.rw * 16;   // one output vector of my row, message type
     T *sV = reinterpret_cast<T *>(slab + QhQspaSmem<T>::f_bytes_per_edge * g.max_dc + QhQspaSmem<T>::r_bytes) + R.rw * 16;
     const int *rd = desc + (size_t)R.row * (QH_MAXDC * QH_DSC);
     const T *lchf = P.lch + (size_t)f * g.N * Q + x0;
@@ -373,18 +373,19 @@ __global__ void __launch_bounds__(32 * QH_WARPS, sizeof(T) == 4 ? 6 : 2) k_itera
         }
         const unsigned tfw = d < dcn ? *reinterpret_cast<const unsigned *>(g.pfwd + (size_t)(e0 + d) * Q + x0) : 0u;
         qh_wht(r, l4);
-        qh_store4<double>(sR + x0, r);
-        __syncwarp();
-        // floor at the fp64 noise of the transform (see cn_qspa.cuh), log, un-permute
-        const double tot = sR[0];
+        // floor at the fp64 noise of the transform (see cn_qspa.cuh) and log on the lane's OWN points -- an elementwise map
+        // commutes with the un-permutation, so what goes through shared memory for the gather is already in the message type
+        const double tot = __shfl_sync(0xffffffffu, r[0], lane & ~3);     // point 0 of my row
         const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
         const double lt = qspa_log<T>(tot > fl ? tot : fl);
+        T y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = (T)(qspa_log<T>(r[i] > fl ? r[i] : fl) - lt);
+        qh_store4<T>(sY + x0, y);
+        __syncwarp();
         T out[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double a = sR[(tfw >> (8 * i)) & 255u];
-            out[i] = (T)(qspa_log<T>(a > fl ? a : fl) - lt);
-        }
+        for (int i = 0; i < 4; ++i) out[i] = sY[(tfw >> (8 * i)) & 255u];
         __syncwarp();
         if (l4 == 0) out[0] = T(0);
         if (d < dcn) qh_store4<T>(coutf + (size_t)(e0 + d) * Q, out);

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_qspa_warp(const IterP
 
     unsigned char *slab = smem_raw + S::bytes_per_warp * warp;
     T *V = reinterpret_cast<T *>(slab);
-    double *R = reinterpret_cast<double *>(slab);                  // reuses V once every input is transformed
+    T *Rv = reinterpret_cast<T *>(slab);                           // one output vector for the un-permutation gather; reuses V once every input is transformed
     double *Fs = reinterpret_cast<double *>(slab + S::off_f);
     const unsigned slab32 = smem_u32(slab);
 
@@ -185,23 +185,24 @@ __global__ void __launch_bounds__(32 * TW_WARPS) k_iterate_qspa_warp(const IterP
             for (int j = 0; j < VEC; ++j) r[j] *= Fl[j];
         }
         warp_wht<VEC>(r, lane);
-        __syncwarp();                                               // the previous output's gathers are done
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) R[x0 + j] = r[j];
-        __syncwarp();
-        // floor at the fp64 noise of the transform (see cn_qspa.cuh), log, un-permute
-        const double tot = R[0];
+        // floor at the fp64 noise of the transform (see cn_qspa.cuh) and log on the lane's OWN points -- an elementwise map
+        // commutes with the un-permutation, so the vector that goes through shared memory for the gather x -> h_d x is already
+        // in the message type (fp32 mode: half the stores and half the gather traffic of the fp64 vector)
+        const double tot = __shfl_sync(0xffffffffu, r[0], 0);
         const double fl = fabs(tot) * 1.1102230246251565e-16 + 1e-300;
         const double lt = qspa_log<T>(tot > fl ? tot : fl);
+        T y[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) y[j] = (T)(qspa_log<T>(r[j] > fl ? r[j] : fl) - lt);
+        __syncwarp();                                               // the previous output's gathers are done
+        st_vec<T, VEC>(Rv + x0, y);
+        __syncwarp();
         unsigned long long tf = 0;
 #pragma unroll
         for (int m = 0; m < TW_DC; ++m) if (m == d) tf = tfw[m];
         T out[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const double a = R[byte_of(tf, j)];
-            out[j] = (T)(qspa_log<T>(a > fl ? a : fl) - lt);
-        }
+        for (int j = 0; j < VEC; ++j) out[j] = Rv[byte_of(tf, j)];
         if (lane == 0) out[0] = T(0);
         st_vec<T, VEC>(coutf + (size_t)(e0 + d) * Q, out);
     }
