@@ -277,6 +277,7 @@ struct nbl_decoder {
     bool warp_path = false;      // T-EMS n_c <= 2 or BS-TEMS, dc <= 4, q >= 32: one warp per check row (tems_warp.cuh)
     bool qspa_warp_path = false; // QSPA, dc <= 4, q >= 32: one warp per check row (qspa_warp.cuh)
     bool ems_warp_path = false;  // EMS, n_m a power of two, n_m^(dc-1) <= EW_MAXCOMBOS, dc <= 4, q >= 32: one warp per check row (ems_warp.cuh)
+    bool warp_ref = false;       // the T-EMS warp kernel records the configuration the reference's enumeration meets first (tie_mode REFERENCE)
     bool warp_regular = false;   // every check row has TW_DC edges and every variable TW_HOIST: degree guards compiled out
     bool ems_half_path = false;  // EMS over GF(16), dc <= 8, dv <= 4, n_m <= 16, n_c <= 3 (ems_half.cuh)
     bool tems_half_path = false; // T-EMS n_c <= 2 over GF(16), dc <= 8, dv <= 4, not the reference tie order (tems_half.cuh)
@@ -450,6 +451,10 @@ extern "C" int nbl_decoder_create(nbl_decoder **out, const nbl_code *code, const
     if (cfg->tie_mode < NBL_TIES_AUTO || cfg->tie_mode > NBL_TIES_BITEXACT) { nbl_set_error("nbl_decoder_create: bad tie_mode"); return fail(NBL_ERR_ARG); }
     const bool ref_ties = cfg->tie_mode == NBL_TIES_REFERENCE || cfg->tie_mode == NBL_TIES_BITEXACT || (cfg->tie_mode == NBL_TIES_AUTO && cfg->precision == NBL_PREC_F64);
     d->warp_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && !ref_ties && fast_ok;
+    // the reference's tie order on the same kernel (a second pass over the handled entries records the configuration the reference's
+    // enumeration meets first, tems_warp.cuh); n_r >= 3 (a third column can tie) and the bit-exact replay stay on the group kernel
+    if (cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && cfg->p0 <= 2 && desc_ok && q >= 32 && cfg->offset >= 0.0 && ref_ties &&
+        cfg->tie_mode != NBL_TIES_BITEXACT && fast_ok) { d->warp_path = true; d->warp_ref = true; }
     d->tems_half_path = cfg->method == NBL_METHOD_TEMS && cfg->p1 <= 2 && q == 16 && d->d_rowdesc8 != nullptr && !ref_ties;
     if (cfg->method == NBL_METHOD_BSTEMS && q == 16 && d->d_rowdesc8 != nullptr) d->tems_half_path = true;      // the same kernel with BS = 1
     d->ems_half_path = cfg->method == NBL_METHOD_EMS && q == 16 && d->d_rowdesc8 != nullptr && cfg->p0 <= EH_MAXNM && cfg->p1 + 1 <= EH_MAXNJ;
@@ -564,6 +569,8 @@ template <typename T, int Q> static int launch_iterate_warp(nbl_decoder *d, cons
     if constexpr (Q >= 32) {
         if (d->cfg.method == NBL_METHOD_BSTEMS)
             return d->warp_regular ? launch_iterate_warp_dc<T, Q, TW_DC, TW_HOIST, 1>(d, P) : launch_iterate_warp_dc<T, Q, 0, 0, 1>(d, P);
+        if (d->warp_ref)
+            return d->warp_regular ? launch_iterate_warp_dc<T, Q, TW_DC, TW_HOIST, 2>(d, P) : launch_iterate_warp_dc<T, Q, 0, 0, 2>(d, P);
         return d->warp_regular ? launch_iterate_warp_dc<T, Q, TW_DC, TW_HOIST>(d, P) : launch_iterate_warp_dc<T, Q, 0, 0>(d, P);
     } else {
         nbl_set_error("internal: warp path needs q >= 32");

@@ -371,12 +371,49 @@ __device__ __noinline__ TwPair<T> tw_pair_of_tag(const unsigned char *slab, int 
     return out;
 }
 
+// Rank of a configuration in the reference's depth-first enumeration (smaller = met earlier): first deviating column fc (later
+// is earlier), its eta fv (ascending), second deviating column sc (4 = none, which comes first; else later is earlier), its eta.
+__device__ __forceinline__ unsigned tw_key(int fc, int fv, int sc, int sv) {
+    return ((unsigned)(3 - fc) << 19) | ((unsigned)fv << 11) | ((unsigned)(4 - sc) << 8) | (unsigned)sv;
+}
+// All column assignments of the pair {a, b = s ^ a} whose cost equals dw exactly; the one the reference records.  key = ~0: none.
+template <typename T> struct TwRef { unsigned key, path; T va, vb; };
+template <typename T, int Q>
+__device__ __noinline__ TwRef<T> tw_ref_pair(const unsigned char *slab, int a, int s, unsigned sidx, T dw, bool second) {
+    constexpr int VEC = Q / 32;
+    using PL = PLayout<T, VEC>;
+    using S = TwSmem<T, Q>;
+    const unsigned char *blk = slab + S::off_blk;
+    const T *sM1 = reinterpret_cast<const T *>(slab + S::off_m1);
+    const uint8_t *c01 = slab + S::off_c01;
+    const int b = s ^ a, ka = c01[a], kb = c01[b];
+    const unsigned sa = (unsigned)PL::swz(a), sb = sidx ^ sa;           // the layout is linear over XOR
+    const T ua[2] = {*reinterpret_cast<const T *>(blk + (a / VEC) * (int)S::blk_stride + (a % VEC) * (int)sizeof(T)), sM1[sa]};
+    const T ub[2] = {*reinterpret_cast<const T *>(blk + (b / VEC) * (int)S::blk_stride + (b % VEC) * (int)sizeof(T)), sM1[sb]};
+    TwRef<T> out; out.key = 0xffffffffu; out.path = 0u; out.va = T(0); out.vb = T(0);
+    if (b == 0) return out;
+    const int lim = second ? 2 : 1;
+    for (int i = 0; i < lim; ++i)
+        for (int j = 0; j < lim; ++j) {
+            const int ca = i ? (ka >> 4) : (ka & 15), cb = j ? (kb >> 4) : (kb & 15);
+            if (ca == cb || !(ua[i] + ub[j] == dw)) continue;
+            const unsigned key = ca < cb ? tw_key(ca, a, cb, b) : tw_key(cb, b, ca, a);
+            if (key < out.key) {
+                out.key = key;
+                out.path = sb | (sa << 8) | ((unsigned)ca << 16) | ((unsigned)cb << 18) | (0x100000u << ca) | (0x100000u << cb) | (1u << 24);
+                out.va = dw - ua[i]; out.vb = dw - ub[j];
+            }
+        }
+    return out;
+}
+
 // DC > 0: every check row has exactly DC edges (no degree guards in the unrolled stages); DC == 0: row degree from the
 // descriptor.  DV > 0: every variable has exactly DV <= TW_HOIST edges; DV == 0: variable degree from the descriptor.
+// BS == 2: T-EMS with the reference's tie order among configurations of equal cost (second pass after the search, see there).
 // BS == 1: BS-TEMS (decode method 7) -- same variable-node step, delta domain, column order, fill-in and output stage; the
 // pair search is replaced by the basic-set construction and the walk over its subsets (see the BS block below).
 template <typename T, int Q, int DC, int DV, int BS = 0>
-__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / TW_WARPS : TW_MINB_VALUE) : 1) k_iterate_tems_warp(const IterParams<T> P) {
+__global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS == 1 ? 5 * 4 / TW_WARPS : TW_MINB_VALUE) : 1) k_iterate_tems_warp(const IterParams<T> P) {
     constexpr int VEC = Q / 32;
     using PL = PLayout<T, VEC>;
     using S = TwSmem<T, Q>;
@@ -536,7 +573,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
         *reinterpret_cast<unsigned *>(mine + S::blk_cls) = cls;
     }
     __syncwarp();                                                  // all reads of v2c in R1 are done; records, M1 and c01 are visible
-    if constexpr (!BS) {
+    if constexpr (BS != 1) {
         // D_c[x]: cheapest allowed column of x other than c (the candidate vectors of the search), over the dead v2c
         T m0[VEC], m1[VEC];
         ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0);
@@ -559,7 +596,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
     __syncwarp();
     const unsigned long long c01w = ld_bytes<VEC>(c01 + x0);
     T *Tout = R1;
-    if constexpr (!BS) {
+    if constexpr (BS != 1) {
         // ---- pair search: deltaW[s] = min(m0(s), min_a m0(a) + D_{c0(a)}[s ^ a]), with EXACT pruning by value ---------------------
         // best starts at the single-deviation cost m0(s), so it is at all times an upper bound of deltaW[s]; a tag is written only
         // when a pair is STRICTLY cheaper.  tag = a (0 .. q-1): the entry whose candidate of the first kind won; 256 + a: of the
@@ -585,6 +622,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
         if (lane == 0) best[0] = T(0);
 #pragma unroll
         for (int r = 0; r < VEC; ++r) tag[r] = TW_NOTAG;
+        unsigned done = 0u;                                             // bit j: first kind handled, bit 8 + j: second kind handled (my block)
         if (P.p1 >= 2) {
             const bool second = P.p0 >= 2;                              // n_r = 1: the second-cheapest column may not deviate
             // TWO ROUNDS.  Round 0 takes the light entries, m0 <= U0/5 (U0 = max_s m0(s), the bound before any pair is known): they
@@ -597,7 +635,6 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
             // handles two of them: 16 candidates by 8 FADD2, one FMNMX3 + one compare + one predicated tag write per output, where
             // one entry at a time costs a compare and two selects per candidate.  The tag names both entries; which of the two
             // attained the minimum is settled once per output in tw_pair_of_tag.
-            unsigned done = 0u;                                         // bit j: first kind handled, bit 8 + j: second kind handled (my block)
 #pragma unroll 1
             T U0 = T(0);
             for (int round = 0; round < TW_ROUNDS; ++round) {
@@ -756,6 +793,64 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
         //      itself when the path does not deviate there (value deltaW[s]), on the partner's index when it does
         unsigned path[VEC];   // sb | sa << 8 | ca << 16 | cb << 18 | (columns the path deviates in) << 20 | pair << 24
         T va[VEC], vb[VEC];                                             // dw - ua, dw - ub of pair paths
+        if constexpr (BS == 2) {
+            // ---- REFERENCE TIE ORDER (tie_mode NBL_TIES_REFERENCE; n_r <= 2).  deltaW is what the search left in best; which of
+            // the configurations of EXACTLY that cost is recorded decides the messages once inputs tie (punctured symbols,
+            // quantised LLRs).  The reference keeps the first one its depth-first enumeration meets (NBLDPC.cpp:1897, strict '<'),
+            // i.e. the lexicographically smallest tuple (q_0, .., q_dc-1), 0 = "column does not deviate" first: the first
+            // deviating column as late as possible, its eta as small as possible, then the same for the second deviation (none
+            // beats any).  That order is a key (tw_key); a second pass over the entries the search handled recomputes their
+            // candidates, and where one EQUALS deltaW[s] (bit-equal sums) tw_ref_pair looks at all column assignments of that
+            // pair.  Every tied pair is met: its lighter element pays <= deltaW/2 <= U/2, so it was handled.
+            const bool second = P.p0 >= 2;
+            unsigned kbest[VEC];
+            {
+                T m0s[VEC], m1s[VEC];
+                ld_vec<T, VEC>(reinterpret_cast<const T *>(blk + lane * (int)S::blk_stride), m0s);
+                ld_split<T, VEC>(sM1, lane, m1s);
+#pragma unroll
+                for (int r = 0; r < VEC; ++r) {
+                    const int s = x0 + r, c0 = byte_of(c01w, r) & 15, c1 = byte_of(c01w, r) >> 4;
+                    va[r] = T(0); vb[r] = T(0); path[r] = 0u; kbest[r] = s == 0 ? 0u : 0xffffffffu;
+                    if (s != 0 && m0s[r] == best[r]) { kbest[r] = tw_key(c0, s, 4, 0); path[r] = 0x100000u << c0; }
+                    if (s != 0 && second && m1s[r] == best[r] && tw_key(c1, s, 4, 0) < kbest[r]) { kbest[r] = tw_key(c1, s, 4, 0); path[r] = 0x100000u << c1; }
+                }
+            }
+#pragma unroll 1
+            for (int bh = 0; bh < 32; ++bh) {
+                const unsigned m = __shfl_sync(0xffffffffu, done, bh);
+                if (!m) continue;                                       // warp-uniform
+                const unsigned char *rec = blk + bh * (int)S::blk_stride;
+                const unsigned cls = *reinterpret_cast<const unsigned *>(rec + S::blk_cls);
+                const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
+#pragma unroll 1
+                for (unsigned mm = (m | (m >> 8)) & ((1u << VEC) - 1u); mm; mm &= mm - 1u) {   // an entry of either kind: all assignments of its pairs are examined
+                    const int bl = __ffs((int)mm) - 1, a = VEC * bh + bl;
+                    const T m0a = *reinterpret_cast<const T *>(rec + bl * (int)sizeof(T));
+                    const T m1a = sM1[PL::index_rt(bh, bl)];
+                    const unsigned c = (cls >> (2 * bl)) & 3u;
+                    T dc[VEC], dx[VEC], cand[VEC];
+                    ld_split_bytes<T, VEC>(Dk + c * VB, dc);
+                    ld_split_bytes<T, VEC>(Dk + (c ? 0u : 1u) * VB, dx);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) cand[j] = second ? fmin(m0a + dc[j], m1a + (dc[j] > dx[j] ? dx[j] : INF)) : m0a + dc[j];   // cheapest assignment of the pair {a, b}
+#pragma unroll
+                    for (int bit = 1; bit < VEC; bit <<= 1) {
+                        const bool sw = (bl & bit) != 0;
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j)
+                            if (!(j & bit)) { const T lo = cand[j], hi = cand[j | bit]; cand[j] = sw ? hi : lo; cand[j | bit] = sw ? lo : hi; }
+                    }
+#pragma unroll
+                    for (int r = 0; r < VEC; ++r) {
+                        if (cand[r] == best[r] && x0 + r != 0) {
+                            const TwRef<T> pr = tw_ref_pair<T, Q>(slab, a, x0 + r, (unsigned)PL::index(lane, r), best[r], second);
+                            if (pr.key < kbest[r]) { kbest[r] = pr.key; path[r] = pr.path; va[r] = pr.va; vb[r] = pr.vb; }
+                        }
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int r = 0; r < VEC; ++r) {
             const int s = x0 + r;
@@ -765,6 +860,7 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS ? 5 * 4 / 
                 const TwPair<T> pr = tw_pair_of_tag<T, Q>(slab, tag[r], s, (unsigned)PL::index(lane, r), best[r]);
                 path[r] = pr.path; va[r] = pr.va; vb[r] = pr.vb;
             }
+        }
         }
         __syncwarp();                                                  // everyone is done with D: its area becomes the output trellis
 #pragma unroll

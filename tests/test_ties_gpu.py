@@ -2,7 +2,7 @@
 
 With continuous LLRs two T-EMS configurations of a syndrome never have exactly the same cost; with erasures or integer
 LLRs they do all the time, and which of the tied paths is RECORDED changes the messages.  tie_mode = REFERENCE must
-reproduce the path the reference's depth-first enumeration keeps (NBLDPC.cpp:1892-1944).  All values in these tests are
+reproduce the path the reference's depth-first enumeration keeps (NBLDPC.cpp:1892-1944) -- on the fast T-EMS kernel too.  All values in these tests are
 dyadic rationals, so fp32 and fp64 arithmetic are both exact and BOTH precisions must match the oracle decision for
 decision.  EMS and QSPA have one kernel each; their tie rules (insertion-sort order, NBLDPC.cpp:1715-1746; first
 maximum) are checked on the same inputs."""
@@ -24,6 +24,7 @@ def _run(code, tmp_path, lch, method, p0, p1, offset, precision, max_iter=5, tie
     dec = capi.Decoder(capi.Code.from_file(str(path)), method, max_iter, p0, p1, 1.0, offset, precision=precision,
                        max_batch=len(lch), tie_mode=tie_mode)
     r = dec.decode(lch, want_post=True)
+    r["kernel"] = dec.kernel()
     return r, want
 
 
@@ -37,6 +38,9 @@ def test_tems_integer_llrs_and_erasures(q, regular, p0, p1, precision, tmp_path)
     lch = rng.integers(-6, 3, size=(F, code["N"], q - 1)).astype(np.float64)     # integer LLRs: ties everywhere
     lch[:, ::3, :] = 0.0                                                          # every third symbol erased
     r, want = _run(code, tmp_path, lch, 4, p0, p1, 0.5, precision)
+    # the reference's tie order runs on the one-warp-per-row kernel (second pass over the handled entries) for q >= 32, n_r <= 2;
+    # n_r = 3 (a third column can tie) and GF(16) on the group kernel
+    assert r["kernel"] == ("tems_warp" if q >= 32 and p0 <= 2 else "group"), r["kernel"]
     assert np.array_equal(r["converged"], np.array([w[0] for w in want], np.int32))
     assert np.array_equal(r["iterations"], np.array([w[1] for w in want], np.int32))
     assert np.array_equal(r["sym"], np.stack([w[2] for w in want]))

@@ -282,8 +282,12 @@ def test_baseline_configurations_run_on_their_fast_kernels(code_files):
         dec = capi.Decoder(code, method, 10, p0, p1, 1.0, off, precision=capi.PREC_F32, max_batch=4)
         assert dec.kernel() == kern, (name, method, p0, p1, dec.kernel())
     code = load_product_code(code_files, G256)
-    assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4).kernel() == "group"          # reference tie order
+    # the fp64 default (reference tie order) runs on the fast kernel too; the bit-exact replay and n_r = 3 with the reference order do not
+    assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4).kernel() == "tems_warp"
     assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4, tie_mode=1).kernel() == "tems_warp"
+    assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F32, max_batch=4, tie_mode=2).kernel() == "tems_warp"
+    assert capi.Decoder(code, 4, 10, 2, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4, tie_mode=3).kernel() == "group"
+    assert capi.Decoder(code, 4, 10, 3, 2, 1.0, 0.5, precision=capi.PREC_F64, max_batch=4, tie_mode=2).kernel() == "group"
 
 
 @pytest.mark.parametrize("regular", [True, False])
