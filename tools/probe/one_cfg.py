@@ -12,6 +12,8 @@ if which == "cfg2":
 elif which == "cfg4":
     code = capi.Code.from_file(paths["divsalar.CNBLDPC.512.256.GF.256"]); args = (capi.METHOD_QSPA, 10, 0, 0, 1.0, 0.0); B = 148 * 8
     kw = dict(modulation=256, constellation=np.array(cons["GRAY_256QAM"], np.float64)); snr = 14.0
+elif which == "cfg5":
+    code = capi.Code.from_hbit(paths["H_bit_GF256"], 256); args = (capi.METHOD_TEMS, 10, 2, 2, 1.0, 0.5); B = 148 * 512; kw = {}; snr = 4.0
 else:
     code = capi.Code.from_file(paths["divsalar.UNBLDPC.128.64.GF.16"]); args = (capi.METHOD_QSPA, 10, 0, 0, 1.0, 0.0); B = 148 * 256; kw = {}; snr = 3.0
 dec = capi.Decoder(code, *args, precision=capi.PREC_F32, early_stop=1, max_batch=B)
