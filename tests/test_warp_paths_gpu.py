@@ -156,6 +156,27 @@ def test_ems_warp_kernel_random_codes(q, regular, tmp_path):
     _check_ems(code, tmp_path, lch[:4], 8, 3, 1.0, 0.5, kernel=2)
 
 
+@pytest.mark.parametrize("q,nm,nc", [(64, 8, 3), (64, 16, 3), (64, 2, 3), (64, 8, 2), (32, 8, 3), (128, 4, 3)])
+def test_ems_fp32_two_stage_enumeration_equals_the_group_kernel(q, nm, nc, tmp_path):
+    """fp32: the EMS warp kernel -- conf(n_m, n_c) in two stages when n_c does not bind, with the two-copy table, FADD2 and FMNMX3
+    for GF(64); direct enumeration otherwise -- against the group kernel's dynamic programme on the same frames: both form
+    every sum left to right and keep a value, not a path, so the outputs are identical bit for bit"""
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(5200 + q + nm + nc)
+    code = _random_code(q, 8, rng, True)
+    lch = _frames(code, 12, 0.62 + 0.02 * (q.bit_length() - 1), rng)
+    path = tmp_path / ("ems32_%d.txt" % q)
+    path.write_text(po.code_text(code))
+    outs = []
+    for kernel in (0, 1):                                                     # AUTO (ems_warp), GROUP
+        dec = capi.Decoder(capi.Code.from_file(str(path)), 2, 6, nm, nc, 1.0, 0.5, precision=capi.PREC_F32, max_batch=len(lch), kernel=kernel)
+        assert dec.kernel() == ("ems_warp" if kernel == 0 else "group")
+        outs.append(dec.decode(lch, want_post=True))
+    for k in ("sym", "converged", "iterations", "post"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
 @pytest.mark.parametrize("q", [16, 32, 64, 128])
 @pytest.mark.parametrize("regular", [True, False])
 def test_qspa_warp_kernel_random_codes(q, regular, tmp_path):
