@@ -114,7 +114,7 @@ typedef struct {
     int tie_mode;    /* T-EMS, exactly tied configuration costs (punctured symbols, quantised LLRs):
                         NBL_TIES_REFERENCE: the recorded path is the one the reference's depth-first
                         enumeration keeps (NBLDPC.cpp:1892-1944) -- on the one-warp-per-row kernel too (n_r <= 2: a second
-                        pass ranks the configurations of exactly equal cost; about 1/4 of the FAST throughput), else
+                        pass ranks the configurations of exactly equal cost; about 1/2 of the FAST throughput), else
                         on the group kernel;
                         NBL_TIES_FAST: first in the fast kernel's scan order (identical results whenever no
                         two configurations of a syndrome tie exactly, i.e. for continuous LLRs);

@@ -816,39 +816,73 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS == 1 ? 5 *
                     if (s != 0 && second && m1s[r] == best[r] && tw_key(c1, s, 4, 0) < kbest[r]) { kbest[r] = tw_key(c1, s, 4, 0); path[r] = 0x100000u << c1; }
                 }
             }
+            // Almost every (entry, output slot) step has SOME lane with a hit, and a hit examined on the spot occupies the whole warp.
+            // So the pass first only COLLECTS: up to four hit entries per output (one byte each) and their number; the assignments
+            // are examined afterwards, all lanes together.  Continuous inputs have one or two hits per output; when any output of
+            // the warp has more than four (integer LLRs, erasures) the pass runs once more and examines every hit where it is met.
+            unsigned hl[VEC]; int hc[VEC];
+#pragma unroll
+            for (int r = 0; r < VEC; ++r) { hl[r] = 0u; hc[r] = 0; }
+            bool direct = false;
 #pragma unroll 1
-            for (int bh = 0; bh < 32; ++bh) {
-                const unsigned m = __shfl_sync(0xffffffffu, done, bh);
-                if (!m) continue;                                       // warp-uniform
-                const unsigned char *rec = blk + bh * (int)S::blk_stride;
-                const unsigned cls = *reinterpret_cast<const unsigned *>(rec + S::blk_cls);
-                const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
+            for (int attempt = 0; attempt < 2; ++attempt) {
 #pragma unroll 1
-                for (unsigned mm = (m | (m >> 8)) & ((1u << VEC) - 1u); mm; mm &= mm - 1u) {   // an entry of either kind: all assignments of its pairs are examined
-                    const int bl = __ffs((int)mm) - 1, a = VEC * bh + bl;
-                    const T m0a = *reinterpret_cast<const T *>(rec + bl * (int)sizeof(T));
-                    const T m1a = sM1[PL::index_rt(bh, bl)];
-                    const unsigned c = (cls >> (2 * bl)) & 3u;
-                    T dc[VEC], dx[VEC], cand[VEC];
-                    ld_split_bytes<T, VEC>(Dk + c * VB, dc);
-                    ld_split_bytes<T, VEC>(Dk + (c ? 0u : 1u) * VB, dx);
+                for (int bh = 0; bh < 32; ++bh) {
+                    const unsigned m = __shfl_sync(0xffffffffu, done, bh);
+                    if (!m) continue;                                   // warp-uniform
+                    const unsigned char *rec = blk + bh * (int)S::blk_stride;
+                    const unsigned cls = *reinterpret_cast<const unsigned *>(rec + S::blk_cls);
+                    const unsigned char *Dk = slab + (lane ^ bh) * (PL::E16 * (int)sizeof(T));
+#pragma unroll 1
+                    for (unsigned mm = m & ((1u << VEC) - 1u); mm; mm &= mm - 1u) {   // (an entry of the second kind is one of the first kind too)
+                        const int bl = __ffs((int)mm) - 1, a = VEC * bh + bl;
+                        const T m0a = *reinterpret_cast<const T *>(rec + bl * (int)sizeof(T));
+                        const T m1a = sM1[PL::index_rt(bh, bl)];
+                        const unsigned c = (cls >> (2 * bl)) & 3u;
+                        T dc[VEC], dx[VEC], cand[VEC];
+                        ld_split_bytes<T, VEC>(Dk + c * VB, dc);
+                        ld_split_bytes<T, VEC>(Dk + (c ? 0u : 1u) * VB, dx);
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) cand[j] = second ? fmin(m0a + dc[j], m1a + (dc[j] > dx[j] ? dx[j] : INF)) : m0a + dc[j];   // cheapest assignment of the pair {a, b}
+                        for (int j = 0; j < VEC; ++j) cand[j] = second ? fmin(m0a + dc[j], m1a + (dc[j] > dx[j] ? dx[j] : INF)) : m0a + dc[j];   // cheapest assignment of the pair {a, b}
 #pragma unroll
-                    for (int bit = 1; bit < VEC; bit <<= 1) {
-                        const bool sw = (bl & bit) != 0;
+                        for (int bit = 1; bit < VEC; bit <<= 1) {
+                            const bool sw = (bl & bit) != 0;
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j)
-                            if (!(j & bit)) { const T lo = cand[j], hi = cand[j | bit]; cand[j] = sw ? hi : lo; cand[j | bit] = sw ? lo : hi; }
+                            for (int j = 0; j < VEC; ++j)
+                                if (!(j & bit)) { const T lo = cand[j], hi = cand[j | bit]; cand[j] = sw ? hi : lo; cand[j | bit] = sw ? lo : hi; }
+                        }
+                        if (!direct) {
+#pragma unroll
+                            for (int r = 0; r < VEC; ++r)
+                                if (cand[r] == best[r] && x0 + r != 0) { hl[r] = (hl[r] << 8) | (unsigned)a; hc[r] += 1; }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < VEC; ++r) {
+                                if (cand[r] == best[r] && x0 + r != 0) {
+                                    const TwRef<T> pr = tw_ref_pair<T, Q>(slab, a, x0 + r, (unsigned)PL::index(lane, r), best[r], second);
+                                    if (pr.key < kbest[r]) { kbest[r] = pr.key; path[r] = pr.path; va[r] = pr.va; vb[r] = pr.vb; }
+                                }
+                            }
+                        }
                     }
+                }
+                if (direct) break;
+                int most = 0;
+#pragma unroll
+                for (int r = 0; r < VEC; ++r) most = hc[r] > most ? hc[r] : most;
+                if (__any_sync(0xffffffffu, most > 4)) { direct = true; continue; }   // warp-uniform: examine every hit where it is met
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {
+                    if (!__any_sync(0xffffffffu, i < most)) break;
 #pragma unroll
                     for (int r = 0; r < VEC; ++r) {
-                        if (cand[r] == best[r] && x0 + r != 0) {
-                            const TwRef<T> pr = tw_ref_pair<T, Q>(slab, a, x0 + r, (unsigned)PL::index(lane, r), best[r], second);
+                        if (i < hc[r]) {
+                            const TwRef<T> pr = tw_ref_pair<T, Q>(slab, (int)((hl[r] >> (8 * i)) & 255u), x0 + r, (unsigned)PL::index(lane, r), best[r], second);
                             if (pr.key < kbest[r]) { kbest[r] = pr.key; path[r] = pr.path; va[r] = pr.va; vb[r] = pr.vb; }
                         }
                     }
                 }
+                break;
             }
         } else {
 #pragma unroll
