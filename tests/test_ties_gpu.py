@@ -30,7 +30,8 @@ def _run(code, tmp_path, lch, method, p0, p1, offset, precision, max_iter=5, tie
 
 @pytest.mark.parametrize("precision", [0, 1])
 @pytest.mark.parametrize("q,regular,p0,p1", [(16, False, 2, 2), (32, False, 2, 2), (64, True, 2, 2), (256, True, 2, 2),
-                                             (64, True, 1, 2), (64, True, 3, 2), (32, False, 2, 1), (64, False, 3, 2)])
+                                             (64, True, 1, 2), (64, True, 3, 2), (32, False, 2, 1), (64, False, 3, 2),
+                                             (256, False, 2, 2), (256, True, 1, 2), (256, False, 2, 1), (128, True, 2, 2), (128, False, 1, 2)])
 def test_tems_integer_llrs_and_erasures(q, regular, p0, p1, precision, tmp_path):
     rng = np.random.default_rng(4000 + q + 10 * p0 + p1)
     code = _random_code(q, 8, rng, regular)
