@@ -247,6 +247,11 @@ struct nbl_decoder {
     // kernels themselves there.  Dropped when the OSD set-up changes.
     std::map<int, cudaGraphExec_t> graphs;
     std::map<int, int> graph_launches;
+    // large batches with HOST samples (nbl_demap_decode_batch): the samples cross PCIe in chunks on a second stream, and chunk c is
+    // demapped and run through iteration 1 while chunk c + 1 is still in flight (iterations 2.. run on the whole batch)
+    struct Pipe { bool active = false; int modulation = 0, ylen = 0, chunks = 0, per = 0; double sigma = 0; const double *ysrc = nullptr; } pipe;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
     const nbl_code *code = nullptr;
     nbl_decoder_config cfg{};
     cudaStream_t stream = nullptr;
@@ -338,6 +343,8 @@ extern "C" void nbl_decoder_destroy(nbl_decoder *d) {
                     d->d_out, d->d_active, d->d_stage, d->d_ystage, d->d_cons, d->d_pool, d->d_counters, d->d_tx, d->d_msg, d->d_osd_H0, d->d_osd_sum, d->d_osd_status, d->d_rowdesc8};
     if (d->sim_enc) nbl_encoder_destroy(d->sim_enc);
     for (auto &kv : d->graphs) cudaGraphExecDestroy(kv.second);
+    for (cudaEvent_t e : d->chunk_ev) cudaEventDestroy(e);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : d->it_ev) if (e) cudaEventDestroy(e);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -683,8 +690,11 @@ template <typename T, int Q> static int launch_posterior_tq(nbl_decoder *d, int 
 
 // Runs the iterations on the frames whose channel LLRs are already in d_lch.  Results stay on the device
 // (d_out, d_conv, d_iters); post_dev (device doubles) is optional.
+static int launch_demap(nbl_decoder *d, int modulation, const double *ysrc, int f0, int nf, int ylen, double sigma, bool to_lch, double *out_dev);
 template <typename T> static int enqueue_decode(nbl_decoder *d, int B, double *post_dev, bool timed);
 constexpr int NBL_GRAPH_MAX_B = 64;       // batches up to this size go through a captured graph
+constexpr int NBL_PIPE_MIN_B = 512;       // host-sample batches from this size on are copied in chunks behind which iteration 1 starts
+constexpr int NBL_PIPE_CHUNKS = 4;
 
 static void drop_graphs(nbl_decoder *d) {
     for (auto &kv : d->graphs) cudaGraphExecDestroy(kv.second);
@@ -748,6 +758,25 @@ template <typename T> static int enqueue_decode(nbl_decoder *d, int B, double *p
             P.vdec = d->d_vdec; P.dec = d->d_dec; P.flag = d->d_flag; P.done = d->d_done;
             P.pfwd_sw = d->d_pfwd_sw; P.pinv_sw = d->d_pinv_sw;
             if (timed) CK(cudaEventRecord(d->it_ev[2 * (it - 1)], d->stream));
+            if (it == 1 && d->pipe.active) {
+                // host samples arriving in chunks (nbl_demap_decode_batch): chunk c is demapped and iterated as soon as its copy has
+                // landed; every per-frame array of the launch is offset to the chunk's first frame
+                const int K = d->pipe.chunks, per = d->pipe.per;
+                const size_t N = (size_t)d->g.N, E = (size_t)d->g.E;
+                for (int ck = 0; ck < K; ++ck) {
+                    const int f0 = ck * per, nf = std::min(per, B - f0);
+                    if (nf <= 0) break;
+                    CK(cudaStreamWaitEvent(d->stream, d->chunk_ev[ck], 0));
+                    if ((rc = launch_demap(d, d->pipe.modulation, d->pipe.ysrc, f0, nf, d->pipe.ylen, d->pipe.sigma, true, nullptr))) return rc;
+                    IterParams<T> Pc = P;
+                    Pc.B = nf; Pc.lch = P.lch + f0 * N * q; Pc.v2c = P.v2c + f0 * E * q; Pc.c2v_in = P.c2v_in + f0 * E * q; Pc.c2v_out = P.c2v_out + f0 * E * q;
+                    Pc.vdec = P.vdec + f0 * E; Pc.dec = P.dec + f0 * N; Pc.flag = P.flag + f0; Pc.done = P.done + f0;
+                    DISPATCH_Q(q, rc = (launch_iterate_tq<T, QQ>(d, Pc)));
+                    if (rc) return rc;
+                    d->last_launches += 2;                           // demapper + iteration kernel of the chunk
+                }
+                rc = NBL_OK; d->last_launches -= 1;                 // (the common count below adds one iteration launch)
+            } else
             DISPATCH_Q(q, rc = (launch_iterate_tq<T, QQ>(d, P)));
             if (rc) return rc;
             if (timed) { CK(cudaEventRecord(d->it_ev[2 * (it - 1) + 1], d->stream)); d->it_recorded = it; }
@@ -948,6 +977,29 @@ static int setup_punct(nbl_decoder *d, int modulation, const int *punct_sym, int
     return NBL_OK;
 }
 
+// the demapper kernels on frames f0 .. f0 + nf - 1 of samples already on the device (ysrc = first frame of the batch)
+static int launch_demap(nbl_decoder *d, int modulation, const double *ysrc, int f0, int nf, int ylen, double sigma, bool to_lch, double *out_dev) {
+    const int N = d->g.N, q = d->g.q;
+    const size_t tot = (size_t)nf * N * q;
+    const unsigned grid = (unsigned)((tot + 255) / 256);
+    const bool f64 = d->cfg.precision == NBL_PREC_F64;
+    const double *ys = ysrc + (size_t)f0 * ylen * (modulation == 2 ? 1 : 2);
+    const size_t loff = (size_t)f0 * N * q;
+    double *od = out_dev ? out_dev + (size_t)f0 * N * (q - 1) : nullptr;
+    if (modulation == 2) {
+        const int threads = 256, syms = 8 * (threads / q);          // q <= 256
+        const unsigned bgrid = (unsigned)(((size_t)nf * N + syms - 1) / syms);
+        const size_t sh = (size_t)syms * d->g.p * sizeof(double);
+        if (f64) k_demap_bpsk<double><<<bgrid, threads, sh, d->stream>>>(nf, N, q, d->g.p, ylen, syms, ys, sigma, d->d_ysym, to_lch ? (double *)d->d_lch + loff : nullptr, od);
+        else k_demap_bpsk<float><<<bgrid, threads, sh, d->stream>>>(nf, N, q, d->g.p, ylen, syms, ys, sigma, d->d_ysym, to_lch ? (float *)d->d_lch + loff : nullptr, od);
+    } else {
+        if (f64) k_demap_qam<double><<<grid, 256, 0, d->stream>>>(nf, N, q, ylen, ys, d->d_cons, sigma, d->d_ysym, to_lch ? (double *)d->d_lch + loff : nullptr, od);
+        else k_demap_qam<float><<<grid, 256, 0, d->stream>>>(nf, N, q, ylen, ys, d->d_cons, sigma, d->d_ysym, to_lch ? (float *)d->d_lch + loff : nullptr, od);
+    }
+    CK(cudaGetLastError());
+    return NBL_OK;
+}
+
 // demap into d_lch (T) and/or a double output
 static int demap_common(nbl_decoder *d, int modulation, const double *y, int B, const double *constellation, double sigma,
                         const int *punct_sym, int n_punct, bool to_lch, double *out_dev) {
@@ -972,21 +1024,7 @@ static int demap_common(nbl_decoder *d, int modulation, const double *y, int B, 
         if (constellation != d->d_cons)                             // nbl_simulate hands in the resident copy
             CK(cudaMemcpyAsync(d->d_cons, constellation, 2 * q * sizeof(double), is_device_ptr(constellation) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d->stream));
     }
-    const size_t tot = (size_t)B * N * q;
-    const unsigned grid = (unsigned)((tot + 255) / 256);
-    const bool f64 = d->cfg.precision == NBL_PREC_F64;
-    if (modulation == 2) {
-        const int threads = 256, syms = 8 * (threads / q);          // q <= 256
-        const unsigned bgrid = (unsigned)(((size_t)B * N + syms - 1) / syms);
-        const size_t sh = (size_t)syms * d->g.p * sizeof(double);
-        if (f64) k_demap_bpsk<double><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, syms, ysrc, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
-        else k_demap_bpsk<float><<<bgrid, threads, sh, d->stream>>>(B, N, q, d->g.p, ylen, syms, ysrc, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
-    } else {
-        if (f64) k_demap_qam<double><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (double *)d->d_lch : nullptr, out_dev);
-        else k_demap_qam<float><<<grid, 256, 0, d->stream>>>(B, N, q, ylen, ysrc, d->d_cons, sigma, d->d_ysym, to_lch ? (float *)d->d_lch : nullptr, out_dev);
-    }
-    CK(cudaGetLastError());
-    return NBL_OK;
+    return launch_demap(d, modulation, ysrc, 0, B, ylen, sigma, to_lch, out_dev);
 }
 
 static int demap_api(nbl_decoder *d, int modulation, const double *y, int B, const double *cons, double sigma, const int *ps, int np, double *L_ch) {
@@ -1020,7 +1058,35 @@ extern "C" int nbl_demap_decode_batch(nbl_decoder *d, int modulation, const doub
     if (B < 0 || B > d->cfg.max_batch) { nbl_set_error("nbl_demap_decode_batch: B exceeds max_batch"); return NBL_ERR_ARG; }
     if (B == 0) return NBL_OK;
     CK(cudaSetDevice(d->cfg.device));
-    int rc = demap_common(d, modulation, y, B, cons, sigma, ps, np, true, nullptr);
+    int rc;
+    const bool osd_acc = d->osd_on && d->osd.order >= 0 && !d->osd.flag;
+    if (B >= NBL_PIPE_MIN_B && (long long)B * d->g.N < (1LL << 31) && !is_device_ptr(y) && d->cfg.max_iter >= 2 && !osd_acc && (modulation == 2 || modulation == d->g.q) && sigma > 0 &&
+        (modulation == 2 || cons)) {
+        // pipelined: samples in NBL_PIPE_CHUNKS chunks on the copy stream; demapper and iteration 1 of a chunk behind its copy
+        int ylen;
+        if ((rc = setup_punct(d, modulation, ps, np, &ylen))) return rc;
+        const size_t per_frame = (size_t)ylen * (modulation == 2 ? 1 : 2);
+        if ((rc = ensure_ystage(d, (size_t)B * per_frame * sizeof(double)))) return rc;
+        if (modulation != 2 && cons != d->d_cons)
+            CK(cudaMemcpyAsync(d->d_cons, cons, 2 * d->g.q * sizeof(double), is_device_ptr(cons) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d->stream));
+        if (!d->copy_stream) CK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        while ((int)d->chunk_ev.size() < NBL_PIPE_CHUNKS + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); d->chunk_ev.push_back(e); }
+        const int per = (B + NBL_PIPE_CHUNKS - 1) / NBL_PIPE_CHUNKS;
+        // the staging buffer may still be read by work queued on the decoder's stream (an asynchronous caller): order the copies behind it
+        CK(cudaEventRecord(d->chunk_ev[NBL_PIPE_CHUNKS], d->stream));
+        CK(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[NBL_PIPE_CHUNKS], 0));
+        for (int ck = 0; ck < NBL_PIPE_CHUNKS; ++ck) {
+            const int f0 = ck * per, nf = std::min(per, B - f0);
+            if (nf > 0) CK(cudaMemcpyAsync(d->d_ystage + (size_t)f0 * per_frame, y + (size_t)f0 * per_frame, (size_t)nf * per_frame * sizeof(double), cudaMemcpyHostToDevice, d->copy_stream));
+            CK(cudaEventRecord(d->chunk_ev[ck], d->copy_stream));
+        }
+        d->pipe.active = true; d->pipe.modulation = modulation; d->pipe.ylen = ylen; d->pipe.chunks = NBL_PIPE_CHUNKS; d->pipe.per = per;
+        d->pipe.sigma = sigma; d->pipe.ysrc = d->d_ystage;
+        rc = decode_common(d, B, out_sym, converged, iterations, nullptr);
+        d->pipe.active = false;
+        return rc;
+    }
+    rc = demap_common(d, modulation, y, B, cons, sigma, ps, np, true, nullptr);
     if (rc) return rc;
     return decode_common(d, B, out_sym, converged, iterations, nullptr);
 }

@@ -210,3 +210,28 @@ def test_graph_replay_and_direct_launches_agree(name, precision_name, code_files
             assert np.array_equal(r[k], direct[k][:8]) and np.array_equal(r[k], direct[k][64:72])
         assert np.array_equal(r["post"], direct["post"][:8])
     assert dec.decode(lch[:1])["iterations"][0] == direct["iterations"][0]      # another batch size: another graph
+
+
+@pytest.mark.parametrize("name,precision_name", [("cfg3_tems_gf256", "f32"), ("cfg3_tems_gf256", "f64"), ("cfg2_ems_gf64", "f32"),
+                                                 ("cfg1_qspa_gf16", "f32"), ("cfg4_qspa_gf256_qam", "f32"), ("cfg5_tems_hbit256", "f32")])
+def test_chunked_host_sample_pipeline_equals_one_piece(name, precision_name, code_files):
+    """nbl_demap_decode_batch with HOST samples: from 512 frames on the samples cross PCIe in four chunks on a second stream, and a
+    chunk is demapped and run through iteration 1 (per-frame arrays offset to the chunk) while the next one is in flight.  The
+    same frames in small batches (one piece, graph replay) and in one large ragged batch give identical results."""
+    from nbldpc_b200 import capi
+    z, meta = load_golden(name)
+    code = load_product_code(code_files, meta["code"])
+    prec = capi.PREC_F64 if precision_name == "f64" else capi.PREC_F32
+    rx = z["rx"]
+    F = len(rx)
+    from conftest import constellation
+    mod = meta["nqam"]
+    y = rx[:, :, 0] if mod == 2 else rx.reshape(F, -1)
+    cons = constellation(meta["constellation"]) if mod != 2 else None
+    small = _decoder(code, meta, prec, F).demap_decode(mod, y, meta["sigma"], constellation=cons)
+    reps = 601 // F + 1                                               # ragged: not a multiple of the chunk count
+    big_y = np.concatenate([y] * reps)[:601]
+    big = _decoder(code, meta, prec, 601).demap_decode(mod, big_y, meta["sigma"], constellation=cons)
+    for k in ("sym", "converged", "iterations"):
+        want = np.concatenate([small[k]] * reps)[:601]
+        assert np.array_equal(big[k], want), k
