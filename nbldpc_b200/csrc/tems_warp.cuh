@@ -19,11 +19,17 @@
 //     (255 x q candidates where the reference enumerates ~94 k configurations; n_r = 1: D_c[x] = +inf where c0(x) == c);
 //   * and it is PRUNED BY VALUE, exactly: an entry a whose m0(a) exceeds half of the largest deltaW any output can still have
 //     cannot be the lighter element of a winning pair and is skipped -- its pairs are reached from their other element (see the
-//     search for the one case that needs a second kind of candidate).  ~50 of the 255 entries survive in the first iterations,
-//     ~11 in the last; the minima and the recorded pairs are those of the full enumeration;
+//     search for the one case that needs a second kind of candidate).  The search runs in TWO ROUNDS -- the light entries
+//     (m0 <= U0/5) first, then what is still live against the refreshed bound -- and ~45 of the 255 entries are handled in the
+//     first iterations, ~11 in the last; the minima and the recorded pairs are those of the full enumeration;
 //   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; entry a = VEC*bh + bl reads block k = t ^ bh of D_{c0(a)}
-//     (its column is part of the ADDRESS: no dispatch), permuted by bl, which is a compile-time constant of the VEC unrolled
-//     entry bodies; sums are FADD2 (two per instruction, sm_100a);
+//     (its column is part of the ADDRESS: no dispatch), permuted by bl.  Entries are taken TWO AT A TIME: 16 candidates by 8
+//     FADD2 (two sums per instruction, sm_100a), then per output one FMNMX3, one compare and one select of a tag that names both
+//     entries (which of the two won is settled once per output, in the path recovery).  For fp32 / q = 256 only bits 0-1 of bl
+//     are compile-time constants (four bodies); bit 2 selects the 16-byte piece, i.e. it is part of the address, and the entries
+//     of a class reach their bodies through a compacted list of 8-byte records built lane-parallel from two ballots;
+//   * tie_mode REFERENCE (template parameter BS == 2): a second pass finds the configurations whose cost EQUALS deltaW and records
+//     the one the reference's depth-first enumeration meets first;
 //   * no block-level barriers: every exchange between lanes is a __syncwarp on the warp's private smem slab;
 //   * all message-sized vectors in shared memory (v2c, D_c, the output trellis) use the same split layout, so that the 128-bit
 //     accesses of a lane to its own elements are conflict free; gathers go through table bytes that are stored pre-swizzled to
@@ -599,8 +605,8 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS == 1 ? 5 *
     if constexpr (BS != 1) {
         // ---- pair search: deltaW[s] = min(m0(s), min_a m0(a) + D_{c0(a)}[s ^ a]), with EXACT pruning by value ---------------------
         // best starts at the single-deviation cost m0(s), so it is at all times an upper bound of deltaW[s]; a tag is written only
-        // when a pair is STRICTLY cheaper.  tag = a (0 .. q-1): the entry whose candidate of the first kind won; 256 + a: of the
-        // second kind; TW_NOTAG: the single deviation stands.
+        // when a pair is STRICTLY cheaper.  tag = a1 | a2 << 8: the two entries of the body whose candidate (first kind) won;
+        // TW_SECOND | a | a << 8: a candidate of the second kind of entry a; TW_NOTAG: the single deviation stands.
         //
         // Let U >= max_s deltaW[s] (any upper bound: the running max of best).  A pair {x, y} can only be the cost of some s if
         // cost <= U, and cost >= m0(x) + m0(y), so its lighter element has m0 <= U/2: an entry a with m0(a) > U/2 ("dead") is
@@ -610,12 +616,10 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS == 1 ? 5 *
         //     D_c[.], covers the term in which the LIVE element pays m0; the term in which the live element a pays m1 while its
         //     dead partner pays m0 is covered by a second kind of candidate, m1(a) + (m0(y) if c0(y) == c else inf), needed only
         //     when m1(a) <= U/2 as well (else the partner is live and reaches the pair itself).
-        // U is refreshed from best before every round of blocks, so the bound tightens while the search runs.  On the headline workload
-        // ~50 of the 255 entries are live in the first iterations and ~11 in the last (tools/probe/prune_stats.py), ~5 need the
-        // second kind -- same minima, same recorded pairs as the full enumeration (no two configurations tie exactly); the full
-        // enumeration with its four-way column dispatch per entry, which this replaces, is in the history of this file.
-        // A live entry loads the block of ITS column only (the address carries the column), and because entries are few the tag
-        // is kept per entry: the recorded pair needs no second scan.
+        // Same minima, same recorded pairs as the full enumeration (no two configurations tie exactly); the full enumeration with
+        // its four-way column dispatch per entry, and the one-entry-at-a-time form with a bound refresh per block range, which this
+        // replaces, are in the history of this file.  A live entry loads the block of ITS column only (the address carries the
+        // column).
         T best[VEC]; int tag[VEC];
         const unsigned char *myrec = blk + lane * (int)S::blk_stride;
         ld_vec<T, VEC>(reinterpret_cast<const T *>(myrec), best);
