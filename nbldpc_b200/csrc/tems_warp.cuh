@@ -20,8 +20,8 @@
 //   * and it is PRUNED BY VALUE, exactly: an entry a whose m0(a) exceeds half of the largest deltaW any output can still have
 //     cannot be the lighter element of a winning pair and is skipped -- its pairs are reached from their other element (see the
 //     search for the one case that needs a second kind of candidate).  The search runs in TWO ROUNDS -- the light entries
-//     (m0 <= U0/5) first, then what is still live against the refreshed bound -- and ~45 of the 255 entries are handled in the
-//     first iterations, ~11 in the last; the minima and the recorded pairs are those of the full enumeration;
+//     (m0 <= U0/5) first, then what is still live against the refreshed bound -- and 35-43 of the 255 entries are handled in the
+//     first iterations, ~12 in the last; the minima and the recorded pairs are those of the full enumeration;
 //   * it is register tiled: lane t owns s = VEC*t .. VEC*t+VEC-1; entry a = VEC*bh + bl reads block k = t ^ bh of D_{c0(a)}
 //     (its column is part of the ADDRESS: no dispatch), permuted by bl.  Entries are taken TWO AT A TIME: 16 candidates by 8
 //     FADD2 (two sums per instruction, sm_100a), then per output one FMNMX3, one compare and one select of a tag that names both
