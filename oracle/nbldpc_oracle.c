@@ -284,6 +284,14 @@ static void ems_sort(double *Ls, int *Es, const double *L, int q1) {
     }
 }
 
+/* Analysis switch (NOT the reference's arithmetic): with it, a configuration's sum is formed afresh, left to right, instead of in
+   the reference's one running sum that is added to on the way down and subtracted from on the way back.  The running sum keeps a
+   rounding residue that later configurations inherit; where two sums are equal in exact arithmetic that residue decides between
+   them.  tools/fuzz_parity.py uses the switch to show that a rare EMS difference between the CUDA path (fresh sums) and the
+   reference is exactly this residue and nothing else. */
+static int g_ems_fresh = 0;
+void orc_set_ems_fresh_sums(int on) { g_ems_fresh = on; }
+
 /* ConstructConf: depth-first over the inputs, running sums updated and then undone in place */
 static void ems_conf(ems_ctx *e, int lim, int begin) {
     const orc_code *c = e->s->c;
@@ -295,12 +303,14 @@ static void ems_conf(ems_ctx *e, int lim, int begin) {
     int h = c->ccoef[e->row * c->maxdc + begin];
     for (int k = 0; k < lim; ++k) {
         int g = MUL(c, e->sym[begin][k], h);
+        const double before = e->sum_llr;
         e->sum_sym ^= g;
         e->sum_llr = e->sum_llr + e->srt[begin][k];
         e->diff += (k != 0);
         int go = e->diff <= e->nc;
         if (go) ems_conf(e, lim, begin + 1);
         e->sum_sym ^= g;
+        if (g_ems_fresh) e->sum_llr = before; else
         e->sum_llr = e->sum_llr - e->srt[begin][k];
         e->diff -= (k != 0);
         if (!go) break;

@@ -59,6 +59,8 @@ int orc_decode_osd(const orc_code *c, int method, int max_iter, int p0, int p1, 
 
 /* number of T-EMS configuration leaves visited in the last orc_decode call (tems_route_num, NBLDPC.cpp:1896) */
 double orc_last_tems_leaves(void);
+/* analysis switch, off by default: EMS configuration sums formed afresh instead of in the reference's add / subtract running sum */
+void orc_set_ems_fresh_sums(int on);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,7 @@ def lib():
         _lib.orc_demap_qam.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double, ip, C.c_int, dp]
         _lib.orc_gf_tables.argtypes = [C.c_int, C.c_int, ip, ip]
         _lib.orc_last_tems_leaves.restype = C.c_double
+        _lib.orc_set_ems_fresh_sums.argtypes = [C.c_int]
         _lib.orc_osd_create.restype = C.c_void_p
         _lib.orc_osd_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.orc_osd_destroy.argtypes = [C.c_void_p]
@@ -153,6 +154,11 @@ class OracleOsd:
         dist = C.c_int(0)
         lib().orc_osd_last(self._h, _ip(order), C.byref(dist))
         return order, dist.value
+
+
+def set_ems_fresh_sums(on):
+    """analysis switch (off = the reference's arithmetic): EMS configuration sums formed afresh, not in the running add / subtract sum"""
+    lib().orc_set_ems_fresh_sums(int(bool(on)))
 
 
 def demap_bpsk(q, N, y_re, sigma, punct=()):

@@ -339,3 +339,43 @@ def test_ems_gf16_kernel_on_the_reference_code(code_files):
         assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
     assert np.array_equal(outs[0][1]["sym"], z["dec_sym"].astype(np.int32))
     assert np.array_equal(outs[0][1]["iterations"], z["iters"].astype(np.int32))
+
+
+def test_ems_running_sum_residue_case(tmp_path):
+    """The one EMS difference the randomised differential test has found (tools/fuzz_parity.py, seed 51, case 75: GF(128),
+    irregular code, n_m = 4, n_c = 1): the reference forms all sums of a check row in one running sum (+= going down, -= coming
+    back, NBLDPC.cpp:1746-1786), whose rounding residue decided between two sums that are equal in exact arithmetic; from
+    iteration 5 on one variable's posterior differs.  Both CUDA kernels form every sum afresh: they agree with each other and
+    with the oracle run in that arithmetic (an analysis switch of the oracle) bit for bit, and with the reference's
+    arithmetic up to iteration 4."""
+    import importlib.util, os
+    from nbldpc_b200 import capi
+    from oracle import pyoracle as po
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(root, "tools", "fuzz_parity.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    d = fz.gen_case(75, 51)
+    code, q = d["code"], d["code"]["q"]
+    assert (q, d["method"], d["p0"], d["p1"]) == (128, 2, 4, 1)
+    L = np.stack([po.demap_bpsk(q, code["N"], yy, d["sigma"], d["punct"]) for yy in d["y"]])
+    path = tmp_path / "residue.txt"
+    path.write_text(po.code_text(code))
+    oc = po.OracleCode(code)
+    outs = []
+    for kernel in (0, 1):
+        dec = capi.Decoder(capi.Code.from_file(str(path)), 2, d["max_iter"], 4, 1, d["factor"], d["offset"], precision=capi.PREC_F64, max_batch=len(L), kernel=kernel)
+        outs.append(dec.decode(L, want_post=True))
+    assert all(np.array_equal(outs[0][k], outs[1][k]) for k in ("sym", "converged", "iterations", "post"))
+    ref = np.stack([oc.decode(2, d["max_iter"], 4, 1, d["factor"], d["offset"], l)[3] for l in L])
+    po.set_ems_fresh_sums(1)
+    try:
+        fresh = [oc.decode(2, d["max_iter"], 4, 1, d["factor"], d["offset"], l) for l in L]
+    finally:
+        po.set_ems_fresh_sums(0)
+    assert np.abs(outs[0]["post"] - ref).max() > 1.0                              # the reference's residue took the other branch ...
+    assert np.array_equal(outs[0]["sym"], np.stack([w[2] for w in fresh]))        # ... the same arithmetic without it does not
+    assert np.array_equal(outs[0]["iterations"], np.array([w[1] for w in fresh], np.int32))
+    assert np.abs(outs[0]["post"] - np.stack([w[3] for w in fresh])).max() < 1e-9
+    ref4 = np.stack([oc.decode(2, 4, 4, 1, d["factor"], d["offset"], l)[3] for l in L])
+    dec4 = capi.Decoder(capi.Code.from_file(str(path)), 2, 4, 4, 1, d["factor"], d["offset"], precision=capi.PREC_F64, max_batch=len(L))
+    assert np.abs(dec4.decode(L, want_post=True)["post"] - ref4).max() < 1e-9

@@ -107,6 +107,7 @@ def main():
     tmp = tempfile.mkdtemp()
     tally = {}
     diverged = []
+    residue = []
     nexact = 0
     t0 = time.time()
     for d in gen_cases(a.seed):
@@ -164,6 +165,26 @@ def main():
             if ok:
                 diverged.append("case %d (q %d, n_r %d, n_c %d, tie mode %d): %s, posterior err %.3g" % (
                     case, q, p0, p1, tie, "decisions and iteration counts equal" if same else "DECISIONS DIFFER", err))
+        # EMS keeps a value, not a path, so its results do not depend on the order among equal sums -- but the reference forms all
+        # sums of a check row in ONE running sum (added to on the way down, subtracted from on the way back), whose rounding
+        # residue later sums inherit.  Where two sums are equal in exact arithmetic that residue decides which symbol enters a
+        # sorted list, and from there on the two decoders differ.  Such a case (about one in 1 500) is listed, not failed, when
+        # the oracle with its sums formed afresh (an analysis switch; everything else the reference's arithmetic) reproduces the
+        # CUDA result: decisions, iteration counts and posteriors to 1e-8.
+        if not ok and method == 2:
+            po.set_ems_fresh_sums(1)
+            try:
+                w2 = [oc.decode(method, max_iter, p0, p1, factor, offset, L[f]) for f in range(F)]
+            finally:
+                po.set_ems_fresh_sums(0)
+            ref2 = np.stack([w[3] for w in w2])
+            same2 = (np.array_equal(r["converged"], np.array([w[0] for w in w2], np.int32)) and
+                     np.array_equal(r["iterations"], np.array([w[1] for w in w2], np.int32)) and np.array_equal(r["sym"], np.stack([w[2] for w in w2])))
+            err2 = float((np.abs(r["post"] - ref2) / np.maximum(np.abs(ref2), 1.0)).max())
+            if same2 and err2 < tol:
+                ok = True
+                residue.append("case %d (q %d, n_m %d, n_c %d): %s against the reference's running sums, posterior err %.3g; identical (err %.3g) "
+                               "against the same arithmetic with sums formed afresh" % (case, q, p0, p1, "decisions equal" if same else "decisions differ", err, err2))
         key = (method, q)
         tally[key] = tally.get(key, 0) + 1
         if a.only >= 0:
@@ -185,6 +206,8 @@ def main():
     lines += ["T-EMS cases also run in tie mode BITEXACT, posteriors bit-identical to the oracle: %d of %d" % (nexact, nexact)]
     lines += ["T-EMS cases whose ordinary (parallel) run resolved configurations of equal exact cost differently: %d" % len(diverged)]
     lines += ["  " + x for x in diverged]
+    lines += ["EMS cases in which the rounding residue of the reference's running sum decided between sums equal in exact arithmetic: %d" % len(residue)]
+    lines += ["  " + x for x in residue]
     print("\n".join(lines))
     if a.out:
         open(a.out, "w").write("\n".join(lines) + "\n")
