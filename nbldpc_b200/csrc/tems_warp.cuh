@@ -126,6 +126,18 @@ template <typename T, int N> __device__ __forceinline__ void st_vec(T *__restric
         for (int i = 0; i < N; ++i) p[i] = v[i];
     }
 }
+// N consecutive elements as one store when they make 16 or 8 bytes
+template <typename T, int N> __device__ __forceinline__ void st_run(T *p, const T (&v)[N]) {
+    if constexpr (N * sizeof(T) == 8) {
+        unsigned long long w;
+        if constexpr (sizeof(T) == 4) w = ((unsigned long long)__float_as_uint((float)v[1]) << 32) | __float_as_uint((float)v[0]);
+        else w = (unsigned long long)__double_as_longlong((double)v[0]);
+        *reinterpret_cast<unsigned long long *>(p) = w;
+    } else st_vec<T, N>(p, v);
+}
+#ifndef TW_CO_PE
+#define TW_CO_PE 4        // elements per trip of the column-order loop (one store per trip and array)
+#endif
 // a lane's VEC elements of a split-layout vector (block k): NP pieces of 16 bytes, PSTRIDE apart
 template <typename T, int VEC> __device__ __forceinline__ void ld_split(const T *__restrict__ vec, int k, T (&v)[VEC]) {
     using PL = PLayout<T, VEC>;
@@ -551,30 +563,41 @@ __global__ void __launch_bounds__(32 * TW_WARPS, sizeof(T) == 4 ? (BS == 1 ? 5 *
         }
         unsigned char *mine = blk + lane * (int)S::blk_stride;
         unsigned cls = 0;
+        // rolled over the 16-byte pieces of the lane's block, unrolled inside a piece: the piece's m0, m1 and column bytes leave
+        // as ONE store each (a scalar store per element meets 4-way bank conflicts on the 48-byte / 16-byte lane strides)
+        constexpr int PE = TW_CO_PE < PL::E16 ? TW_CO_PE : PL::E16;
 #pragma unroll 1
-        for (int j = 0; j < VEC; ++j) {
-            T uu[TW_DC];
+        for (int jp = 0; jp < VEC; jp += PE) {
+            T m0p[PE], m1p[PE]; unsigned ckp = 0u;
 #pragma unroll
-            for (int d = 0; d < TW_DC; ++d) {
-                uu[d] = INF;
-                if (DC || d < dcn) {
-                    const unsigned bb = ((unsigned)(tiv[d] >> (8 * j)) & 255u) << G::SH;
-                    uu[d] = vmx[d] - lds_addr(S::xor_gather ? (bb ^ key[d]) : (slab32 + d * VB + (bb ^ key[d])), T());
+            for (int jj = 0; jj < PE; ++jj) {
+                const int j = jp + jj;
+                T uu[TW_DC];
+#pragma unroll
+                for (int d = 0; d < TW_DC; ++d) {
+                    uu[d] = INF;
+                    if (DC || d < dcn) {
+                        const unsigned bb = ((unsigned)(tiv[d] >> (8 * j)) & 255u) << G::SH;
+                        uu[d] = vmx[d] - lds_addr(S::xor_gather ? (bb ^ key[d]) : (slab32 + d * VB + (bb ^ key[d])), T());
+                    }
                 }
+                const T a = uu[0], b = uu[1], c = uu[2], dd = uu[3];
+                const T m0 = fmin(min3(a, b, c), dd);
+                const int k0 = (a == m0) ? 0 : (b == m0) ? 1 : (c == m0) ? 2 : 3;               // stable: the lower column wins ties
+                const T a1 = k0 == 0 ? INF : a, b1 = k0 == 1 ? INF : b, c1 = k0 == 2 ? INF : c, d1 = k0 == 3 ? INF : dd;
+                const T m1 = fmin(min3(a1, b1, c1), d1);
+                int k1 = (k0 != 3) ? 3 : 2;                         // lowest column other than k0 that attains m1 (row degree >= 2)
+                if (c1 == m1) k1 = 2;
+                if (b1 == m1) k1 = 1;
+                if (a1 == m1) k1 = 0;
+                m0p[jj] = (x0 + j == 0) ? INF : m0;                 // the search never takes eta = 0
+                m1p[jj] = m1;
+                ckp |= (unsigned)(k0 | (k1 << 4)) << (8 * jj);
+                cls |= (unsigned)k0 << (2 * j);
             }
-            const T a = uu[0], b = uu[1], c = uu[2], dd = uu[3];
-            const T m0 = fmin(min3(a, b, c), dd);
-            const int k0 = (a == m0) ? 0 : (b == m0) ? 1 : (c == m0) ? 2 : 3;                   // stable: the lower column wins ties
-            const T a1 = k0 == 0 ? INF : a, b1 = k0 == 1 ? INF : b, c1 = k0 == 2 ? INF : c, d1 = k0 == 3 ? INF : dd;
-            const T m1 = fmin(min3(a1, b1, c1), d1);
-            int k1 = (k0 != 3) ? 3 : 2;                             // lowest column other than k0 that attains m1 (row degree >= 2)
-            if (c1 == m1) k1 = 2;
-            if (b1 == m1) k1 = 1;
-            if (a1 == m1) k1 = 0;
-            *reinterpret_cast<T *>(mine + j * (int)sizeof(T)) = (x0 + j == 0) ? INF : m0;       // the search never takes eta = 0
-            sM1[PL::index_rt(lane, j)] = m1;
-            c01[x0 + j] = (uint8_t)(k0 | (k1 << 4));
-            cls |= (unsigned)k0 << (2 * j);
+            st_run<T, PE>(reinterpret_cast<T *>(mine + jp * (int)sizeof(T)), m0p);
+            st_run<T, PE>(sM1 + PL::index_rt(lane, jp), m1p);
+            st_bytes<PE>(c01 + x0 + jp, ckp);
         }
         *reinterpret_cast<unsigned *>(mine + S::blk_cls) = cls;
     }
