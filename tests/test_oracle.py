@@ -130,3 +130,24 @@ def test_oracle_against_live_reference(tmp_path):
         lpost = np.frombuffer(raw, np.float64, N * (q - 1), off).reshape(N, q - 1); off += 8 * N * (q - 1)
         r, it, out, post = oc.decode(4, max_iter, 2, 2, 1.0, 0.5, lch)
         assert (r, it) == (ret, iters) and np.array_equal(out, dec) and np.array_equal(post, lpost)
+
+
+def test_ems_fresh_sum_switch_is_an_analysis_aid_only():
+    """orc_set_ems_fresh_sums (off by default) forms every EMS configuration sum afresh instead of in the reference's running
+    add / subtract sum: on the golden EMS frames it changes posteriors by rounding residue only (same decisions, same iteration
+    counts), and switching it off again restores the reference's arithmetic bit for bit."""
+    name = "cfg2_ems_gf64"
+    z, meta = load_golden(name)
+    oc = po.OracleCode(get_code_dict(meta["code"]))
+    lch = golden_lch(z, meta, 4)
+    base = [oc.decode(meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], l) for l in lch]
+    po.set_ems_fresh_sums(1)
+    try:
+        fresh = [oc.decode(meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], l) for l in lch]
+    finally:
+        po.set_ems_fresh_sums(0)
+    again = [oc.decode(meta["method"], meta["max_iter"], meta["p0"], meta["p1"], meta["factor"], meta["offset"], l) for l in lch]
+    for b, f, a in zip(base, fresh, again):
+        assert (b[0], b[1]) == (f[0], f[1]) and np.array_equal(b[2], f[2])
+        assert np.abs(b[3] - f[3]).max() < 1e-9
+        assert np.array_equal(b[3], a[3])
