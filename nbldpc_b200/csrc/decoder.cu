@@ -658,8 +658,40 @@ template <typename T, int Q> static int launch_iterate_tq(nbl_decoder *d, const 
         default: return launch_iterate_tqm<T, Q, NBL_METHOD_QSPA>(d, P);
     }
 }
+// The decision-only form of k_posterior for q >= 32 (the last iteration of every decode): ONE WARP per (frame, variable), VEC = Q / 32
+// consecutive elements per lane with 128-bit loads, the same sums in the same order, the decision by warp_decide (tems_warp.cuh) --
+// no shared memory, no block barrier; the group form reaches 45 % of the copy bandwidth, this one is bound by it.
+template <typename T, int Q>
+__global__ void __launch_bounds__(256) k_posterior_warp(DevGraph g, int B, int first, int early_stop, const T *__restrict__ lch,
+                                                      const T *__restrict__ c2v_in, const uint8_t *__restrict__ done, uint8_t *dec) {
+    constexpr int VEC = Q / 32;
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (long long)B * g.N) return;
+    const int f = (int)(w / g.N), col = (int)(w % g.N);
+    if (early_stop && done[f]) return;
+    T post[VEC];
+    nbl::ld_vec<T, VEC>(lch + ((size_t)f * g.N + col) * Q + VEC * lane, post);
+    if (!first)
+        for (int s = g.var_ptr[col]; s < g.var_ptr[col + 1]; ++s) {
+            T m[VEC];
+            nbl::ld_vec<T, VEC>(c2v_in + ((size_t)f * g.E + g.var_edge[s]) * Q + VEC * lane, m);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) post[i] = post[i] + m[i];
+        }
+    const int dsym = nbl::warp_decide<T, VEC>(post, lane);
+    if (lane == 0) dec[(size_t)f * g.N + col] = (uint8_t)dsym;
+}
+
 template <typename T, int Q> static int launch_posterior_tq(nbl_decoder *d, int B, int first, const T *c2v_in, double *post_out, const uint8_t *sel) {
     const long long groups = (long long)B * d->g.N;
+    if constexpr (Q >= 32) {
+        if (!post_out && d->cfg.kernel != NBL_KERNEL_GROUP) {
+            k_posterior_warp<T, Q><<<(unsigned)((groups + 7) / 8), 256, 0, d->stream>>>(d->g, B, first, d->cfg.early_stop, (const T *)d->d_lch, c2v_in, d->d_done, d->d_dec);
+            CK(cudaGetLastError());
+            return NBL_OK;
+        }
+    }
     const unsigned grid = (unsigned)((groups + Grp<Q>::G - 1) / Grp<Q>::G);
     k_posterior<T, Q><<<grid, Grp<Q>::THREADS, 0, d->stream>>>(d->g, B, first, d->cfg.early_stop, (const T *)d->d_lch, c2v_in, d->d_done,
                                                                d->d_dec, post_out, sel);
@@ -977,6 +1009,40 @@ static int setup_punct(nbl_decoder *d, int modulation, const int *punct_sym, int
     return NBL_OK;
 }
 
+// BPSK demapper for q >= 32: ONE WARP per (frame, symbol).  The LLR of x is the sum of its set bits' terms in ascending bit order
+// (Comm.cpp:340-407); lane l forms the partial sum over bits 0..4 of x = 32 h + l once and extends it by the set bits of h for each
+// of its q / 32 outputs -- the same additions in the same order as one thread per output (bit-identical LLRs), 5 + 3 * 2^(p-5) / 2
+// of them per lane instead of p * 2^(p-5), and every store a full 128-byte line.
+template <typename T>
+__global__ void __launch_bounds__(256) k_demap_bpsk_warp(int B, int N, int q, int p, int ylen, const double *__restrict__ y, double sigma,
+                                                       const int *__restrict__ ysym, T *lch /*[B][N][q] or null*/, double *out /*[B][N][q-1] or null*/) {
+    const int lane = threadIdx.x & 31;
+    const long long fs = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (fs >= (long long)B * N) return;
+    const int s = (int)(fs % N), f = (int)(fs / N);
+    const int off = ysym[s];
+    double v = 0;                                                   // lane b < p: the term of bit b (punctured symbols: all-zero LLRs)
+    if (off >= 0 && lane < p) v = -2 * y[(size_t)f * ylen + off + lane] / (sigma * sigma);
+    double lo = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const double vb = __shfl_sync(0xffffffffu, v, b);
+        if (lane & (1 << b)) lo += vb;
+    }
+    double hb[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) hb[b] = __shfl_sync(0xffffffffu, v, 5 + b);     // p <= 8
+    const int nh = q >> 5;
+    for (int h = 0; h < nh; ++h) {
+        double a = lo;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) if (h & (1 << b)) a += hb[b];
+        const int x = 32 * h + lane;
+        if (lch) lch[(size_t)fs * q + x] = (T)a;
+        if (out && x != 0) out[(size_t)fs * (q - 1) + x - 1] = a;
+    }
+}
+
 // the demapper kernels on frames f0 .. f0 + nf - 1 of samples already on the device (ysrc = first frame of the batch)
 static int launch_demap(nbl_decoder *d, int modulation, const double *ysrc, int f0, int nf, int ylen, double sigma, bool to_lch, double *out_dev) {
     const int N = d->g.N, q = d->g.q;
@@ -990,6 +1056,11 @@ static int launch_demap(nbl_decoder *d, int modulation, const double *ysrc, int 
         const int threads = 256, syms = 8 * (threads / q);          // q <= 256
         const unsigned bgrid = (unsigned)(((size_t)nf * N + syms - 1) / syms);
         const size_t sh = (size_t)syms * d->g.p * sizeof(double);
+        if (q >= 32 && d->g.p <= 8) {
+            const unsigned wgrid = (unsigned)(((size_t)nf * N + 7) / 8);
+            if (f64) k_demap_bpsk_warp<double><<<wgrid, 256, 0, d->stream>>>(nf, N, q, d->g.p, ylen, ys, sigma, d->d_ysym, to_lch ? (double *)d->d_lch + loff : nullptr, od);
+            else k_demap_bpsk_warp<float><<<wgrid, 256, 0, d->stream>>>(nf, N, q, d->g.p, ylen, ys, sigma, d->d_ysym, to_lch ? (float *)d->d_lch + loff : nullptr, od);
+        } else
         if (f64) k_demap_bpsk<double><<<bgrid, threads, sh, d->stream>>>(nf, N, q, d->g.p, ylen, syms, ys, sigma, d->d_ysym, to_lch ? (double *)d->d_lch + loff : nullptr, od);
         else k_demap_bpsk<float><<<bgrid, threads, sh, d->stream>>>(nf, N, q, d->g.p, ylen, syms, ys, sigma, d->d_ysym, to_lch ? (float *)d->d_lch + loff : nullptr, od);
     } else {
