@@ -167,22 +167,25 @@ __global__ void k_syndrome(DevGraph g, int B, int early_stop, const uint8_t *__r
 // active[iter - 1] += frames that were still decoding when iteration `iter` ran (one atomic per CTA): the early-stop statistics
 __global__ void k_finalize(int B, int N, int iter, int max_iter, int *flag, uint8_t *done, int *iters, int *conv,
                            const uint8_t *__restrict__ dec, int *out_sym, uint8_t *newly, int *active) {
-    const int f = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    const int was_active = __syncthreads_count(f < B && lane == 0 && !done[f]);
+    // one THREAD per frame for the latch test (a warp per frame made 37 888 tiny CTAs per iteration of the GF(16) configuration);
+    // the frames of a warp that latch in this iteration -- each frame does so once per decode -- are then copied by the whole
+    // warp, one after the other, coalesced
+    const int f = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x), lane = threadIdx.x & 31;
+    const bool act = f < B && !done[f];
+    const int was_active = __syncthreads_count(act);
     if (threadIdx.x == 0 && was_active) atomicAdd(active + iter - 1, was_active);
-    if (f >= B) return;
     int l = 0;
-    if (lane == 0) {
-        if (!done[f]) {
-            const bool ok = flag[f] == 0;
-            flag[f] = 0;
-            if (ok || iter == max_iter) { done[f] = 1; conv[f] = ok ? 1 : 0; iters[f] = ok ? iter : max_iter; l = 1; }
-        }
-        newly[f] = (uint8_t)l;
+    if (act) {
+        const bool ok = flag[f] == 0;
+        flag[f] = 0;
+        if (ok || iter == max_iter) { done[f] = 1; conv[f] = ok ? 1 : 0; iters[f] = ok ? iter : max_iter; l = 1; }
     }
-    l = __shfl_sync(0xffffffffu, l, 0);
-    if (l)
-        for (int i = lane; i < N; i += 32) out_sym[(size_t)f * N + i] = dec[(size_t)f * N + i];
+    if (f < B) newly[f] = (uint8_t)l;
+    const int f0 = f - lane;                                        // first frame of my warp
+    for (unsigned m = __ballot_sync(0xffffffffu, l != 0); m; m &= m - 1u) {
+        const size_t base = (size_t)(f0 + __ffs((int)m) - 1) * N;
+        for (int i = lane; i < N; i += 32) out_sym[base + i] = dec[base + i];
+    }
 }
 
 // ---- soft demapper (CComm::Demodulate, Comm.cpp:340-407); fp64 in the reference's operation order -----
@@ -821,7 +824,7 @@ template <typename T> static int enqueue_decode(nbl_decoder *d, int B, double *p
             CK(cudaGetLastError());
             d->last_launches += 2;
         }
-        k_finalize<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, d->stream>>>(B, d->g.N, it, c.max_iter, d->d_flag, d->d_done, d->d_iters, d->d_conv, d->d_dec, d->d_out, d->d_newly, d->d_active);
+        k_finalize<<<(unsigned)((B + 255) / 256), 256, 0, d->stream>>>(B, d->g.N, it, c.max_iter, d->d_flag, d->d_done, d->d_iters, d->d_conv, d->d_dec, d->d_out, d->d_newly, d->d_active);
         CK(cudaGetLastError());
         d->last_launches += 1;
         if (post_dev) {
