@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Development probe: the one EMS case of tools/fuzz_parity.py that differs from the oracle (seed 51, case 75; DESIGN.md 2, "EMS and the
+same residue") through both kernels and both precisions -- they agree with each other, not with the reference's running sums."""
 import sys, os, json
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np
