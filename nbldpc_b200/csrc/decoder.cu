@@ -686,8 +686,39 @@ __global__ void __launch_bounds__(256) k_posterior_warp(DevGraph g, int B, int f
     if (lane == 0) dec[(size_t)f * g.N + col] = (uint8_t)dsym;
 }
 
+// The same over GF(16): four lanes per (frame, variable) with four elements each (the layout of qspa_half.cuh), eight variables per warp
+template <typename T>
+__global__ void __launch_bounds__(256) k_posterior_q16(DevGraph g, int B, int first, int early_stop, const T *__restrict__ lch,
+                                                     const T *__restrict__ c2v_in, const uint8_t *__restrict__ done, uint8_t *dec) {
+    const int l4 = threadIdx.x & 3;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = w < (long long)B * g.N;
+    const int f = live ? (int)(w / g.N) : 0, col = live ? (int)(w % g.N) : 0;
+    const bool act = live && !(early_stop && done[f]);
+    T post[4] = {T(0), T(0), T(0), T(0)};
+    if (act) {
+        nbl::qh_load4<T>(lch + ((size_t)f * g.N + col) * 16 + 4 * l4, post);
+        if (!first)
+            for (int s = g.var_ptr[col]; s < g.var_ptr[col + 1]; ++s) {
+                T m[4];
+                nbl::qh_load4<T>(c2v_in + ((size_t)f * g.E + g.var_edge[s]) * 16 + 4 * l4, m);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) post[i] = post[i] + m[i];
+            }
+    }
+    const int dsym = nbl::qh_decide<T>(post, 4 * l4);               // every lane takes part in the shuffles
+    if (act && l4 == 0) dec[(size_t)f * g.N + col] = (uint8_t)dsym;
+}
+
 template <typename T, int Q> static int launch_posterior_tq(nbl_decoder *d, int B, int first, const T *c2v_in, double *post_out, const uint8_t *sel) {
     const long long groups = (long long)B * d->g.N;
+    if constexpr (Q == 16) {
+        if (!post_out && d->cfg.kernel != NBL_KERNEL_GROUP) {
+            k_posterior_q16<T><<<(unsigned)((groups * 4 + 255) / 256), 256, 0, d->stream>>>(d->g, B, first, d->cfg.early_stop, (const T *)d->d_lch, c2v_in, d->d_done, d->d_dec);
+            CK(cudaGetLastError());
+            return NBL_OK;
+        }
+    }
     if constexpr (Q >= 32) {
         if (!post_out && d->cfg.kernel != NBL_KERNEL_GROUP) {
             k_posterior_warp<T, Q><<<(unsigned)((groups + 7) / 8), 256, 0, d->stream>>>(d->g, B, first, d->cfg.early_stop, (const T *)d->d_lch, c2v_in, d->d_done, d->d_dec);
